@@ -1,0 +1,145 @@
+/*
+ * b200_iop.h — C ABI of the B200-native libiop prover hot path.
+ *
+ * This is the drop-in boundary.  The reference (scipr-lab/libiop) has no FFI layer:
+ * callers invoke C++ templates on std::vector<FieldT>.  Each entry point below replaces one of
+ * those templates; the C++ adapter in libiop_b200/host/ keeps the reference's names and
+ * signatures and forwards here.  Reference citations are relative to /root/reference.
+ *
+ * Conventions
+ *   - field element = 3 x uint64 little-endian limbs = 24 bytes, for both
+ *       gf192       GF(2)[x]/(x^192+x^7+x^2+x+1)          depends/libff/.../binary/gf192.hpp:19-20,98-99
+ *       Fp (3 limb) Montgomery form, R = 2^192            depends/libff/.../prime_base/fp.hpp:42
+ *   - all sizes are in elements unless the name says bytes
+ *   - every call returns 0 or a negative b200_status; b200_last_error(ctx) holds the message
+ *   - a context is bound to one device and one stream; calls are stream-ordered and asynchronous,
+ *     results become visible to the host through download/gather (which synchronise)
+ *   - a context is NOT thread-safe (neither is the reference: SURVEY.md §8b "Threading")
+ *   - there is no CPU fallback: without a CUDA device b200_ctx_create fails
+ */
+#ifndef B200_IOP_H
+#define B200_IOP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+typedef uint64_t b200_buf;   /* device array of 24-byte field elements (a device address) */
+typedef uint64_t b200_bytes; /* device byte array (digests, salts)          (a device address) */
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_INVALID = -1,   /* std::invalid_argument in the reference (e.g. fft.tcc:333,368) */
+    B200_ERR_LOGIC = -2,     /* std::logic_error in the reference (e.g. merkle_tree.tcc:98-108) */
+    B200_ERR_CUDA = -3,
+    B200_ERR_NOMEM = -4
+} b200_status;
+
+enum { B200_DOMAIN_AFFINE_SUBSPACE = 1, B200_DOMAIN_MULTIPLICATIVE_COSET = 2 };
+enum { B200_FIELD_GF192 = 1, B200_FIELD_FP = 2 };
+
+/* Prime-field description: Fp_model<3, modulus> statics (fp.hpp:40-60; edwards_fields.cpp:24-46). */
+typedef struct {
+    uint64_t modulus[3];
+    uint64_t r2[3];        /* Rsquared */
+    uint64_t one_mont[3];  /* R mod p  */
+    uint64_t inv;          /* -modulus^-1 mod 2^64 */
+    uint32_t two_adicity;  /* s */
+    uint32_t num_bits;
+} b200_fp_params;
+
+/* field_subset<FieldT> (libiop/algebra/field_subset/field_subset.hpp:25-77) flattened.
+ *   kind 1: affine_subspace  — element idx = shift + sum_k bit_k(idx)*basis[k]      (subspace.tcc:54-71,161-170)
+ *   kind 2: multiplicative_coset — element idx = shift * generator^idx, Montgomery  (subgroup.tcc:280-304) */
+typedef struct {
+    int kind;
+    uint32_t dim;              /* log2(#elements) */
+    const uint64_t *basis;     /* kind 1: dim*3 limbs (host pointer) */
+    uint64_t shift[3];
+    uint64_t generator[3];     /* kind 2 */
+} b200_domain;
+
+/* ---- context / memory --------------------------------------------------------------------- */
+b200_ctx *b200_ctx_create(int device);
+void b200_ctx_destroy(b200_ctx *);
+const char *b200_last_error(b200_ctx *);
+int b200_sync(b200_ctx *);
+void *b200_stream(b200_ctx *);                       /* cudaStream_t the context launches on */
+int b200_device_info(b200_ctx *, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
+
+b200_buf b200_alloc(b200_ctx *, size_t n_elems);     /* 0 on failure */
+void b200_free(b200_ctx *, b200_buf);
+b200_bytes b200_alloc_bytes(b200_ctx *, size_t n_bytes);
+void b200_free_bytes(b200_ctx *, b200_bytes);
+void *b200_host_alloc(b200_ctx *, size_t n_bytes);   /* pinned host memory for upload/download */
+void b200_host_free(b200_ctx *, void *);
+
+int b200_upload(b200_ctx *, b200_buf dst, size_t dst_offset, const uint64_t *src, size_t n_elems);
+int b200_download(b200_ctx *, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems);
+int b200_upload_bytes(b200_ctx *, b200_bytes dst, const uint8_t *src, size_t n_bytes);
+int b200_download_bytes(b200_ctx *, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes);
+int b200_copy(b200_ctx *, b200_buf dst, size_t dst_offset, b200_buf src, size_t src_offset, size_t n_elems);
+int b200_fill_zero(b200_ctx *, b200_buf dst, size_t dst_offset, size_t n_elems);
+/* iop_protocol::get_oracle_evaluation_at_point (libiop/iop/iop.tcc:670-688): query answers */
+int b200_gather(b200_ctx *, uint64_t *dst, b200_buf src, const size_t *idx, size_t k);
+
+/* device timing on the context's stream (CUDA events) */
+int b200_timer_start(b200_ctx *);
+int b200_timer_stop(b200_ctx *, float *ms);          /* synchronises */
+
+/* ---- GF(2^192): additive FFT ---------------------------------------------------------------- */
+/* FFT_over_field_subset<gf192>(coeffs, L) -> additive_FFT      libiop/algebra/fft.tcc:39-124, 414-419
+ * coeffs: n_coeffs <= 2^L->dim monomial coefficients (zero-padded, fft.tcc:43-44); evals_out: 2^dim. */
+int b200_gf192_fft(b200_ctx *, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out);
+/* IFFT_over_field_subset<gf192>(evals, H) -> additive_IFFT     libiop/algebra/fft.tcc:126-204, 428-433 */
+int b200_gf192_ifft(b200_ctx *, const b200_domain *H, b200_buf evals, b200_buf coeffs_out);
+/* element-wise helpers (gf192::operator*=, inverse: gf192.cpp:72-184, 245-288) */
+int b200_gf192_mul(b200_ctx *, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int b200_gf192_inv(b200_ctx *, b200_buf out, b200_buf a, size_t n);
+
+/* ---- Fp: radix-2 NTT ------------------------------------------------------------------------ */
+/* FFT_over_field_subset<Fp>(coeffs, L) -> multiplicative_FFT_degree_aware   fft.tcc:236-317, 407-412 */
+int b200_fp_ntt(b200_ctx *, const b200_fp_params *, const b200_domain *L, b200_buf coeffs, size_t n_coeffs,
+                b200_buf evals_out);
+/* IFFT_over_field_subset<Fp>(evals, H) -> libfqfft iFFT / icosetFFT        fft.tcc:343-361 */
+int b200_fp_intt(b200_ctx *, const b200_fp_params *, const b200_domain *H, b200_buf evals, b200_buf coeffs_out);
+/* element-wise helpers (Fp_model::mul_reduce/+=/-=/invert: fp.tcc:25-194,323-532,670-722) */
+int b200_fp_mul(b200_ctx *, const b200_fp_params *, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int b200_fp_add(b200_ctx *, const b200_fp_params *, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int b200_fp_sub(b200_ctx *, const b200_fp_params *, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int b200_fp_inv(b200_ctx *, const b200_fp_params *, b200_buf out, b200_buf a, size_t n);
+
+/* ---- FRI commit-phase fold ------------------------------------------------------------------- */
+/* evaluate_next_f_i_over_entire_domain(f_i, L_i, 2^eta, x_i)   libiop/protocols/ldt/fri/fri_aux.tcc:6-249
+ * field = B200_FIELD_GF192 (L_i affine subspace) or B200_FIELD_FP (L_i multiplicative coset; fp != NULL).
+ * f_i: 2^dim elements; f_next_out: 2^(dim-eta). */
+int b200_fri_fold(b200_ctx *, int field, const b200_fp_params *fp, const b200_domain *L_i, uint32_t eta,
+                  const uint64_t x_i[3], b200_buf f_i, b200_buf f_next_out);
+
+/* ---- BCS Merkle tree ------------------------------------------------------------------------- */
+/* merkle_tree::construct_with_leaves_serialized_by_cosets + compute_inner_nodes
+ *                                                              libiop/bcs/merkle_tree.tcc:93-151, 201-229
+ * leaf i = BLAKE2b( for oracle k, for j < coset_size: oracle_k[pos(i,j)] ), pos per domain_kind
+ * (subspace.tcc:87-91 / subgroup.tcc:192-197); zk: H(H(leaf) || salt_i)  (blake2b.tcc:127-136).
+ * nodes_out: (2*leaves-1)*digest_len bytes in heap order, root first (merkle_tree.tcc:145,201-229). */
+int b200_merkle_build(b200_ctx *, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset_size,
+                      int domain_kind, const uint8_t *zk_salts_host /* NULL or leaves*salt_len */, size_t salt_len,
+                      size_t digest_len, b200_bytes nodes_out);
+int b200_merkle_root(b200_ctx *, b200_bytes nodes, uint8_t *root_out, size_t digest_len); /* get_root(), merkle_tree.tcc:232-240 */
+/* node fetch for get_set_membership_proof (merkle_tree.tcc:243-336) */
+int b200_merkle_nodes(b200_ctx *, b200_bytes nodes, const size_t *node_idx, size_t k, size_t digest_len, uint8_t *out);
+/* blake2b_two_to_one_hash / blake2b_field_element_hash over a batch (blake2b.cpp:28-48, blake2b.tcc:141-160):
+ * out[i] = BLAKE2b-digest_len( in[i*msg_len .. (i+1)*msg_len) ) */
+int b200_blake2b_batch(b200_ctx *, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
+
+/* library identification */
+const char *b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_IOP_H */

@@ -1,0 +1,329 @@
+"""ctypes binding of include/b200_iop.h.  Field elements are numpy uint64 arrays of shape (n, 3)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libb200iop.so")
+
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+_szp = C.POINTER(C.c_size_t)
+
+DOMAIN_AFFINE, DOMAIN_MULT = 1, 2
+FIELD_GF192, FIELD_FP = 1, 2
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class FpParams(C.Structure):
+    """b200_fp_params (Fp_model statics: fp.hpp:40-60)."""
+    _fields_ = [("modulus", C.c_uint64 * 3), ("r2", C.c_uint64 * 3), ("one_mont", C.c_uint64 * 3),
+                ("inv", C.c_uint64), ("two_adicity", C.c_uint32), ("num_bits", C.c_uint32)]
+
+    @staticmethod
+    def edwards_fr():
+        """edwards_Fr (depends/libff/libff/algebra/curves/edwards/edwards_fields.cpp:24-46)."""
+        p = 1552511030102430251236801561344621993261920897571225601
+        R = 1 << 192
+        P = FpParams()
+        for i in range(3):
+            P.modulus[i] = (p >> (64 * i)) & (2**64 - 1)
+            P.r2[i] = ((R * R % p) >> (64 * i)) & (2**64 - 1)
+            P.one_mont[i] = ((R % p) >> (64 * i)) & (2**64 - 1)
+        P.inv = (-pow(p, -1, 2**64)) % 2**64
+        P.two_adicity = 31
+        P.num_bits = 181
+        return P
+
+    def p(self):
+        return sum(int(self.modulus[i]) << (64 * i) for i in range(3))
+
+    def to_mont(self, v):
+        v = (v << 192) % self.p()
+        return np.array([(v >> (64 * i)) & (2**64 - 1) for i in range(3)], dtype=np.uint64)
+
+    def from_mont(self, limbs):
+        v = sum(int(limbs[i]) << (64 * i) for i in range(3))
+        return v * pow(1 << 192, -1, self.p()) % self.p()
+
+    def subgroup_generator(self, logn, generator=19):
+        """multiplicative_generator^((p-1)/2^logn) in Montgomery form (subgroup.tcc:56-59)."""
+        return self.to_mont(pow(generator, (self.p() - 1) >> logn, self.p()))
+
+
+class _CDomain(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dim", C.c_uint32), ("basis", _u64p),
+                ("shift", C.c_uint64 * 3), ("generator", C.c_uint64 * 3)]
+
+
+class Domain:
+    """field_subset<FieldT> flattened (field_subset.hpp:25-77)."""
+
+    def __init__(self, kind, dim, basis=None, shift=None, generator=None):
+        self.kind, self.dim = kind, dim
+        self.basis = None if basis is None else np.ascontiguousarray(basis, dtype=np.uint64).reshape(-1, 3)
+        self.shift = np.zeros(3, dtype=np.uint64) if shift is None else np.ascontiguousarray(shift, dtype=np.uint64)
+        self.generator = np.zeros(3, dtype=np.uint64) if generator is None else np.ascontiguousarray(generator, dtype=np.uint64)
+        self.c = _CDomain()
+        self.c.kind, self.c.dim = kind, dim
+        if self.basis is not None:
+            assert len(self.basis) >= dim
+            self.c.basis = self.basis.ctypes.data_as(_u64p)
+        for i in range(3):
+            self.c.shift[i] = int(self.shift[i])
+            self.c.generator[i] = int(self.generator[i])
+
+    @staticmethod
+    def affine(basis, shift):
+        basis = np.ascontiguousarray(basis, dtype=np.uint64).reshape(-1, 3)
+        return Domain(DOMAIN_AFFINE, len(basis), basis=basis, shift=shift)
+
+    @staticmethod
+    def standard(dim, shift_int=None):
+        """affine_subspace::shifted_standard_basis (subspace.tcc:94-108,220-224): basis x^i, shift x^dim."""
+        b = np.zeros((dim, 3), dtype=np.uint64)
+        for i in range(dim):
+            b[i, i // 64] = np.uint64(1) << np.uint64(i % 64)
+        s = np.zeros(3, dtype=np.uint64)
+        sv = (1 << dim) if shift_int is None else shift_int
+        for i in range(3):
+            s[i] = (sv >> (64 * i)) & (2**64 - 1)
+        return Domain(DOMAIN_AFFINE, dim, basis=b, shift=s)
+
+    @staticmethod
+    def coset(fp, logn, shift):
+        return Domain(DOMAIN_MULT, logn, shift=shift, generator=fp.subgroup_generator(logn))
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.b200_ctx_create.restype = C.c_void_p
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_version.restype = C.c_char_p
+    lib.b200_alloc.restype = C.c_uint64
+    lib.b200_alloc_bytes.restype = C.c_uint64
+    lib.b200_host_alloc.restype = C.c_void_p
+    lib.b200_stream.restype = C.c_void_p
+    return lib
+
+
+class B200:
+    """One context = one device + one stream (b200_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = self.lib.b200_ctx_create(C.c_int(device))
+        if not self.ctx:
+            raise B200Error("b200_ctx_create failed: no CUDA device visible (the hot path has no CPU fallback)")
+        self.ctx = C.c_void_p(self.ctx)
+        self.launches = 0
+
+    def close(self):
+        if self.ctx:
+            self.lib.b200_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise B200Error(f"b200 error {rc}: {self.lib.b200_last_error(self.ctx).decode()}")
+
+    # ---- memory ----
+    def alloc(self, n):
+        b = self.lib.b200_alloc(self.ctx, C.c_size_t(n))
+        if not b:
+            raise B200Error(self.lib.b200_last_error(self.ctx).decode())
+        return b
+
+    def alloc_bytes(self, n):
+        b = self.lib.b200_alloc_bytes(self.ctx, C.c_size_t(n))
+        if not b:
+            raise B200Error(self.lib.b200_last_error(self.ctx).decode())
+        return b
+
+    def free(self, b):
+        self.lib.b200_free(self.ctx, C.c_uint64(b))
+
+    def upload(self, arr, buf=None, offset=0):
+        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 3)
+        if buf is None:
+            buf = self.alloc(max(len(arr), 1))
+        self._chk(self.lib.b200_upload(self.ctx, C.c_uint64(buf), C.c_size_t(offset), arr.ctypes.data_as(_u64p), C.c_size_t(len(arr))))
+        self.sync()  # the source array may be garbage-collected
+        return buf
+
+    def download(self, buf, n, offset=0):
+        out = np.zeros((n, 3), dtype=np.uint64)
+        self._chk(self.lib.b200_download(self.ctx, out.ctypes.data_as(_u64p), C.c_uint64(buf), C.c_size_t(offset), C.c_size_t(n)))
+        return out
+
+    def download_bytes(self, buf, n, offset=0):
+        out = np.zeros(n, dtype=np.uint8)
+        self._chk(self.lib.b200_download_bytes(self.ctx, out.ctypes.data_as(_u8p), C.c_uint64(buf), C.c_size_t(offset), C.c_size_t(n)))
+        return out.tobytes()
+
+    def upload_bytes(self, data, buf=None):
+        data = np.frombuffer(bytes(data), dtype=np.uint8)
+        if buf is None:
+            buf = self.alloc_bytes(max(len(data), 8))
+        self._chk(self.lib.b200_upload_bytes(self.ctx, C.c_uint64(buf), data.ctypes.data_as(_u8p), C.c_size_t(len(data))))
+        self.sync()
+        return buf
+
+    def gather(self, buf, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.zeros((len(idx), 3), dtype=np.uint64)
+        self._chk(self.lib.b200_gather(self.ctx, out.ctypes.data_as(_u64p), C.c_uint64(buf), idx.ctypes.data_as(_szp), C.c_size_t(len(idx))))
+        return out
+
+    def sync(self):
+        self._chk(self.lib.b200_sync(self.ctx))
+
+    def timer_start(self):
+        self._chk(self.lib.b200_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._chk(self.lib.b200_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    # ---- device-buffer level entry points ----
+    def gf192_fft_dev(self, dom, coeffs, n_coeffs, out):
+        self._chk(self.lib.b200_gf192_fft(self.ctx, C.byref(dom.c), C.c_uint64(coeffs), C.c_size_t(n_coeffs), C.c_uint64(out)))
+
+    def gf192_ifft_dev(self, dom, evals, out):
+        self._chk(self.lib.b200_gf192_ifft(self.ctx, C.byref(dom.c), C.c_uint64(evals), C.c_uint64(out)))
+
+    def fp_ntt_dev(self, fp, dom, coeffs, n_coeffs, out):
+        self._chk(self.lib.b200_fp_ntt(self.ctx, C.byref(fp), C.byref(dom.c), C.c_uint64(coeffs), C.c_size_t(n_coeffs), C.c_uint64(out)))
+
+    def fp_intt_dev(self, fp, dom, evals, out):
+        self._chk(self.lib.b200_fp_intt(self.ctx, C.byref(fp), C.byref(dom.c), C.c_uint64(evals), C.c_uint64(out)))
+
+    def fri_fold_dev(self, field, fp, dom, eta, x, f, out):
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        self._chk(self.lib.b200_fri_fold(self.ctx, C.c_int(field), C.byref(fp) if fp is not None else None, C.byref(dom.c),
+                                         C.c_uint32(eta), x.ctypes.data_as(_u64p), C.c_uint64(f), C.c_uint64(out)))
+
+    def merkle_build_dev(self, oracle_bufs, n_elems, coset, kind, nodes, salts=None, salt_len=32, digest_len=32):
+        arr = (C.c_uint64 * len(oracle_bufs))(*oracle_bufs)
+        sp = None
+        if salts is not None:
+            self._salts_keepalive = np.frombuffer(bytes(salts), dtype=np.uint8)
+            sp = self._salts_keepalive.ctypes.data_as(_u8p)
+        self._chk(self.lib.b200_merkle_build(self.ctx, arr, C.c_size_t(len(oracle_bufs)), C.c_size_t(n_elems), C.c_size_t(coset),
+                                             C.c_int(kind), sp, C.c_size_t(salt_len), C.c_size_t(digest_len), C.c_uint64(nodes)))
+
+    # ---- host-buffer convenience (upload, run, download): what the C++ adapter does ----
+    def gf192_fft(self, dom, coeffs):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+        n = 1 << dom.dim
+        a = self.upload(coeffs); o = self.alloc(n)
+        try:
+            self.gf192_fft_dev(dom, a, len(coeffs), o)
+            return self.download(o, n)
+        finally:
+            self.free(a); self.free(o)
+
+    def gf192_ifft(self, dom, evals):
+        evals = np.ascontiguousarray(evals, dtype=np.uint64).reshape(-1, 3)
+        n = 1 << dom.dim
+        assert len(evals) == n
+        a = self.upload(evals); o = self.alloc(n)
+        try:
+            self.gf192_ifft_dev(dom, a, o)
+            return self.download(o, n)
+        finally:
+            self.free(a); self.free(o)
+
+    def _binop(self, fn, a, b, fp=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 3)
+        da = self.upload(a); o = self.alloc(len(a)); db = None
+        try:
+            args = [self.ctx] + ([C.byref(fp)] if fp is not None else []) + [C.c_uint64(o), C.c_uint64(da)]
+            if b is not None:
+                db = self.upload(np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 3))
+                args.append(C.c_uint64(db))
+            args.append(C.c_size_t(len(a)))
+            self._chk(fn(*args))
+            return self.download(o, len(a))
+        finally:
+            self.free(da); self.free(o)
+            if db:
+                self.free(db)
+
+    def gf192_mul(self, a, b):
+        return self._binop(self.lib.b200_gf192_mul, a, b)
+
+    def gf192_inv(self, a):
+        return self._binop(self.lib.b200_gf192_inv, a, None)
+
+    def fp_mul(self, fp, a, b):
+        return self._binop(self.lib.b200_fp_mul, a, b, fp)
+
+    def fp_add(self, fp, a, b):
+        return self._binop(self.lib.b200_fp_add, a, b, fp)
+
+    def fp_sub(self, fp, a, b):
+        return self._binop(self.lib.b200_fp_sub, a, b, fp)
+
+    def fp_inv(self, fp, a):
+        return self._binop(self.lib.b200_fp_inv, a, None, fp)
+
+    def fp_ntt(self, fp, dom, coeffs):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+        n = 1 << dom.dim
+        a = self.upload(coeffs); o = self.alloc(n)
+        try:
+            self.fp_ntt_dev(fp, dom, a, len(coeffs), o)
+            return self.download(o, n)
+        finally:
+            self.free(a); self.free(o)
+
+    def fp_intt(self, fp, dom, evals):
+        evals = np.ascontiguousarray(evals, dtype=np.uint64).reshape(-1, 3)
+        n = 1 << dom.dim
+        a = self.upload(evals); o = self.alloc(n)
+        try:
+            self.fp_intt_dev(fp, dom, a, o)
+            return self.download(o, n)
+        finally:
+            self.free(a); self.free(o)
+
+    def fri_fold(self, field, fp, dom, eta, x, f):
+        f = np.ascontiguousarray(f, dtype=np.uint64).reshape(-1, 3)
+        n_out = len(f) >> eta
+        a = self.upload(f); o = self.alloc(n_out)
+        try:
+            self.fri_fold_dev(field, fp, dom, eta, x, a, o)
+            return self.download(o, n_out)
+        finally:
+            self.free(a); self.free(o)
+
+    def merkle_build(self, oracles, coset, kind, salts=None, salt_len=32, digest_len=32):
+        oracles = [np.ascontiguousarray(o, dtype=np.uint64).reshape(-1, 3) for o in oracles]
+        n = len(oracles[0]); leaves = n // coset
+        bufs = [self.upload(o) for o in oracles]
+        nodes = self.alloc_bytes((2 * leaves - 1) * digest_len)
+        try:
+            self.merkle_build_dev(bufs, n, coset, kind, nodes, salts, salt_len, digest_len)
+            return self.download_bytes(nodes, (2 * leaves - 1) * digest_len)
+        finally:
+            for b in bufs:
+                self.free(b)
+            self.free(nodes)
+
+    def blake2b_batch(self, msgs, msg_len, digest_len=32):
+        n = len(msgs) // msg_len
+        i = self.upload_bytes(msgs); o = self.alloc_bytes(n * digest_len)
+        try:
+            self._chk(self.lib.b200_blake2b_batch(self.ctx, C.c_uint64(i), C.c_size_t(msg_len), C.c_size_t(n), C.c_size_t(digest_len), C.c_uint64(o)))
+            return self.download_bytes(o, n * digest_len)
+        finally:
+            self.free(i); self.free(o)

@@ -1,0 +1,556 @@
+/*
+ * additive_fft.cu — Gao–Mateer additive FFT / IFFT over GF(2^192) on affine subspaces, sm_100a.
+ *
+ * Replaces additive_FFT (libiop/algebra/fft.tcc:39-124) and additive_IFFT (fft.tcc:126-204) behind
+ * FFT_over_field_subset / IFFT_over_field_subset (fft.tcc:414-433).  Outputs are the evaluations of
+ * the unique polynomial on the points `shift + sum_k bit_k(idx) basis[k]` in index order
+ * (subspace.tcc:54-71,161-170), so they are bit-identical to the reference whatever the schedule.
+ *
+ * B200 design (not the reference's ~m^2/2 full-array sweeps):
+ *   - The array lives in HBM/L2; every kernel launch ("tile pass") stages a tile of 2^TB elements in
+ *     shared memory (SoA, 3 x u64 planes), runs as many consecutive algorithm steps as touch only
+ *     the index bits of that tile, and writes the tile back.  Steps are twist (TW), Taylor/radix
+ *     conversion at one stride (TAY) and butterfly stage (BF); a host-side scheduler packs them.
+ *   - The forward half (monomial -> "novel" basis: twists + Taylor expansions) depends only on the
+ *     basis, not on the shift.  An FFT of n_coeffs <= 2^d coefficients onto a 2^m-point domain is
+ *     therefore done as ONE forward half on 2^d points followed by 2^(m-d) independent butterfly
+ *     halves, one per coset of span(basis[0..d)) (contiguous output blocks), instead of the
+ *     reference's size-2^m transform of a zero-padded vector: 100 instead of 276 field multiplications
+ *     per input coefficient for the Aurora LDE shape (d = 20, m = 23).
+ *   - twist factors beta_j^e are cached per domain in HBM (the prover reuses its domains for every
+ *     oracle); butterfly twiddles `shift + subset-sum` are rebuilt per butterfly from 256-entry
+ *     subset-sum tables, so no per-shift twiddle array exists.
+ */
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.h"
+#include "gf192.cuh"
+
+namespace b200 {
+
+enum : uint32_t { OP_TW = 1, OP_TAY = 2, OP_BF = 3 };
+#define B200_MAX_OPS 160
+#define B200_SMEM_PAD 4 /* u64 words of padding between planes */
+#define B200_SUM_CHUNKS 4 /* 8-bit chunks of the butterfly index: stages up to 2^32 */
+
+struct PassParams {
+    const gf192 *src;
+    gf192 *dst;
+    const gf192 *tw;    /* twist tables (forward or inverse) */
+    const gf192 *sums;  /* [d][B200_SUM_CHUNKS][256] subset sums of the recursed bases */
+    const gf192 *taus;  /* [(1 + n_extra)][d] recursed shifts: row 0 for the domain shift, 1+k for basis[d+k] */
+    uint32_t d, lo, hi, c, ctop;
+    uint32_t bitrev;    /* load src at bitrev_d(i) (out-of-place first butterfly pass) */
+    uint32_t n_extra;
+    uint32_t src_coset_stride_log; /* src advances by coset << this (use 32 for "shared source") */
+    uint32_t n_ops;
+    uint32_t ops[B200_MAX_OPS];
+};
+
+struct AdditivePlan {
+    uint32_t d = 0;
+    std::vector<gf192> basis, beta, betainv;
+    std::vector<std::vector<gf192>> gamma; /* gamma[j][b], b < d-1-j : recursed_betas of fft.tcc:85-92 */
+    gf192 *tw = nullptr, *itw = nullptr, *sums = nullptr;
+    ~AdditivePlan() { cudaFree(tw); cudaFree(itw); cudaFree(sums); }
+};
+
+__host__ __device__ __forceinline__ size_t tw_offset(uint32_t d, uint32_t j)
+{
+    return ((size_t)2 << d) - ((size_t)2 << (d - j));
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* shared-memory tile access (SoA: three planes of u64)                                           */
+struct Tile {
+    uint64_t *p0, *p1, *p2;
+    __device__ __forceinline__ gf192 ld(uint32_t L) const
+    {
+        const uint64_t a = p0[L], b = p1[L], c = p2[L];
+        gf192 r;
+        r.w[0] = (uint32_t)a; r.w[1] = (uint32_t)(a >> 32);
+        r.w[2] = (uint32_t)b; r.w[3] = (uint32_t)(b >> 32);
+        r.w[4] = (uint32_t)c; r.w[5] = (uint32_t)(c >> 32);
+        return r;
+    }
+    __device__ __forceinline__ void st(uint32_t L, const gf192 &x) const
+    {
+        p0[L] = (uint64_t)x.w[0] | ((uint64_t)x.w[1] << 32);
+        p1[L] = (uint64_t)x.w[2] | ((uint64_t)x.w[3] << 32);
+        p2[L] = (uint64_t)x.w[4] | ((uint64_t)x.w[5] << 32);
+    }
+    __device__ __forceinline__ void xor_into(uint32_t Ldst, uint32_t Lsrc) const
+    {
+        p0[Ldst] ^= p0[Lsrc]; p1[Ldst] ^= p1[Lsrc]; p2[Ldst] ^= p2[Lsrc];
+    }
+};
+
+__device__ __forceinline__ gf192 ldg_elem(const gf192 *p)
+{
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(p);
+    const uint64_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    gf192 r;
+    r.w[0] = (uint32_t)a; r.w[1] = (uint32_t)(a >> 32);
+    r.w[2] = (uint32_t)b; r.w[3] = (uint32_t)(b >> 32);
+    r.w[4] = (uint32_t)c; r.w[5] = (uint32_t)(c >> 32);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t insert_zero(uint32_t k, uint32_t pos)
+{
+    const uint32_t low = k & ((1u << pos) - 1u);
+    return ((k >> pos) << (pos + 1)) | low;
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256) additive_tile_pass(const PassParams P)
+{
+    extern __shared__ uint64_t smem[];
+    __shared__ gf192 tau_s[32];
+
+    const uint32_t mainb = P.hi - P.lo;
+    const uint32_t tb = mainb + P.c + P.ctop;
+    const uint32_t T = 1u << tb;
+    Tile t;
+    t.p0 = smem; t.p1 = smem + T + B200_SMEM_PAD; t.p2 = smem + 2 * (T + B200_SMEM_PAD);
+
+    const uint32_t coset = blockIdx.y;
+    const uint32_t midbits = P.lo - P.c;
+    const uint32_t mid = blockIdx.x & ((1u << midbits) - 1u);
+    const uint32_t top = blockIdx.x >> midbits;
+    const uint32_t d = P.d;
+
+    /* recursed shift of this coset for every depth: F2-linear in the shift, so
+       tau(shift + sum_k q_k basis[d+k]) = tau(shift) + sum_k q_k tau(basis[d+k]) */
+    if (threadIdx.x < d) {
+        gf192 v = ldg_elem(P.taus + threadIdx.x);
+        for (uint32_t k = 0; k < P.n_extra; ++k)
+            if ((coset >> k) & 1u) gf_addto(v, ldg_elem(P.taus + (size_t)(1 + k) * d + threadIdx.x));
+        tau_s[threadIdx.x] = v;
+    }
+
+    const gf192 *src = P.src + (P.src_coset_stride_log < 32 ? ((size_t)coset << P.src_coset_stride_log) : 0);
+    gf192 *dst = P.dst + ((size_t)coset << d);
+
+    auto global_index = [&](uint32_t L) -> uint32_t {
+        const uint32_t w = L & ((1u << P.c) - 1u);
+        const uint32_t u = (L >> P.c) & ((1u << mainb) - 1u);
+        const uint32_t tbv = L >> (P.c + mainb);
+        return w | (mid << P.c) | (u << P.lo) | (top << P.hi) | (P.ctop ? (tbv << (d - P.ctop)) : 0u);
+    };
+
+    for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
+        const uint32_t i = global_index(L);
+        const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
+        t.st(L, ldg_elem(src + a));
+    }
+
+    for (uint32_t o = 0; o < P.n_ops; ++o) {
+        __syncthreads();
+        const uint32_t kind = P.ops[o] >> 8, bit = P.ops[o] & 0xffu;
+        if (kind == OP_TW) {
+            /* twist at depth j = bit: S[i] *= beta_j^(i >> j)     (fft.tcc:61-70 / 190-200) */
+            const gf192 *tab = P.tw + tw_offset(d, bit);
+            for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
+                const uint32_t e = global_index(L) >> bit;
+                if (e != 0) t.st(L, gf_mul(t.ld(L), ldg_elem(tab + e)));
+            }
+        } else if (kind == OP_TAY) {
+            /* radix conversion at linear stride 2^bit: [A B C D] -> [A, B+C+D, C+D, D] (fft.tcc:72-83),
+               inverse [A, B+C, C+D, D] (fft.tcc:175-188) */
+            const uint32_t pos = bit - P.lo + P.c;
+            for (uint32_t k = threadIdx.x; k < (T >> 2); k += blockDim.x) {
+                const uint32_t low = k & ((1u << pos) - 1u);
+                const uint32_t base = ((k >> pos) << (pos + 2)) | low;
+                const uint32_t B = base | (1u << pos), C = base | (2u << pos), D = base | (3u << pos);
+                if (!INV) { t.xor_into(C, D); t.xor_into(B, C); }
+                else      { t.xor_into(B, C); t.xor_into(C, D); }
+            }
+        } else { /* OP_BF: butterfly stage jj = bit, twiddle = tau + subset sum over index bits < jj */
+            const uint32_t jj = bit, pos = jj - P.lo + P.c;
+            const uint32_t depth = d - 1 - jj;
+            const gf192 tau = tau_s[depth];
+            const gf192 *stab = P.sums + (size_t)jj * B200_SUM_CHUNKS * 256;
+            for (uint32_t k = threadIdx.x; k < (T >> 1); k += blockDim.x) {
+                const uint32_t L0 = insert_zero(k, pos), L1 = L0 | (1u << pos);
+                const uint32_t tix = global_index(L0) & ((1u << jj) - 1u);
+                gf192 tw = tau;
+                if (jj > 0) gf_addto(tw, ldg_elem(stab + (tix & 255u)));
+                if (jj > 8) gf_addto(tw, ldg_elem(stab + 256 + ((tix >> 8) & 255u)));
+                if (jj > 16) gf_addto(tw, ldg_elem(stab + 512 + ((tix >> 16) & 255u)));
+                if (jj > 24) gf_addto(tw, ldg_elem(stab + 768 + (tix >> 24)));
+                gf192 a = t.ld(L0), b = t.ld(L1);
+                if (!INV) {          /* fft.tcc:116-117 */
+                    gf_addto(a, gf_mul(b, tw));
+                    gf_addto(b, a);
+                } else {             /* fft.tcc:164-165 */
+                    gf_addto(b, a);
+                    gf_addto(a, gf_mul(b, tw));
+                }
+                t.st(L0, a); t.st(L1, b);
+            }
+        }
+    }
+    __syncthreads();
+
+    uint64_t *out = reinterpret_cast<uint64_t *>(dst);
+    for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
+        const uint32_t i = global_index(L);
+        const uint32_t a = (P.bitrev == 2) ? (__brev(i) >> (32 - d)) : i;
+        uint64_t *q = out + (size_t)a * 3;
+        q[0] = t.p0[L]; q[1] = t.p1[L]; q[2] = t.p2[L];
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* plan construction                                                                              */
+
+/* powers by doubling: tab[2^b + e] = tab[e] * base^(2^b) */
+__global__ void power_table_step(gf192 *tab, gf192 factor, uint32_t len)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < len) tab[len + e] = gf_mul(tab[e], factor);
+}
+
+static int build_power_tables(b200_ctx *c, gf192 **out, const std::vector<gf192> &base, uint32_t d)
+{
+    const size_t total = ((size_t)2 << d);
+    gf192 *tab = nullptr;
+    if (cudaMalloc(&tab, total * sizeof(gf192)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(c, B200_ERR_NOMEM, "cannot allocate %zu bytes of twist tables", total * sizeof(gf192));
+    }
+    for (uint32_t j = 0; j < d; ++j) {
+        gf192 *t = tab + tw_offset(d, j);
+        const gf192 one = gf_one();
+        B200_CUDA(c, cudaMemcpyAsync(t, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+        gf192 f = base[j];
+        for (uint32_t b = 0; b < d - j; ++b) {
+            const uint32_t len = 1u << b;
+            power_table_step<<<(len + 255) / 256, 256, 0, c->stream>>>(t, f, len);
+            f = gf_sqr(f);
+        }
+    }
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaStreamSynchronize(c->stream)); /* `one` is a stack temporary */
+    *out = tab;
+    return 0;
+}
+
+static int get_plan(b200_ctx *c, const gf192 *basis, uint32_t d, bool need_inverse,
+                    std::shared_ptr<AdditivePlan> *out)
+{
+    std::string key((const char *)basis, (size_t)d * sizeof(gf192));
+    key.push_back((char)d);
+    auto it = c->additive_plans.find(key);
+    std::shared_ptr<AdditivePlan> pl;
+    if (it != c->additive_plans.end()) pl = it->second;
+    else {
+        pl = std::make_shared<AdditivePlan>();
+        pl->d = d;
+        pl->basis.assign(basis, basis + d);
+        pl->beta.resize(d); pl->betainv.resize(d); pl->gamma.resize(d);
+        std::vector<gf192> betas2(pl->basis);
+        for (uint32_t j = 0; j < d; ++j) {                 /* fft.tcc:56-97 (basis recursion only) */
+            const gf192 beta = betas2[d - 1 - j];
+            if (gf_is_zero(beta)) return set_err(c, B200_ERR_INVALID, "subspace basis is linearly dependent");
+            const gf192 binv = gf_inv(beta);
+            pl->beta[j] = beta; pl->betainv[j] = binv;
+            pl->gamma[j].resize(d - 1 - j);
+            for (uint32_t i = 0; i + 1 + j < d; ++i) {
+                const gf192 nb = gf_mul(betas2[i], binv);
+                pl->gamma[j][i] = nb;
+                betas2[i] = gf_add(gf_sqr(nb), nb);
+            }
+        }
+        /* subset-sum tables per butterfly stage jj (depth d-1-jj), three 8-bit chunks */
+        std::vector<gf192> sums((size_t)(d ? d : 1) * B200_SUM_CHUNKS * 256, gf_zero());
+        for (uint32_t jj = 0; jj < d; ++jj) {
+            const std::vector<gf192> &g = pl->gamma[d - 1 - jj]; /* jj elements */
+            for (uint32_t q = 0; q < B200_SUM_CHUNKS; ++q)
+                for (uint32_t v = 1; v < 256; ++v) {
+                    const uint32_t lowbit = v & (~v + 1u);
+                    const uint32_t b = 8 * q + (31 - __builtin_clz(lowbit));
+                    gf192 s = sums[((size_t)jj * B200_SUM_CHUNKS + q) * 256 + (v ^ lowbit)];
+                    if (b < jj) gf_addto(s, g[b]);
+                    sums[((size_t)jj * B200_SUM_CHUNKS + q) * 256 + v] = s;
+                }
+        }
+        if (cudaMalloc(&pl->sums, sums.size() * sizeof(gf192)) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(c, B200_ERR_NOMEM, "cannot allocate subset-sum tables");
+        }
+        B200_CUDA(c, cudaMemcpy(pl->sums, sums.data(), sums.size() * sizeof(gf192), cudaMemcpyHostToDevice));
+        c->additive_plans[key] = pl;
+    }
+    if (!need_inverse && !pl->tw && d > 0) { int rc = build_power_tables(c, &pl->tw, pl->beta, d); if (rc) return rc; }
+    if (need_inverse && !pl->itw && d > 0) { int rc = build_power_tables(c, &pl->itw, pl->betainv, d); if (rc) return rc; }
+    *out = pl;
+    return 0;
+}
+
+void plans_clear_additive(b200_ctx *c) { c->additive_plans.clear(); }
+
+/* recursed shifts tau_j(s), j < d   (fft.tcc:94-96) */
+static void compute_taus(const AdditivePlan &pl, gf192 s, gf192 *out)
+{
+    for (uint32_t j = 0; j < pl.d; ++j) {
+        const gf192 ns = gf_mul(s, pl.betainv[j]);
+        out[j] = ns;
+        s = gf_add(gf_sqr(ns), ns);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* scheduler: pack consecutive steps into tile passes                                             */
+struct Pass { uint32_t lo, hi, c, ctop, bitrev; std::vector<uint32_t> ops; };
+
+static const uint32_t kTileBits = 12;  /* 4096 elements = 96 KiB of shared memory, 2 CTAs per SM */
+static const uint32_t kCoalesceBits = 4; /* strided tiles keep runs of 16 elements = 384 B */
+
+static void finish_pass(std::vector<Pass> &out, std::vector<uint32_t> &ops, int bmin, int bmax, uint32_t d)
+{
+    if (ops.empty()) return;
+    Pass p; p.ctop = 0; p.bitrev = 0; p.ops = ops;
+    const uint32_t tb = std::min(kTileBits, d);
+    if (bmin < 0) { bmin = 0; bmax = 0; } /* only element-wise steps */
+    uint32_t lo = (uint32_t)bmin, hi = (uint32_t)bmax + 1;
+    if (lo <= kCoalesceBits || hi <= tb) { p.c = 0; lo = 0; if (hi < tb) hi = tb; }
+    else {
+        p.c = kCoalesceBits;
+        while (hi - lo + p.c < tb) { if (lo > p.c) --lo; else if (hi < d) ++hi; else break; }
+        if (lo == p.c) { lo = 0; p.c = 0; }
+    }
+    p.lo = lo; p.hi = hi;
+    out.push_back(p);
+    ops.clear();
+}
+
+static bool fits(int bmin, int bmax, uint32_t d)
+{
+    const uint32_t tb = std::min(kTileBits, d);
+    const uint32_t lo = (uint32_t)bmin, hi = (uint32_t)bmax + 1;
+    if (hi <= tb) return true;                       /* contiguous tile [0, tb) */
+    if (lo <= kCoalesceBits) return false;
+    return hi - lo + kCoalesceBits <= tb;
+}
+
+/* steps: sequence of (kind, bit) with the index bits each needs */
+static std::vector<Pass> schedule(const std::vector<uint32_t> &steps, uint32_t d)
+{
+    std::vector<Pass> passes;
+    std::vector<uint32_t> cur;
+    int bmin = -1, bmax = -1;
+    for (uint32_t s : steps) {
+        const uint32_t kind = s >> 8, bit = s & 0xff;
+        int nmin = bmin, nmax = bmax;
+        if (kind == OP_TAY) { nmin = (bmin < 0) ? (int)bit : std::min(bmin, (int)bit); nmax = std::max(bmax, (int)bit + 1); }
+        else if (kind == OP_BF) { nmin = (bmin < 0) ? (int)bit : std::min(bmin, (int)bit); nmax = std::max(bmax, (int)bit); }
+        if ((nmin >= 0 && !fits(nmin, nmax, d)) || cur.size() >= B200_MAX_OPS) {
+            finish_pass(passes, cur, bmin, bmax, d);
+            bmin = bmax = -1;
+            if (kind == OP_TAY) { bmin = (int)bit; bmax = (int)bit + 1; }
+            else if (kind == OP_BF) { bmin = bmax = (int)bit; }
+        } else { bmin = nmin; bmax = nmax; }
+        cur.push_back(s);
+    }
+    finish_pass(passes, cur, bmin, bmax, d);
+    return passes;
+}
+
+template <bool INV>
+static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uint32_t n_cosets)
+{
+    P.lo = p.lo; P.hi = p.hi; P.c = p.c; P.ctop = p.ctop; P.bitrev = p.bitrev; P.d = d;
+    P.n_ops = (uint32_t)p.ops.size();
+    std::copy(p.ops.begin(), p.ops.end(), P.ops);
+    const uint32_t tb = (p.hi - p.lo) + p.c + p.ctop;
+    const size_t smem = 3 * (((size_t)1 << tb) + B200_SMEM_PAD) * sizeof(uint64_t);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[INV]) {
+        B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t))));
+        attr_set[INV] = true;
+    }
+    dim3 grid(1u << (d - tb), n_cosets);
+    additive_tile_pass<INV><<<grid, 256, smem, c->stream>>>(P);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+__global__ void fill_kernel(gf192 *dst, const gf192 *src_elem, size_t n)
+{
+    const gf192 v = src_elem ? *src_elem : gf_zero();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+static int upload_taus(b200_ctx *c, const AdditivePlan &pl, const b200_domain *L, uint32_t d, uint32_t m, gf192 **dev)
+{
+    const uint32_t rows = 1 + (m - d);
+    const size_t bytes = (size_t)rows * std::max(d, 1u) * sizeof(gf192);
+    gf192 *h = (gf192 *)staging_get(c, std::max(bytes, (size_t)4096));
+    gf192 *dv = (gf192 *)scratch_get(c, 1, std::max(bytes, (size_t)4096));
+    if (!h || !dv) return set_err(c, B200_ERR_NOMEM, "cannot allocate tau staging");
+    B200_CUDA(c, cudaStreamSynchronize(c->stream)); /* staging buffer may still be in flight */
+    gf192 s; memcpy(&s, L->shift, sizeof s);
+    compute_taus(pl, s, h);
+    const gf192 *basis = (const gf192 *)L->basis;
+    for (uint32_t k = 0; k < m - d; ++k) compute_taus(pl, basis[d + k], h + (size_t)(1 + k) * d);
+    B200_CUDA(c, cudaMemcpyAsync(dv, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = dv;
+    return 0;
+}
+
+int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out)
+{
+    if (!L || L->kind != B200_DOMAIN_AFFINE_SUBSPACE)
+        return set_err(c, B200_ERR_INVALID, "additive FFT needs an affine subspace domain");
+    const uint32_t m = L->dim;
+    if (m > 31) return set_err(c, B200_ERR_INVALID, "domain dimension %u too large", m);
+    const size_t n = (size_t)1 << m;
+    if (n_coeffs > n) return set_err(c, B200_ERR_INVALID, "more coefficients (%zu) than domain elements (%zu)", n_coeffs, n);
+    gf192 *o = (gf192 *)out;
+    if (n_coeffs <= 1) { /* constant polynomial */
+        fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(o, n_coeffs ? (const gf192 *)coeffs : nullptr, n);
+        B200_LAUNCH_CHECK(c);
+        return 0;
+    }
+    const uint32_t d = ceil_log2(n_coeffs);
+    std::shared_ptr<AdditivePlan> pl;
+    int rc = get_plan(c, (const gf192 *)L->basis, d, false, &pl);
+    if (rc) return rc;
+    gf192 *taus = nullptr;
+    rc = upload_taus(c, *pl, L, d, m, &taus);
+    if (rc) return rc;
+
+    const size_t nd = (size_t)1 << d;
+    gf192 *X = (gf192 *)scratch_get(c, 0, nd * sizeof(gf192));
+    if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate FFT work array");
+    B200_CUDA(c, cudaMemcpyAsync(X, (const void *)coeffs, n_coeffs * sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
+    if (n_coeffs < nd) B200_CUDA(c, cudaMemsetAsync(X + n_coeffs, 0, (nd - n_coeffs) * sizeof(gf192), c->stream));
+
+    PassParams P; memset(&P, 0, sizeof P);
+    P.tw = pl->tw; P.sums = pl->sums; P.taus = taus; P.n_extra = m - d;
+
+    /* forward half on X (shared by all cosets): fft.tcc:56-83 */
+    std::vector<uint32_t> steps;
+    for (uint32_t j = 0; j < d; ++j) {
+        steps.push_back((OP_TW << 8) | j);
+        for (int s = (int)d - 2; s >= (int)j; --s) steps.push_back((OP_TAY << 8) | (uint32_t)s);
+    }
+    for (const Pass &p : schedule(steps, d)) {
+        P.src = X; P.dst = X; P.src_coset_stride_log = 32; P.n_extra = 0;
+        rc = launch_pass<false>(c, p, P, d, 1);
+        if (rc) return rc;
+    }
+    /* butterfly half per coset: bit-reversed load from X (fft.tcc:99), stages 0..d-1 (fft.tcc:101-120) */
+    P.n_extra = m - d;
+    const uint32_t n_cosets = 1u << (m - d);
+    const uint32_t tb = std::min(kTileBits, d);
+    uint32_t first_hi = d <= tb ? d : tb - kCoalesceBits;
+    {
+        Pass p; p.lo = 0; p.hi = first_hi; p.c = 0; p.ctop = d <= tb ? 0 : kCoalesceBits; p.bitrev = 1;
+        for (uint32_t jj = 0; jj < first_hi; ++jj) p.ops.push_back((OP_BF << 8) | jj);
+        P.src = X; P.dst = o; P.src_coset_stride_log = 32;
+        rc = launch_pass<false>(c, p, P, d, n_cosets);
+        if (rc) return rc;
+    }
+    steps.clear();
+    for (uint32_t jj = first_hi; jj < d; ++jj) steps.push_back((OP_BF << 8) | jj);
+    for (const Pass &p : schedule(steps, d)) {
+        P.src = o; P.dst = o; P.src_coset_stride_log = d;
+        rc = launch_pass<false>(c, p, P, d, n_cosets);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out)
+{
+    if (!H || H->kind != B200_DOMAIN_AFFINE_SUBSPACE)
+        return set_err(c, B200_ERR_INVALID, "additive IFFT needs an affine subspace domain");
+    const uint32_t m = H->dim;
+    if (m > 31) return set_err(c, B200_ERR_INVALID, "domain dimension %u too large", m);
+    const size_t n = (size_t)1 << m;
+    if (m == 0) {
+        B200_CUDA(c, cudaMemcpyAsync((void *)out, (const void *)evals, sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    std::shared_ptr<AdditivePlan> pl;
+    int rc = get_plan(c, (const gf192 *)H->basis, m, true, &pl);
+    if (rc) return rc;
+    gf192 *taus = nullptr;
+    rc = upload_taus(c, *pl, H, m, m, &taus);
+    if (rc) return rc;
+
+    gf192 *X = (gf192 *)scratch_get(c, 0, n * sizeof(gf192));
+    if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate IFFT work array");
+    gf192 *o = (gf192 *)out;
+    PassParams P; memset(&P, 0, sizeof P);
+    P.tw = pl->itw; P.sums = pl->sums; P.taus = taus; P.n_extra = 0; P.src_coset_stride_log = 32;
+
+    /* inverse butterflies, large stride first (fft.tcc:139-168): evals -> X */
+    const uint32_t tb = std::min(kTileBits, m);
+    std::vector<uint32_t> steps;
+    const uint32_t last_hi = m <= tb ? m : tb - kCoalesceBits; /* stages [0, last_hi) go into the bit-reversing pass */
+    for (int jj = (int)m - 1; jj >= (int)last_hi; --jj) steps.push_back((OP_BF << 8) | (uint32_t)jj);
+    const gf192 *cur = (const gf192 *)evals;
+    for (const Pass &p : schedule(steps, m)) {
+        P.src = cur; P.dst = X;
+        rc = launch_pass<true>(c, p, P, m, 1);
+        if (rc) return rc;
+        cur = X;
+    }
+    {   /* last inverse stages, then store bit-reversed (fft.tcc:170) into `out` */
+        Pass p; p.lo = 0; p.hi = last_hi; p.c = 0; p.ctop = m <= tb ? 0 : kCoalesceBits; p.bitrev = 2;
+        for (int jj = (int)last_hi - 1; jj >= 0; --jj) p.ops.push_back((OP_BF << 8) | (uint32_t)jj);
+        P.src = cur; P.dst = o;
+        rc = launch_pass<true>(c, p, P, m, 1);
+        if (rc) return rc;
+    }
+    /* radix combinations + inverse twists, deepest level first (fft.tcc:172-201) */
+    steps.clear();
+    for (int jd = (int)m - 1; jd >= 0; --jd) {
+        for (int s = jd; s <= (int)m - 2; ++s) steps.push_back((OP_TAY << 8) | (uint32_t)s);
+        steps.push_back((OP_TW << 8) | (uint32_t)jd);
+    }
+    for (const Pass &p : schedule(steps, m)) {
+        P.src = o; P.dst = o;
+        rc = launch_pass<true>(c, p, P, m, 1);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* element-wise helpers                                                                           */
+__global__ void gf192_mul_kernel(gf192 *out, const gf192 *a, const gf192 *b, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = gf_mul(a[i], b[i]);
+}
+__global__ void gf192_inv_kernel(gf192 *out, const gf192 *a, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = gf_inv(a[i]);
+}
+
+int gf192_mul_vec(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n)
+{
+    if (!n) return 0;
+    gf192_mul_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
+        (gf192 *)out, (const gf192 *)a, (const gf192 *)b, n);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+int gf192_inv_vec(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
+{
+    if (!n) return 0;
+    gf192_inv_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, 148 * 8), 128, 0, c->stream>>>(
+        (gf192 *)out, (const gf192 *)a, n);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+} // namespace b200

@@ -1,0 +1,236 @@
+/*
+ * api.cu — C ABI of libb200iop.so (declared in include/b200_iop.h): context, memory, and thin
+ * forwarding to the kernels.  No CPU fallback: every compute entry point launches CUDA kernels.
+ */
+#include <cstring>
+#include <new>
+
+#include "ctx.h"
+
+namespace b200 {
+void plans_clear(b200_ctx *c) { c->additive_plans.clear(); c->ntt_plans.clear(); }
+}
+
+using namespace b200;
+
+extern "C" {
+
+const char *b200_version(void) { return "libb200iop 0.1 (sm_100a)"; }
+
+b200_ctx *b200_ctx_create(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return nullptr; }
+    if (device < 0 || device >= count) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    b200_ctx *c = new (std::nothrow) b200_ctx();
+    if (!c) return nullptr;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return nullptr; }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaGetLastError(); delete c; return nullptr;
+    }
+    return c;
+}
+
+void b200_ctx_destroy(b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    plans_clear(c);
+    for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->staging) cudaFreeHost(c->staging);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *b200_last_error(b200_ctx *c) { return c ? c->err : "no context (is a CUDA device present?)"; }
+
+int b200_sync(b200_ctx *c)
+{
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void *b200_stream(b200_ctx *c) { return (void *)c->stream; }
+
+int b200_device_info(b200_ctx *c, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor)
+{
+    cudaDeviceProp prop;
+    B200_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+b200_buf b200_alloc(b200_ctx *c, size_t n_elems) { return b200_alloc_bytes(c, n_elems * 24); }
+void b200_free(b200_ctx *c, b200_buf b) { b200_free_bytes(c, b); }
+b200_bytes b200_alloc_bytes(b200_ctx *c, size_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, n_bytes ? n_bytes : 8) != cudaSuccess) {
+        cudaGetLastError();
+        set_err(c, B200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", n_bytes);
+        return 0;
+    }
+    return (b200_bytes)(uintptr_t)p;
+}
+void b200_free_bytes(b200_ctx *c, b200_bytes b)
+{
+    if (!b) return;
+    cudaStreamSynchronize(c->stream);
+    cudaFree((void *)(uintptr_t)b);
+}
+void *b200_host_alloc(b200_ctx *c, size_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, n_bytes ? n_bytes : 8) != cudaSuccess) {
+        cudaGetLastError();
+        set_err(c, B200_ERR_NOMEM, "cudaMallocHost of %zu bytes failed", n_bytes);
+        return nullptr;
+    }
+    return p;
+}
+void b200_host_free(b200_ctx *, void *p) { if (p) cudaFreeHost(p); }
+
+int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *src, size_t n_elems)
+{
+    B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, src, n_elems * 24, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems)
+{
+    B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + src_offset * 24, n_elems * 24, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_bytes)
+{
+    B200_CUDA(c, cudaMemcpyAsync((void *)(uintptr_t)dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes)
+{
+    B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + offset, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int b200_copy(b200_ctx *c, b200_buf dst, size_t dst_offset, b200_buf src, size_t src_offset, size_t n_elems)
+{
+    B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, (const char *)(uintptr_t)src + src_offset * 24,
+                                 n_elems * 24, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int b200_fill_zero(b200_ctx *c, b200_buf dst, size_t dst_offset, size_t n_elems)
+{
+    B200_CUDA(c, cudaMemsetAsync((char *)(uintptr_t)dst + dst_offset * 24, 0, n_elems * 24, c->stream));
+    return 0;
+}
+
+__global__ void gather_kernel(uint64_t *out, const uint64_t *src, const size_t *idx, size_t k)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < k * 3) out[t] = src[idx[t / 3] * 3 + t % 3];
+}
+
+int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, size_t k)
+{
+    if (!k) return 0;
+    const size_t bytes = k * sizeof(size_t) + k * 24;
+    char *dev = (char *)scratch_get(c, 3, bytes);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate gather buffer");
+    size_t *didx = (size_t *)dev;
+    uint64_t *dout = (uint64_t *)(dev + k * sizeof(size_t));
+    B200_CUDA(c, cudaMemcpyAsync(didx, idx, k * sizeof(size_t), cudaMemcpyHostToDevice, c->stream));
+    gather_kernel<<<(unsigned)((k * 3 + 255) / 256), 256, 0, c->stream>>>(dout, (const uint64_t *)(uintptr_t)src, didx, k);
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaMemcpyAsync(dst, dout, k * 24, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int b200_timer_start(b200_ctx *c) { B200_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
+int b200_timer_stop(b200_ctx *c, float *ms)
+{
+    B200_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    B200_CUDA(c, cudaEventSynchronize(c->ev1));
+    B200_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+int b200_gf192_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
+{
+    return additive_fft(c, L, coeffs, n_coeffs, evals_out);
+}
+int b200_gf192_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
+{
+    return additive_ifft(c, H, evals, coeffs_out);
+}
+int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { return gf192_mul_vec(c, out, a, b, n); }
+int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n) { return gf192_inv_vec(c, out, a, n); }
+
+int b200_fp_ntt(b200_ctx *c, const b200_fp_params *P, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
+{
+    return fp_ntt(c, P, L, coeffs, n_coeffs, evals_out);
+}
+int b200_fp_intt(b200_ctx *c, const b200_fp_params *P, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
+{
+    return fp_intt(c, P, H, evals, coeffs_out);
+}
+int b200_fp_mul(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 0, out, a, b, n); }
+int b200_fp_add(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 1, out, a, b, n); }
+int b200_fp_sub(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 2, out, a, b, n); }
+int b200_fp_inv(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, size_t n) { return fp_binop_vec(c, P, 3, out, a, 0, n); }
+
+int b200_fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_domain *L_i, uint32_t eta,
+                  const uint64_t x_i[3], b200_buf f_i, b200_buf f_next_out)
+{
+    return fri_fold(c, field, fp, L_i, eta, x_i, f_i, f_next_out);
+}
+
+int b200_merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset_size,
+                      int domain_kind, const uint8_t *zk_salts_host, size_t salt_len, size_t digest_len, b200_bytes nodes_out)
+{
+    return merkle_build(c, oracles, n_oracles, n_elems, coset_size, domain_kind, zk_salts_host, salt_len, digest_len, nodes_out);
+}
+int b200_merkle_root(b200_ctx *c, b200_bytes nodes, uint8_t *root_out, size_t digest_len)
+{
+    return b200_download_bytes(c, root_out, nodes, 0, digest_len);
+}
+
+__global__ void node_gather_kernel(uint64_t *out, const uint64_t *nodes, const size_t *idx, size_t k, uint32_t dw)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < k * dw) out[t] = nodes[idx[t / dw] * dw + t % dw];
+}
+
+int b200_merkle_nodes(b200_ctx *c, b200_bytes nodes, const size_t *node_idx, size_t k, size_t digest_len, uint8_t *out)
+{
+    if (!k) return 0;
+    if (digest_len % 8) return set_err(c, B200_ERR_INVALID, "digest length must be a multiple of 8");
+    const uint32_t dw = (uint32_t)(digest_len / 8);
+    char *dev = (char *)scratch_get(c, 3, k * sizeof(size_t) + k * digest_len);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate gather buffer");
+    size_t *didx = (size_t *)dev;
+    uint64_t *dout = (uint64_t *)(dev + k * sizeof(size_t));
+    B200_CUDA(c, cudaMemcpyAsync(didx, node_idx, k * sizeof(size_t), cudaMemcpyHostToDevice, c->stream));
+    node_gather_kernel<<<(unsigned)((k * dw + 255) / 256), 256, 0, c->stream>>>(dout, (const uint64_t *)(uintptr_t)nodes, didx, k, dw);
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaMemcpyAsync(out, dout, k * digest_len, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int b200_blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out)
+{
+    return blake2b_batch(c, in, msg_len, n_msgs, digest_len, out);
+}
+
+} /* extern "C" */

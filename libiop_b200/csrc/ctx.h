@@ -1,0 +1,108 @@
+/* ctx.h — internal context shared by the translation units of libb200iop.so */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_iop.h"
+
+namespace b200 {
+struct AdditivePlan;
+struct NttPlan;
+}
+
+struct b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    char err[512] = {0};
+    /* grow-only device scratch (work arrays of the FFTs), keyed by slot */
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    /* pinned staging for small host<->device transfers */
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    /* cached per-domain plans */
+    std::map<std::string, std::shared_ptr<b200::AdditivePlan>> additive_plans;
+    std::map<std::string, std::shared_ptr<b200::NttPlan>> ntt_plans;
+};
+
+namespace b200 {
+
+inline int set_err(b200_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof c->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define B200_CUDA(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return b200::set_err((ctx), B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                                 cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define B200_LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                   \
+            return b200::set_err((ctx), B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
+                                 cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+/* grow-only scratch buffer */
+inline void *scratch_get(b200_ctx *c, int slot, size_t bytes)
+{
+    if (c->scratch_bytes[slot] >= bytes) return c->scratch[slot];
+    if (c->scratch[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[slot]); c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0; }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    c->scratch[slot] = p; c->scratch_bytes[slot] = bytes;
+    return p;
+}
+
+inline void *staging_get(b200_ctx *c, size_t bytes)
+{
+    if (c->staging_bytes >= bytes) return c->staging;
+    if (c->staging) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->staging); c->staging = nullptr; c->staging_bytes = 0; }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    c->staging = p; c->staging_bytes = bytes;
+    return p;
+}
+
+inline uint32_t ceil_log2(size_t n)
+{
+    uint32_t r = 0;
+    while (((size_t)1 << r) < n) ++r;
+    return r;
+}
+
+/* implemented in the per-subsystem translation units */
+int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out);
+int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out);
+int gf192_mul_vec(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int gf192_inv_vec(b200_ctx *c, b200_buf out, b200_buf a, size_t n);
+int fp_ntt(b200_ctx *c, const b200_fp_params *P, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out);
+int fp_intt(b200_ctx *c, const b200_fp_params *P, const b200_domain *H, b200_buf evals, b200_buf out);
+int fp_binop_vec(b200_ctx *c, const b200_fp_params *P, int op, b200_buf out, b200_buf a, b200_buf b, size_t n);
+int fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_domain *L, uint32_t eta,
+             const uint64_t x[3], b200_buf f, b200_buf out);
+int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset,
+                 int kind, const uint8_t *salts, size_t salt_len, size_t digest_len, b200_bytes nodes);
+int blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
+void plans_clear(b200_ctx *c);
+
+} // namespace b200

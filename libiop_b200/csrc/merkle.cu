@@ -1,0 +1,330 @@
+/*
+ * merkle.cu — BLAKE2b Merkle-tree build for the BCS transformation, sm_100a.
+ *
+ * Replaces merkle_tree::construct_with_leaves_serialized_by_cosets (libiop/bcs/merkle_tree.tcc:93-151),
+ * compute_inner_nodes (merkle_tree.tcc:201-229) and the hash callables injected into it:
+ * blake2b_field_element_hash (libiop/bcs/hashing/blake2b.tcc:141-160), blake2b_leafhash::zk_hash
+ * (blake2b.tcc:127-136) and blake2b_two_to_one_hash (libiop/bcs/hashing/blake2b.cpp:28-48).
+ * BLAKE2b itself is RFC 7693 as provided by libsodium's crypto_generichash_blake2b (unkeyed,
+ * digest_length = outlen, fanout = depth = 1).
+ *
+ * Leaf i hashes, for oracle k (registration order) and j < coset_size, the raw 24-byte element at
+ * pos(i,j) = i*coset + j (affine subspace, subspace.tcc:87-91) or i + j*leaves (multiplicative coset,
+ * subgroup.tcc:192-197), laid out slice[j + k*coset] (merkle_tree.tcc:127-134).  Nodes are stored in
+ * heap order, root at 0, leaf i at leaves-1+i (merkle_tree.tcc:145).
+ *
+ * B200 design: one thread per hash (BLAKE2b is 64-bit ARX: no cross-lane traffic is needed, the
+ * 16-word state and the 16-word message block live in registers).  The leaf kernel gathers the
+ * column slice straight from the oracle arrays; because the tree is heap-ordered, a CTA that hashes
+ * 2^k consecutive leaves also owns the k levels above them, so the lower levels are reduced inside
+ * shared memory in the same launch and only the top of the tree runs as small per-level launches.
+ */
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace b200 {
+
+__constant__ uint64_t c_blake_iv[8] = {
+    0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+
+#define BLAKE_IV0 0x6a09e667f3bcc908ULL
+#define BLAKE_IV1 0xbb67ae8584caa73bULL
+#define BLAKE_IV2 0x3c6ef372fe94f82bULL
+#define BLAKE_IV3 0xa54ff53a5f1d36f1ULL
+#define BLAKE_IV4 0x510e527fade682d1ULL
+#define BLAKE_IV5 0x9b05688c2b3e6c1fULL
+#define BLAKE_IV6 0x1f83d9abfb41bd6bULL
+#define BLAKE_IV7 0x5be0cd19137e2179ULL
+
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+__device__ __forceinline__ uint64_t rotr32x(uint64_t x) { return (x >> 32) | (x << 32); }
+/* byte-granular rotations as byte permutes */
+__device__ __forceinline__ uint64_t rotr24(uint64_t x)
+{
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return (uint64_t)__byte_perm(lo, hi, 0x6543) | ((uint64_t)__byte_perm(lo, hi, 0x2107) << 32);
+}
+__device__ __forceinline__ uint64_t rotr16(uint64_t x)
+{
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return (uint64_t)__byte_perm(lo, hi, 0x5432) | ((uint64_t)__byte_perm(lo, hi, 0x1076) << 32);
+}
+
+#define BLAKE_G(a, b, c, d, x, y)                  \
+    do {                                           \
+        a = a + b + (x); d = rotr32x(d ^ a);       \
+        c = c + d;       b = rotr24(b ^ c);        \
+        a = a + b + (y); d = rotr16(d ^ a);        \
+        c = c + d;       b = rotr64(b ^ c, 63);    \
+    } while (0)
+
+#define BLAKE_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    do {                                                                                      \
+        BLAKE_G(v0, v4, v8, v12, m[s0], m[s1]);                                               \
+        BLAKE_G(v1, v5, v9, v13, m[s2], m[s3]);                                               \
+        BLAKE_G(v2, v6, v10, v14, m[s4], m[s5]);                                              \
+        BLAKE_G(v3, v7, v11, v15, m[s6], m[s7]);                                              \
+        BLAKE_G(v0, v5, v10, v15, m[s8], m[s9]);                                              \
+        BLAKE_G(v1, v6, v11, v12, m[s10], m[s11]);                                            \
+        BLAKE_G(v2, v7, v8, v13, m[s12], m[s13]);                                             \
+        BLAKE_G(v3, v4, v9, v14, m[s14], m[s15]);                                             \
+    } while (0)
+
+/* one BLAKE2b compression; m[] must be indexable with compile-time constants (registers) */
+__device__ __forceinline__ void blake2b_compress(uint64_t h[8], const uint64_t m[16], uint64_t t, bool last)
+{
+    uint64_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    uint64_t v8 = BLAKE_IV0, v9 = BLAKE_IV1, v10 = BLAKE_IV2, v11 = BLAKE_IV3;
+    uint64_t v12 = BLAKE_IV4 ^ t, v13 = BLAKE_IV5, v14 = last ? ~BLAKE_IV6 : BLAKE_IV6, v15 = BLAKE_IV7;
+    BLAKE_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    BLAKE_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    BLAKE_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
+    BLAKE_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
+    BLAKE_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
+    BLAKE_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
+    BLAKE_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
+    BLAKE_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
+    BLAKE_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
+    BLAKE_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
+    BLAKE_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    BLAKE_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    h[0] ^= v0 ^ v8; h[1] ^= v1 ^ v9; h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+    h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+
+__device__ __forceinline__ void blake2b_init(uint64_t h[8], uint32_t outlen)
+{
+    h[0] = BLAKE_IV0 ^ 0x01010000ULL ^ (uint64_t)outlen;
+    h[1] = BLAKE_IV1; h[2] = BLAKE_IV2; h[3] = BLAKE_IV3; h[4] = BLAKE_IV4; h[5] = BLAKE_IV5; h[6] = BLAKE_IV6; h[7] = BLAKE_IV7;
+}
+
+/* Hash a message delivered word by word: word(w) returns the w-th little-endian u64 of the message,
+   n_words its length in whole words (all messages on this path are multiples of 8 bytes). */
+template <typename WordFn>
+__device__ __forceinline__ void blake2b_words(uint64_t h[8], uint32_t outlen, size_t n_words, WordFn word)
+{
+    blake2b_init(h, outlen);
+    uint64_t m[16];
+    size_t done = 0;
+    for (;;) {
+        const size_t remaining = n_words - done;
+        const bool last = remaining <= 16;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) m[t] = ((size_t)t < remaining) ? word(done + t) : 0ull;
+        const size_t consumed = last ? remaining : 16;
+        done += consumed;
+        blake2b_compress(h, m, (uint64_t)done * 8, last);
+        if (last) break;
+    }
+}
+
+/* two-to-one hash of 2 x digest_words u64 (digest_len <= 64, multiple of 8) */
+__device__ __forceinline__ void blake2b_two_to_one(uint64_t h[8], uint32_t outlen, const uint64_t *left, const uint64_t *right, uint32_t dw)
+{
+    blake2b_init(h, outlen);
+    uint64_t m[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        uint64_t v = 0;
+        if ((uint32_t)t < dw) v = left[t];
+        else if ((uint32_t)t < 2 * dw) v = right[t - dw];
+        m[t] = v;
+    }
+    blake2b_compress(h, m, (uint64_t)dw * 16, true);
+}
+
+struct LeafParams {
+    const uint64_t *oracles[64];
+    uint32_t n_oracles;
+    uint32_t coset;        /* power of two */
+    uint32_t coset_log;
+    int kind;
+    size_t leaves;
+    const uint64_t *salts; /* device, leaves * salt_words, or null */
+    uint32_t salt_words, digest_words, digest_len;
+    uint64_t *nodes;       /* (2*leaves-1) * digest_words */
+    uint32_t fused_levels; /* levels reduced inside the CTA (CTA covers 2^fused_levels leaves) */
+    const uint64_t *const *oracle_table; /* device array when n_oracles > 64 */
+};
+
+#define MERKLE_CTA 256
+
+__global__ void __launch_bounds__(MERKLE_CTA) merkle_leaf_kernel(const LeafParams P)
+{
+    __shared__ uint64_t sdig[MERKLE_CTA * 8];
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const uint32_t dw = P.digest_words;
+    uint64_t h[8];
+    if (i < P.leaves) {
+        const size_t n_words = (size_t)3 * P.n_oracles * P.coset;
+        const uint32_t cmask = P.coset - 1;
+        auto word = [&](size_t w) -> uint64_t {
+            const size_t e = w / 3;                    /* element index in the slice: j + k*coset */
+            const uint32_t limb = (uint32_t)(w - 3 * e);
+            const uint32_t j = (uint32_t)e & cmask;
+            const size_t k = e >> P.coset_log;
+            const size_t pos = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? (i + (size_t)j * P.leaves) : (i * P.coset + j);
+            const uint64_t *base = P.oracle_table ? P.oracle_table[k] : P.oracles[k];
+            return __ldg(base + pos * 3 + limb);
+        };
+        blake2b_words(h, P.digest_len, n_words, word);
+        if (P.salts) {                                  /* zk: H(H(leaf) || salt)  (blake2b.tcc:127-136) */
+            uint64_t inner[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) inner[t] = h[t];
+            const uint64_t *salt = P.salts + i * P.salt_words;
+            const uint32_t sw = P.salt_words;
+            auto word2 = [&](size_t w) -> uint64_t {
+                uint64_t v = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (w == (size_t)t) v = inner[t];
+                if (w >= dw) v = salt[w - dw];
+                return v;
+            };
+            blake2b_words(h, P.digest_len, (size_t)dw + sw, word2);
+        }
+        uint64_t *dst = P.nodes + (P.leaves - 1 + i) * dw;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) if ((uint32_t)t < dw) { dst[t] = h[t]; sdig[threadIdx.x * 8 + t] = h[t]; }
+    }
+    /* reduce the CTA's subtree in shared memory: level l has MERKLE_CTA >> l nodes */
+    uint32_t width = MERKLE_CTA;
+    size_t level_nodes = P.leaves;              /* nodes of the current level in the whole tree */
+    for (uint32_t l = 0; l < P.fused_levels; ++l) {
+        __syncthreads();
+        width >>= 1; level_nodes >>= 1;
+        uint64_t r[8];
+        const bool active = threadIdx.x < width && (blockIdx.x * (size_t)width + threadIdx.x) < level_nodes;
+        if (active) blake2b_two_to_one(r, P.digest_len, &sdig[(2 * threadIdx.x) * 8], &sdig[(2 * threadIdx.x + 1) * 8], dw);
+        __syncthreads();
+        if (active) {
+            const size_t node = (level_nodes - 1) + blockIdx.x * (size_t)width + threadIdx.x;
+            uint64_t *dst = P.nodes + node * dw;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) if ((uint32_t)t < dw) { dst[t] = r[t]; sdig[threadIdx.x * 8 + t] = r[t]; }
+        }
+    }
+}
+
+/* one level of inner nodes: node j in [first, first+count) = H(node 2j+1 || node 2j+2) (merkle_tree.tcc:209-218) */
+__global__ void merkle_level_kernel(uint64_t *nodes, size_t first, size_t count, uint32_t dw, uint32_t digest_len)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const size_t j = first + t;
+    uint64_t l[8], r[8], h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        l[q] = ((uint32_t)q < dw) ? nodes[(2 * j + 1) * dw + q] : 0;
+        r[q] = ((uint32_t)q < dw) ? nodes[(2 * j + 2) * dw + q] : 0;
+    }
+    blake2b_two_to_one(h, digest_len, l, r, dw);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if ((uint32_t)q < dw) nodes[j * dw + q] = h[q];
+}
+
+/* top of the tree (<= 2^10 nodes wide) in a single CTA */
+__global__ void __launch_bounds__(1024) merkle_top_kernel(uint64_t *nodes, size_t width, uint32_t dw, uint32_t digest_len)
+{
+    /* width = number of nodes of the highest level already computed (power of two <= 2048) */
+    for (size_t w = width >> 1; w >= 1; w >>= 1) {
+        if (threadIdx.x < w) {
+            const size_t j = (w - 1) + threadIdx.x;
+            uint64_t l[8], r[8], h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                l[q] = ((uint32_t)q < dw) ? nodes[(2 * j + 1) * dw + q] : 0;
+                r[q] = ((uint32_t)q < dw) ? nodes[(2 * j + 2) * dw + q] : 0;
+            }
+            blake2b_two_to_one(h, digest_len, l, r, dw);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if ((uint32_t)q < dw) nodes[j * dw + q] = h[q];
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset,
+                 int kind, const uint8_t *salts, size_t salt_len, size_t digest_len, b200_bytes nodes)
+{
+    if (!oracles || n_oracles == 0) return set_err(c, B200_ERR_INVALID, "no oracles");
+    if (coset == 0 || (coset & (coset - 1)) || n_elems % coset)
+        return set_err(c, B200_ERR_LOGIC, "Attempting to construct a Merkle tree with a constituent vector of wrong size");
+    const size_t leaves = n_elems / coset;
+    if (leaves < 2 || (leaves & (leaves - 1)))   /* merkle_tree.tcc:27-31 */
+        return set_err(c, B200_ERR_INVALID, "Merkle tree size must be a power of two, and at least 2.");
+    if (digest_len == 0 || digest_len > 64 || digest_len % 8)
+        return set_err(c, B200_ERR_INVALID, "digest length must be a multiple of 8 bytes, at most 64");
+    if (salts && (salt_len % 8 || salt_len == 0 || digest_len + salt_len > 128))
+        return set_err(c, B200_ERR_INVALID, "unsupported zk salt length");
+    if (kind != B200_DOMAIN_AFFINE_SUBSPACE && kind != B200_DOMAIN_MULTIPLICATIVE_COSET)
+        return set_err(c, B200_ERR_INVALID, "unknown domain kind");
+
+    LeafParams P; memset(&P, 0, sizeof P);
+    P.n_oracles = (uint32_t)n_oracles; P.coset = (uint32_t)coset; P.coset_log = ceil_log2(coset);
+    P.kind = kind; P.leaves = leaves; P.digest_len = (uint32_t)digest_len; P.digest_words = (uint32_t)(digest_len / 8);
+    P.nodes = (uint64_t *)nodes;
+    if (n_oracles <= 64) {
+        for (size_t k = 0; k < n_oracles; ++k) P.oracles[k] = (const uint64_t *)oracles[k];
+    } else {                                       /* Ligero: hundreds of rows per leaf */
+        const uint64_t **tab = (const uint64_t **)scratch_get(c, 3, n_oracles * sizeof(uint64_t *));
+        if (!tab) return set_err(c, B200_ERR_NOMEM, "cannot allocate oracle table");
+        B200_CUDA(c, cudaMemcpyAsync(tab, oracles, n_oracles * sizeof(uint64_t *), cudaMemcpyHostToDevice, c->stream));
+        P.oracle_table = tab;
+    }
+    if (salts) {
+        uint8_t *ds = (uint8_t *)scratch_get(c, 2, leaves * salt_len);
+        if (!ds) return set_err(c, B200_ERR_NOMEM, "cannot allocate salt buffer");
+        B200_CUDA(c, cudaMemcpyAsync(ds, salts, leaves * salt_len, cudaMemcpyHostToDevice, c->stream));
+        P.salts = (const uint64_t *)ds; P.salt_words = (uint32_t)(salt_len / 8);
+    }
+    /* fused levels: a CTA of 256 leaves owns 8 levels above them */
+    uint32_t fused = 0;
+    while (fused < 8 && (leaves >> (fused + 1)) >= 1 && (MERKLE_CTA >> (fused + 1)) >= 1 && ((size_t)MERKLE_CTA <= leaves)) ++fused;
+    if (leaves < MERKLE_CTA) fused = 0;
+    P.fused_levels = fused;
+    const unsigned blocks = (unsigned)((leaves + MERKLE_CTA - 1) / MERKLE_CTA);
+    merkle_leaf_kernel<<<blocks, MERKLE_CTA, 0, c->stream>>>(P);
+    B200_LAUNCH_CHECK(c);
+    /* remaining levels */
+    size_t width = leaves >> fused;   /* nodes in the highest level already computed */
+    while (width > 2048) {
+        const size_t count = width >> 1, first = count - 1;
+        merkle_level_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(P.nodes, first, count, P.digest_words, P.digest_len);
+        B200_LAUNCH_CHECK(c);
+        width = count;
+    }
+    if (width > 1) {
+        merkle_top_kernel<<<1, 1024, 0, c->stream>>>(P.nodes, width, P.digest_words, P.digest_len);
+        B200_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
+struct BatchParams { const uint64_t *in; uint64_t *out; size_t msg_words, n; uint32_t digest_len, dw; };
+__global__ void blake2b_batch_kernel(const BatchParams P)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint64_t *msg = P.in + i * P.msg_words;
+    uint64_t h[8];
+    blake2b_words(h, P.digest_len, P.msg_words, [&](size_t w) { return msg[w]; });
+    for (uint32_t t = 0; t < P.dw; ++t) P.out[i * P.dw + t] = h[t];
+}
+
+int blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out)
+{
+    if (msg_len % 8 || digest_len % 8 || digest_len == 0 || digest_len > 64)
+        return set_err(c, B200_ERR_INVALID, "message and digest lengths must be multiples of 8 bytes");
+    if (!n_msgs) return 0;
+    BatchParams P{(const uint64_t *)in, (uint64_t *)out, msg_len / 8, n_msgs, (uint32_t)digest_len, (uint32_t)(digest_len / 8)};
+    blake2b_batch_kernel<<<(unsigned)((n_msgs + 127) / 128), 128, 0, c->stream>>>(P);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+} // namespace b200
