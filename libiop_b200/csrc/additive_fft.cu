@@ -115,11 +115,13 @@ __global__ void __launch_bounds__(256) additive_tile_pass(const PassParams P)
     Tile t;
     t.p0 = smem; t.p1 = smem + T + B200_SMEM_PAD; t.p2 = smem + 2 * (T + B200_SMEM_PAD);
 
-    const uint32_t coset = blockIdx.y;
-    const uint32_t midbits = P.lo - P.c;
-    const uint32_t mid = blockIdx.x & ((1u << midbits) - 1u);
-    const uint32_t top = blockIdx.x >> midbits;
     const uint32_t d = P.d;
+    const uint32_t tilebits = d - tb;                       /* tiles per coset = 2^tilebits */
+    const uint32_t coset = blockIdx.x >> tilebits;
+    const uint32_t tile = blockIdx.x & ((1u << tilebits) - 1u);
+    const uint32_t midbits = P.lo - P.c;
+    const uint32_t mid = tile & ((1u << midbits) - 1u);
+    const uint32_t top = tile >> midbits;
 
     /* recursed shift of this coset for every depth: F2-linear in the shift, so
        tau(shift + sum_k q_k basis[d+k]) = tau(shift) + sum_k q_k tau(basis[d+k]) */
@@ -373,8 +375,9 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
                                           (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t))));
         attr_set[INV] = true;
     }
-    dim3 grid(1u << (d - tb), n_cosets);
-    additive_tile_pass<INV><<<grid, 256, smem, c->stream>>>(P);
+    const uint64_t nblocks = ((uint64_t)1 << (d - tb)) * n_cosets;
+    if (nblocks > 0x7fffffffull) return set_err(c, B200_ERR_INVALID, "grid too large");
+    additive_tile_pass<INV><<<(unsigned)nblocks, 256, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
     return 0;
 }
