@@ -1,0 +1,39 @@
+"""Times the individual hot-path calls (CUDA events, device-resident).  Usage: python bench/time_ops.py [reps]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import libiop_b200 as L
+
+dev = L.B200(0)
+rng = np.random.default_rng(0)
+n, m = 20, 23
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+def rnd(k):
+    b = dev.alloc(k)
+    for off in range(0, k, 1 << 18):
+        kk = min(1 << 18, k - off)
+        dev.upload(rng.integers(0, 2**64, size=(kk, 3), dtype=np.uint64), b, off)
+    return b
+c = rnd(1 << 21); e = dev.alloc(1 << m); o = dev.alloc(1 << 21)
+def t(fn, reps=reps):
+    fn(); fn(); dev.sync(); dev.timer_start()
+    for _ in range(reps): fn()
+    return dev.timer_stop() / reps
+dom = L.Domain.standard(m)
+res = {}
+res["fft 2^20->2^23"] = t(lambda: dev.gf192_fft_dev(dom, c, 1 << n, e))
+res["fft 2^20->2^20"] = t(lambda: dev.gf192_fft_dev(L.Domain.standard(n), c, 1 << n, o))
+res["fft 32->2^23"] = t(lambda: dev.gf192_fft_dev(dom, c, 32, e))
+res["ifft 2^20"] = t(lambda: dev.gf192_ifft_dev(L.Domain.standard(n), c, o))
+res["ifft 2^21"] = t(lambda: dev.gf192_ifft_dev(L.Domain.standard(n + 1), c, o))
+x = rng.integers(0, 2**64, size=3, dtype=np.uint64)
+f = dev.alloc(1 << (m - 1))
+res["fold 2^23 eta1"] = t(lambda: dev.fri_fold_dev(1, None, dom, 1, x, e, f))
+d22 = L.Domain.standard(22)
+res["fold 2^22 eta2"] = t(lambda: dev.fri_fold_dev(1, None, d22, 2, x, e, f))
+nodes = dev.alloc_bytes(32 * (2 * (1 << (m - 1)) - 1))
+e2 = [rnd(1 << m) for _ in range(3)]
+res["merkle 4x2^23 c2"] = t(lambda: dev.merkle_build_dev([e] + e2, 1 << m, 2, 1, nodes))
+res["merkle 1x2^23 c2"] = t(lambda: dev.merkle_build_dev([e], 1 << m, 2, 1, nodes))
+res["merkle 1x2^22 c4"] = t(lambda: dev.merkle_build_dev([e], 1 << 22, 4, 1, nodes))
+print(os.environ.get("B200_LIB", "default"), " | ".join(f"{k}: {v:.3f} ms" for k, v in res.items()))

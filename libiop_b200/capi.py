@@ -100,6 +100,8 @@ class Domain:
 
 
 def load_library():
+    global LIB_PATH
+    LIB_PATH = os.environ.get("B200_LIB", LIB_PATH)   # kernel-tuning experiments only
     if not os.path.exists(LIB_PATH):
         raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")

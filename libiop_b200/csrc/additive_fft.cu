@@ -31,6 +31,15 @@ namespace b200 {
 
 enum : uint32_t { OP_TW = 1, OP_TAY = 2, OP_BF = 3 };
 #define B200_MAX_OPS 160
+#ifndef B200_ILP
+#define B200_ILP 2
+#endif
+#ifndef B200_TILE_THREADS
+#define B200_TILE_THREADS 256
+#endif
+#ifndef B200_TILE_MINBLOCKS
+#define B200_TILE_MINBLOCKS 2
+#endif
 #define B200_SMEM_PAD 4 /* u64 words of padding between planes */
 #define B200_SUM_CHUNKS 4 /* 8-bit chunks of the butterfly index: stages up to 2^32 */
 
@@ -41,6 +50,7 @@ struct PassParams {
     const gf192 *sums;  /* [d][B200_SUM_CHUNKS][256] subset sums of the recursed bases */
     const gf192 *taus;  /* [(1 + n_extra)][d] recursed shifts: row 0 for the domain shift, 1+k for basis[d+k] */
     uint32_t d, lo, hi, c, ctop;
+    uint32_t cb;        /* log2(cosets per tile): small transforms pack several cosets into one CTA */
     uint32_t bitrev;    /* load src at bitrev_d(i) (out-of-place first butterfly pass) */
     uint32_t n_extra;
     uint32_t src_coset_stride_log; /* src advances by coset << this (use 32 for "shared source") */
@@ -104,48 +114,53 @@ __device__ __forceinline__ uint32_t insert_zero(uint32_t k, uint32_t pos)
 }
 
 template <bool INV>
-__global__ void __launch_bounds__(256) additive_tile_pass(const PassParams P)
+__global__ void __launch_bounds__(B200_TILE_THREADS, B200_TILE_MINBLOCKS) additive_tile_pass(const PassParams P)
 {
     extern __shared__ uint64_t smem[];
-    __shared__ gf192 tau_s[32];
 
     const uint32_t mainb = P.hi - P.lo;
-    const uint32_t tb = mainb + P.c + P.ctop;
+    const uint32_t tbw = mainb + P.c + P.ctop;              /* index bits of one coset inside the tile */
+    const uint32_t tb = tbw + P.cb;
     const uint32_t T = 1u << tb;
+    const uint32_t wmask = (1u << tbw) - 1u;
     Tile t;
     t.p0 = smem; t.p1 = smem + T + B200_SMEM_PAD; t.p2 = smem + 2 * (T + B200_SMEM_PAD);
+    gf192 *tau_s = reinterpret_cast<gf192 *>(smem + 3 * (T + B200_SMEM_PAD));   /* [2^cb][d] */
 
     const uint32_t d = P.d;
-    const uint32_t tilebits = d - tb;                       /* tiles per coset = 2^tilebits */
-    const uint32_t coset = blockIdx.x >> tilebits;
+    const uint32_t tilebits = d - tbw;                      /* tiles per coset = 2^tilebits */
+    const uint32_t coset_base = (blockIdx.x >> tilebits) << P.cb;
     const uint32_t tile = blockIdx.x & ((1u << tilebits) - 1u);
     const uint32_t midbits = P.lo - P.c;
     const uint32_t mid = tile & ((1u << midbits) - 1u);
     const uint32_t top = tile >> midbits;
 
-    /* recursed shift of this coset for every depth: F2-linear in the shift, so
+    /* recursed shift of each coset for every depth: F2-linear in the shift, so
        tau(shift + sum_k q_k basis[d+k]) = tau(shift) + sum_k q_k tau(basis[d+k]) */
-    if (threadIdx.x < d) {
-        gf192 v = ldg_elem(P.taus + threadIdx.x);
+    for (uint32_t e = threadIdx.x; e < (d << P.cb); e += blockDim.x) {
+        const uint32_t cl = e / d, dep = e - cl * d;
+        const uint32_t coset = coset_base + cl;
+        gf192 v = ldg_elem(P.taus + dep);
         for (uint32_t k = 0; k < P.n_extra; ++k)
-            if ((coset >> k) & 1u) gf_addto(v, ldg_elem(P.taus + (size_t)(1 + k) * d + threadIdx.x));
-        tau_s[threadIdx.x] = v;
+            if ((coset >> k) & 1u) gf_addto(v, ldg_elem(P.taus + (size_t)(1 + k) * d + dep));
+        tau_s[e] = v;
     }
 
-    const gf192 *src = P.src + (P.src_coset_stride_log < 32 ? ((size_t)coset << P.src_coset_stride_log) : 0);
-    gf192 *dst = P.dst + ((size_t)coset << d);
+    const bool shared_src = P.src_coset_stride_log >= 32;
 
     auto global_index = [&](uint32_t L) -> uint32_t {
-        const uint32_t w = L & ((1u << P.c) - 1u);
-        const uint32_t u = (L >> P.c) & ((1u << mainb) - 1u);
-        const uint32_t tbv = L >> (P.c + mainb);
+        const uint32_t Lw = L & wmask;
+        const uint32_t w = Lw & ((1u << P.c) - 1u);
+        const uint32_t u = (Lw >> P.c) & ((1u << mainb) - 1u);
+        const uint32_t tbv = Lw >> (P.c + mainb);
         return w | (mid << P.c) | (u << P.lo) | (top << P.hi) | (P.ctop ? (tbv << (d - P.ctop)) : 0u);
     };
 
     for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
-        t.st(L, ldg_elem(src + a));
+        const size_t cofs = shared_src ? 0 : ((size_t)(coset_base + (L >> tbw)) << P.src_coset_stride_log);
+        t.st(L, ldg_elem(P.src + cofs + a));
     }
 
     for (uint32_t o = 0; o < P.n_ops; ++o) {
@@ -154,9 +169,19 @@ __global__ void __launch_bounds__(256) additive_tile_pass(const PassParams P)
         if (kind == OP_TW) {
             /* twist at depth j = bit: S[i] *= beta_j^(i >> j)     (fft.tcc:61-70 / 190-200) */
             const gf192 *tab = P.tw + tw_offset(d, bit);
-            for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
-                const uint32_t e = global_index(L) >> bit;
-                if (e != 0) t.st(L, gf_mul(t.ld(L), ldg_elem(tab + e)));
+            for (uint32_t L = threadIdx.x; L < T; L += blockDim.x * B200_ILP) {
+                gf192 v[B200_ILP], f[B200_ILP];
+                bool act[B200_ILP];
+#pragma unroll
+                for (int u = 0; u < B200_ILP; ++u) {
+                    const uint32_t LL = L + u * blockDim.x;
+                    const uint32_t e = (LL < T) ? (global_index(LL) >> bit) : 0u;
+                    act[u] = e != 0;
+                    if (act[u]) { v[u] = t.ld(LL); f[u] = ldg_elem(tab + e); }
+                }
+#pragma unroll
+                for (int u = 0; u < B200_ILP; ++u)
+                    if (act[u]) t.st(L + u * blockDim.x, gf_mul(v[u], f[u]));
             }
         } else if (kind == OP_TAY) {
             /* radix conversion at linear stride 2^bit: [A B C D] -> [A, B+C+D, C+D, D] (fft.tcc:72-83),
@@ -172,35 +197,45 @@ __global__ void __launch_bounds__(256) additive_tile_pass(const PassParams P)
         } else { /* OP_BF: butterfly stage jj = bit, twiddle = tau + subset sum over index bits < jj */
             const uint32_t jj = bit, pos = jj - P.lo + P.c;
             const uint32_t depth = d - 1 - jj;
-            const gf192 tau = tau_s[depth];
             const gf192 *stab = P.sums + (size_t)jj * B200_SUM_CHUNKS * 256;
-            for (uint32_t k = threadIdx.x; k < (T >> 1); k += blockDim.x) {
-                const uint32_t L0 = insert_zero(k, pos), L1 = L0 | (1u << pos);
-                const uint32_t tix = global_index(L0) & ((1u << jj) - 1u);
-                gf192 tw = tau;
-                if (jj > 0) gf_addto(tw, ldg_elem(stab + (tix & 255u)));
-                if (jj > 8) gf_addto(tw, ldg_elem(stab + 256 + ((tix >> 8) & 255u)));
-                if (jj > 16) gf_addto(tw, ldg_elem(stab + 512 + ((tix >> 16) & 255u)));
-                if (jj > 24) gf_addto(tw, ldg_elem(stab + 768 + (tix >> 24)));
-                gf192 a = t.ld(L0), b = t.ld(L1);
-                if (!INV) {          /* fft.tcc:116-117 */
-                    gf_addto(a, gf_mul(b, tw));
-                    gf_addto(b, a);
-                } else {             /* fft.tcc:164-165 */
-                    gf_addto(b, a);
-                    gf_addto(a, gf_mul(b, tw));
+            for (uint32_t k = threadIdx.x; k < (T >> 1); k += blockDim.x * B200_ILP) {
+                gf192 a[B200_ILP], b[B200_ILP], tw[B200_ILP];
+                uint32_t L0[B200_ILP];
+                bool act[B200_ILP];
+#pragma unroll
+                for (int u = 0; u < B200_ILP; ++u) {
+                    const uint32_t kk = k + u * blockDim.x;
+                    act[u] = kk < (T >> 1);
+                    if (act[u]) {
+                        L0[u] = insert_zero(kk, pos);
+                        const uint32_t tix = global_index(L0[u]) & ((1u << jj) - 1u);
+                        tw[u] = tau_s[(L0[u] >> tbw) * d + depth];
+                        if (jj > 0) gf_addto(tw[u], ldg_elem(stab + (tix & 255u)));
+                        if (jj > 8) gf_addto(tw[u], ldg_elem(stab + 256 + ((tix >> 8) & 255u)));
+                        if (jj > 16) gf_addto(tw[u], ldg_elem(stab + 512 + ((tix >> 16) & 255u)));
+                        if (jj > 24) gf_addto(tw[u], ldg_elem(stab + 768 + (tix >> 24)));
+                        a[u] = t.ld(L0[u]); b[u] = t.ld(L0[u] | (1u << pos));
+                        if (INV) gf_addto(b[u], a[u]);            /* fft.tcc:164 */
+                    }
                 }
-                t.st(L0, a); t.st(L1, b);
+#pragma unroll
+                for (int u = 0; u < B200_ILP; ++u) {
+                    if (act[u]) {
+                        gf_addto(a[u], gf_mul(b[u], tw[u]));      /* fft.tcc:116 / 165 */
+                        if (!INV) gf_addto(b[u], a[u]);           /* fft.tcc:117 */
+                        t.st(L0[u], a[u]); t.st(L0[u] | (1u << pos), b[u]);
+                    }
+                }
             }
         }
     }
     __syncthreads();
 
-    uint64_t *out = reinterpret_cast<uint64_t *>(dst);
+    uint64_t *out = reinterpret_cast<uint64_t *>(P.dst);
     for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 2) ? (__brev(i) >> (32 - d)) : i;
-        uint64_t *q = out + (size_t)a * 3;
+        uint64_t *q = out + (((size_t)(coset_base + (L >> tbw)) << d) + a) * 3;
         q[0] = t.p0[L]; q[1] = t.p1[L]; q[2] = t.p2[L];
     }
 }
@@ -306,7 +341,7 @@ static void compute_taus(const AdditivePlan &pl, gf192 s, gf192 *out)
 
 /* ---------------------------------------------------------------------------------------------- */
 /* scheduler: pack consecutive steps into tile passes                                             */
-struct Pass { uint32_t lo, hi, c, ctop, bitrev; std::vector<uint32_t> ops; };
+struct Pass { uint32_t lo, hi, c, ctop, bitrev, cb = 0; std::vector<uint32_t> ops; };
 
 static const uint32_t kTileBits = 12;  /* 4096 elements = 96 KiB of shared memory, 2 CTAs per SM */
 static const uint32_t kCoalesceBits = 4; /* strided tiles keep runs of 16 elements = 384 B */
@@ -364,20 +399,21 @@ static std::vector<Pass> schedule(const std::vector<uint32_t> &steps, uint32_t d
 template <bool INV>
 static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uint32_t n_cosets)
 {
-    P.lo = p.lo; P.hi = p.hi; P.c = p.c; P.ctop = p.ctop; P.bitrev = p.bitrev; P.d = d;
+    P.lo = p.lo; P.hi = p.hi; P.c = p.c; P.ctop = p.ctop; P.bitrev = p.bitrev; P.d = d; P.cb = p.cb;
     P.n_ops = (uint32_t)p.ops.size();
     std::copy(p.ops.begin(), p.ops.end(), P.ops);
-    const uint32_t tb = (p.hi - p.lo) + p.c + p.ctop;
-    const size_t smem = 3 * (((size_t)1 << tb) + B200_SMEM_PAD) * sizeof(uint64_t);
+    const uint32_t tbw = (p.hi - p.lo) + p.c + p.ctop;
+    const uint32_t tb = tbw + p.cb;
+    const size_t smem = 3 * (((size_t)1 << tb) + B200_SMEM_PAD) * sizeof(uint64_t) + ((size_t)d << p.cb) * sizeof(gf192);
     static bool attr_set[2] = {false, false};
     if (!attr_set[INV]) {
         B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t))));
+                                          (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t) + 8192)));
         attr_set[INV] = true;
     }
-    const uint64_t nblocks = ((uint64_t)1 << (d - tb)) * n_cosets;
+    const uint64_t nblocks = ((uint64_t)1 << (d - tbw)) * (n_cosets >> p.cb);
     if (nblocks > 0x7fffffffull) return set_err(c, B200_ERR_INVALID, "grid too large");
-    additive_tile_pass<INV><<<(unsigned)nblocks, 256, smem, c->stream>>>(P);
+    additive_tile_pass<INV><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
     return 0;
 }
@@ -454,6 +490,10 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
     uint32_t first_hi = d <= tb ? d : tb - kCoalesceBits;
     {
         Pass p; p.lo = 0; p.hi = first_hi; p.c = 0; p.ctop = d <= tb ? 0 : kCoalesceBits; p.bitrev = 1;
+        if (d < kTileBits) {                      /* small transform: several cosets per CTA, tau table <= 8 KiB */
+            p.cb = std::min(kTileBits - d, m - d);
+            while (p.cb > 0 && ((size_t)d << p.cb) * sizeof(gf192) > 8192) --p.cb;
+        }
         for (uint32_t jj = 0; jj < first_hi; ++jj) p.ops.push_back((OP_BF << 8) | jj);
         P.src = X; P.dst = o; P.src_coset_stride_log = 32;
         rc = launch_pass<false>(c, p, P, d, n_cosets);

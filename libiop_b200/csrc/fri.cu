@@ -73,52 +73,66 @@ __global__ void __launch_bounds__(128) fold_additive_generic(const AddFoldParams
     dst[2] = (uint64_t)acc.w[4] | ((uint64_t)acc.w[5] << 32);
 }
 
-template <int ETA>
-__global__ void __launch_bounds__(128) fold_additive_kernel(const AddFoldParams P)
+/* eta = 1, 2: every quantity that depends on the coset is an F2-linear function of the coset offset
+   (z = x - v_0, z*c, (z^2 + b0 z)*c are additive in z), so it is rebuilt from per-basis-vector tables
+   with XORs only.
+     eta = 1:  P(x) = f0 + (f0 + f1) * t,                       t = z / b0                    (1 multiplication)
+     eta = 2:  with q(Z) = Z^2 + b0 Z, s = q(z)/q(b1), t = z/b0, c2 = b1/b0:
+               P(x) = A + t * B,  A = f0 + (f0 + f2 + c2 (f2+f3)) s,  B = (f0+f1) + (f0+f1+f2+f3) s   (4 multiplications) */
+struct AddFoldLinParams {
+    const gf192 *f;
+    gf192 *out;
+    gf192 t_tab[32];   /* t(basis[b]) for index bit b >= eta */
+    gf192 s_tab[32];   /* s(basis[b]) (eta = 2) */
+    gf192 t0, s0;      /* t(x - shift), s(x - shift) */
+    gf192 c2;          /* b1 / b0 (eta = 2) */
+    uint32_t m, eta;
+    size_t n_out;
+};
+
+__device__ __forceinline__ gf192 ld_elem(const gf192 *p)
 {
-    constexpr int S = 1 << ETA;
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(p);
+    const uint64_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    gf192 r;
+    r.w[0] = (uint32_t)a; r.w[1] = (uint32_t)(a >> 32);
+    r.w[2] = (uint32_t)b; r.w[3] = (uint32_t)(b >> 32);
+    r.w[4] = (uint32_t)c; r.w[5] = (uint32_t)(c >> 32);
+    return r;
+}
+__device__ __forceinline__ void st_elem(gf192 *p, const gf192 &v)
+{
+    uint64_t *dst = reinterpret_cast<uint64_t *>(p);
+    dst[0] = (uint64_t)v.w[0] | ((uint64_t)v.w[1] << 32);
+    dst[1] = (uint64_t)v.w[2] | ((uint64_t)v.w[3] << 32);
+    dst[2] = (uint64_t)v.w[4] | ((uint64_t)v.w[5] << 32);
+}
+
+__global__ void __launch_bounds__(256) fold_additive_eta1(const AddFoldLinParams P)
+{
     const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (j >= P.n_out) return;
-    /* a_0 = x - v_0, v_0 = shift + subset sum of basis over the bits of j << eta */
-    gf192 a0 = P.x_plus_shift;
-    for (uint32_t b = ETA; b < P.m; ++b)
-        if ((j >> (b - ETA)) & 1u) gf_addto(a0, P.basis[b]);
-    gf192 a[S], fv[S];
-    const uint64_t *src = reinterpret_cast<const uint64_t *>(P.f + j * S);
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-        a[k] = gf_add(a0, P.w[k]);
-        const uint64_t q0 = __ldg(src + 3 * k), q1 = __ldg(src + 3 * k + 1), q2 = __ldg(src + 3 * k + 2);
-        fv[k].w[0] = (uint32_t)q0; fv[k].w[1] = (uint32_t)(q0 >> 32);
-        fv[k].w[2] = (uint32_t)q1; fv[k].w[3] = (uint32_t)(q1 >> 32);
-        fv[k].w[4] = (uint32_t)q2; fv[k].w[5] = (uint32_t)(q2 >> 32);
-    }
-    /* N_k = prod_{k' != k} a_k' through prefix / suffix products */
-    gf192 acc = gf_zero();
-    if (S == 2) {
-        acc = gf_add(gf_mul(fv[0], a[1]), gf_mul(fv[1], a[0]));
-    } else {
-        gf192 pre[S], suf[S];
-        pre[0] = a[0];
-#pragma unroll
-        for (int k = 1; k < S; ++k) pre[k] = gf_mul(pre[k - 1], a[k]);
-        suf[S - 1] = a[S - 1];
-#pragma unroll
-        for (int k = S - 2; k >= 0; --k) suf[k] = gf_mul(suf[k + 1], a[k]);
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-            gf192 nk;
-            if (k == 0) nk = suf[1];
-            else if (k == S - 1) nk = pre[S - 2];
-            else nk = gf_mul(pre[k - 1], suf[k + 1]);
-            gf_addto(acc, gf_mul(fv[k], nk));
-        }
-    }
-    acc = gf_mul(acc, P.denom_inv);
-    uint64_t *dst = reinterpret_cast<uint64_t *>(P.out + j);
-    dst[0] = (uint64_t)acc.w[0] | ((uint64_t)acc.w[1] << 32);
-    dst[1] = (uint64_t)acc.w[2] | ((uint64_t)acc.w[3] << 32);
-    dst[2] = (uint64_t)acc.w[4] | ((uint64_t)acc.w[5] << 32);
+    gf192 t = P.t0;
+    for (uint32_t b = 1; b < P.m; ++b)
+        if ((j >> (b - 1)) & 1u) gf_addto(t, P.t_tab[b]);
+    const gf192 f0 = ld_elem(P.f + 2 * j), f1 = ld_elem(P.f + 2 * j + 1);
+    st_elem(P.out + j, gf_add(f0, gf_mul(gf_add(f0, f1), t)));
+}
+
+__global__ void __launch_bounds__(256) fold_additive_eta2(const AddFoldLinParams P)
+{
+    const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= P.n_out) return;
+    gf192 t = P.t0, s = P.s0;
+    for (uint32_t b = 2; b < P.m; ++b)
+        if ((j >> (b - 2)) & 1u) { gf_addto(t, P.t_tab[b]); gf_addto(s, P.s_tab[b]); }
+    const gf192 f0 = ld_elem(P.f + 4 * j), f1 = ld_elem(P.f + 4 * j + 1);
+    const gf192 f2 = ld_elem(P.f + 4 * j + 2), f3 = ld_elem(P.f + 4 * j + 3);
+    const gf192 f01 = gf_add(f0, f1), f23 = gf_add(f2, f3);
+    const gf192 a1 = gf_add(f2, gf_mul(f23, P.c2));                 /* A(q(b1)) */
+    const gf192 A = gf_add(f0, gf_mul(gf_add(f0, a1), s));
+    const gf192 B = gf_add(f01, gf_mul(gf_add(f01, f23), s));       /* b0 * B(q(z)) */
+    st_elem(P.out + j, gf_add(A, gf_mul(t, B)));
 }
 
 static int fold_additive(b200_ctx *c, const b200_domain *L, uint32_t eta, const uint64_t x[3], b200_buf f, b200_buf out)
@@ -144,11 +158,27 @@ static int fold_additive(b200_ctx *c, const b200_domain *L, uint32_t eta, const 
         prod = gf_mul(prod, P.w[v]);
     }
     P.denom_inv = gf_inv(prod);
-    const unsigned blocks = (unsigned)((P.n_out + 127) / 128);
-    switch (eta) {
-    case 1: fold_additive_kernel<1><<<blocks, 128, 0, c->stream>>>(P); break;
-    case 2: fold_additive_kernel<2><<<blocks, 128, 0, c->stream>>>(P); break;
-    default: fold_additive_generic<<<blocks, 128, 0, c->stream>>>(P); break;
+    if (eta <= 2) {
+        AddFoldLinParams Q; memset(&Q, 0, sizeof Q);
+        Q.f = P.f; Q.out = P.out; Q.m = m; Q.eta = eta; Q.n_out = P.n_out;
+        const gf192 b0 = P.basis[0];
+        const gf192 c0 = gf_inv(b0);
+        gf192 c1 = gf_zero();
+        if (eta == 2) {
+            const gf192 b1 = P.basis[1];
+            c1 = gf_inv(gf_add(gf_sqr(b1), gf_mul(b0, b1)));        /* 1 / q(b1) */
+            Q.c2 = gf_mul(b1, c0);
+        }
+        auto tfun = [&](const gf192 &z) { return gf_mul(z, c0); };
+        auto sfun = [&](const gf192 &z) { return gf_mul(gf_add(gf_sqr(z), gf_mul(b0, z)), c1); };
+        Q.t0 = tfun(P.x_plus_shift); Q.s0 = sfun(P.x_plus_shift);
+        for (uint32_t b = eta; b < m; ++b) { Q.t_tab[b] = tfun(P.basis[b]); Q.s_tab[b] = sfun(P.basis[b]); }
+        const unsigned blocks = (unsigned)((Q.n_out + 255) / 256);
+        if (eta == 1) fold_additive_eta1<<<blocks, 256, 0, c->stream>>>(Q);
+        else fold_additive_eta2<<<blocks, 256, 0, c->stream>>>(Q);
+    } else {
+        const unsigned blocks = (unsigned)((P.n_out + 127) / 128);
+        fold_additive_generic<<<blocks, 128, 0, c->stream>>>(P);
     }
     B200_LAUNCH_CHECK(c);
     return 0;
