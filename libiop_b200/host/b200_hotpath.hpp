@@ -1,0 +1,142 @@
+/*
+ * b200_hotpath.hpp — the reference's hot-path function templates, same names / argument order /
+ * by-value-by-reference conventions / element orderings / exceptions, forwarding to the C ABI:
+ *   FFT_over_field_subset, IFFT_over_field_subset, IFFT_of_known_degree_over_field_subset
+ *                                                  libiop/algebra/fft.hpp:62-88 (fft.tcc:407-475)
+ *   evaluate_next_f_i_over_entire_domain          libiop/protocols/ldt/fri/fri_aux.hpp:23-28 (fri_aux.tcc:6-34)
+ * The templates are generic over the field type and the domain type: anything with the reference's
+ * field_subset method names (type(), dimension(), num_elements(), basis(), shift(), generator(),
+ * get_subset_of_order()) works — libiop_b200::field_subset or libiop::field_subset itself — as long as
+ * field_traits<FieldT> is specialised (b200_fields.hpp; INTEGRATION.md for libff types).
+ */
+#ifndef LIBIOP_B200_HOTPATH_HPP_
+#define LIBIOP_B200_HOTPATH_HPP_
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "b200_device.hpp"
+#include "b200_fields.hpp"
+
+namespace libiop_b200 {
+
+/* flatten a field_subset-like object into the C ABI's b200_domain; `basis_store` keeps the limbs alive */
+template<typename FieldT, typename DomainT>
+b200_domain make_domain(const DomainT &domain, std::vector<uint64_t> &basis_store)
+{
+    b200_domain d;
+    std::memset(&d, 0, sizeof d);
+    d.dim = (uint32_t)domain.dimension();
+    const FieldT shift = domain.shift();
+    std::memcpy(d.shift, &shift, 24);
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        d.kind = B200_DOMAIN_AFFINE_SUBSPACE;
+        const std::vector<FieldT> &b = domain.basis();
+        basis_store.resize(3 * b.size() + 3);
+        if (!b.empty()) std::memcpy(basis_store.data(), b.data(), 24 * b.size());
+        d.basis = basis_store.data();
+    } else if ((int)domain.type() == B200_DOMAIN_MULTIPLICATIVE_COSET) {
+        d.kind = B200_DOMAIN_MULTIPLICATIVE_COSET;
+        const FieldT g = domain.generator();
+        std::memcpy(d.generator, &g, 24);
+    } else {
+        throw std::invalid_argument("field_subset type unsupported.");
+    }
+    return d;
+}
+
+/* fft.hpp:62-68.  Device-resident variant first (what a device-aware prover calls), host vectors below. */
+template<typename FieldT, typename DomainT>
+void FFT_over_field_subset_device(const device_buffer &coeffs, std::size_t n_coeffs, const DomainT &domain, device_buffer &evals_out)
+{
+    std::vector<uint64_t> store;
+    const b200_domain d = make_domain<FieldT>(domain, store);
+    int rc;
+    if (field_traits<FieldT>::kind == B200_FIELD_GF192) rc = b200_gf192_fft(context(), &d, coeffs.get(), n_coeffs, evals_out.get());
+    else rc = b200_fp_ntt(context(), field_traits<FieldT>::fp(), &d, coeffs.get(), n_coeffs, evals_out.get());
+    throw_status(context(), rc);
+}
+
+template<typename FieldT, typename DomainT>
+void IFFT_over_field_subset_device(const device_buffer &evals, const DomainT &domain, device_buffer &coeffs_out)
+{
+    std::vector<uint64_t> store;
+    const b200_domain d = make_domain<FieldT>(domain, store);
+    int rc;
+    if (field_traits<FieldT>::kind == B200_FIELD_GF192) rc = b200_gf192_ifft(context(), &d, evals.get(), coeffs_out.get());
+    else rc = b200_fp_intt(context(), field_traits<FieldT>::fp(), &d, evals.get(), coeffs_out.get());
+    throw_status(context(), rc);
+}
+
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, DomainT domain)
+{
+    if (coeffs.size() > domain.num_elements())
+        throw std::invalid_argument("FFT_over_field_subset: more coefficients than domain elements");
+    device_buffer in(coeffs.size()), out(domain.num_elements());
+    in.upload(coeffs);
+    FFT_over_field_subset_device<FieldT>(in, coeffs.size(), domain, out);
+    return out.template download<FieldT>(domain.num_elements());
+}
+
+/* fft.hpp:70-76 */
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> IFFT_over_field_subset(const std::vector<FieldT> evals, DomainT domain)
+{
+    if (evals.size() != domain.num_elements())
+        throw std::invalid_argument("IFFT_over_field_subset: evaluation vector does not match the domain");
+    if (evals.size() == 1) return evals;           /* fft.tcc:397-401 */
+    device_buffer in(evals.size()), out(evals.size());
+    in.upload(evals);
+    IFFT_over_field_subset_device<FieldT>(in, domain, out);
+    return out.template download<FieldT>(evals.size());
+}
+
+/* fft.hpp:78-88 (fft.tcc:435-475): additive -> first 2^k evaluations over the first k basis vectors,
+   multiplicative -> every (n/2^k)-th evaluation over the order-2^k sub-coset */
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> IFFT_of_known_degree_over_field_subset(const std::vector<FieldT> evals, std::size_t degree, DomainT domain)
+{
+    std::size_t closest_power_of_two = 1;
+    while (closest_power_of_two < degree) closest_power_of_two <<= 1;
+    const DomainT minimal = domain.get_subset_of_order(closest_power_of_two);
+    std::vector<FieldT> sub;
+    sub.reserve(closest_power_of_two);
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        sub.insert(sub.end(), evals.begin(), evals.begin() + closest_power_of_two);
+    } else {
+        const std::size_t freq = domain.num_elements() / closest_power_of_two;
+        for (std::size_t i = 0; i < domain.num_elements(); i += freq) sub.emplace_back(evals[i]);
+    }
+    return IFFT_over_field_subset<FieldT>(sub, minimal);
+}
+
+/* fri_aux.hpp:23-28 */
+template<typename FieldT, typename DomainT>
+void evaluate_next_f_i_over_entire_domain_device(const device_buffer &f_i, const DomainT &f_i_domain, std::size_t coset_size,
+                                                 const FieldT x_i, device_buffer &f_next_out)
+{
+    std::vector<uint64_t> store;
+    const b200_domain d = make_domain<FieldT>(f_i_domain, store);
+    uint32_t eta = 0;
+    while ((std::size_t(1) << eta) < coset_size) ++eta;
+    uint64_t x[3];
+    std::memcpy(x, &x_i, 24);
+    throw_status(context(), b200_fri_fold(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), &d, eta, x,
+                                          f_i.get(), f_next_out.get()));
+}
+
+template<typename FieldT, typename DomainT>
+std::shared_ptr<std::vector<FieldT>> evaluate_next_f_i_over_entire_domain(
+    const std::shared_ptr<std::vector<FieldT>> &f_i_evals, const DomainT &f_i_domain, const std::size_t coset_size, const FieldT x_i)
+{
+    const std::size_t n = f_i_evals->size();
+    device_buffer in(n), out(n / coset_size);
+    in.upload(*f_i_evals);
+    evaluate_next_f_i_over_entire_domain_device<FieldT>(in, f_i_domain, coset_size, x_i, out);
+    return std::make_shared<std::vector<FieldT>>(out.template download<FieldT>(n / coset_size));
+}
+
+} // namespace libiop_b200
+#endif

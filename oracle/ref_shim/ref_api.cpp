@@ -33,6 +33,12 @@
 #include "libiop/snark/aurora_snark.hpp"
 #include "libiop/relations/examples/r1cs_examples.hpp"
 
+#ifdef B200_GPU_INTEGRATION
+#define REFN(name) refgpu_##name
+#else
+#define REFN(name) ref_##name
+#endif
+
 using namespace libiop;
 typedef libff::gf192 G;
 typedef libff::edwards_Fr Fr;
@@ -67,7 +73,7 @@ public:
 
 extern "C" {
 
-void ref_init(void)
+void REFN(init)(void)
 {
     static bool done = false;
     if (!done) { libff::edwards_pp::init_public_params(); done = true; }
@@ -75,45 +81,45 @@ void ref_init(void)
     libff::inhibit_profiling_counters = true;
 }
 
-void ref_seed(uint64_t seed) { b200_shim_randombytes_seed(seed); }
+void REFN(seed)(uint64_t seed) { b200_shim_randombytes_seed(seed); }
 
 /* ---- field ops ---- */
-void ref_gf192_mul(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
+void REFN(gf192_mul)(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         G r = el_from<G>(a + 3 * i) * el_from<G>(b + 3 * i);
         std::memcpy(out + 3 * i, &r, 24);
     }
 }
-void ref_gf192_inv(uint64_t *out, const uint64_t *a, size_t n)
+void REFN(gf192_inv)(uint64_t *out, const uint64_t *a, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         G r = el_from<G>(a + 3 * i).inverse();
         std::memcpy(out + 3 * i, &r, 24);
     }
 }
-void ref_fp_mul(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
+void REFN(fp_mul)(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         Fr r = el_from<Fr>(a + 3 * i) * el_from<Fr>(b + 3 * i);
         std::memcpy(out + 3 * i, &r, 24);
     }
 }
-void ref_fp_add(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
+void REFN(fp_add)(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         Fr r = el_from<Fr>(a + 3 * i) + el_from<Fr>(b + 3 * i);
         std::memcpy(out + 3 * i, &r, 24);
     }
 }
-void ref_fp_sub(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
+void REFN(fp_sub)(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         Fr r = el_from<Fr>(a + 3 * i) - el_from<Fr>(b + 3 * i);
         std::memcpy(out + 3 * i, &r, 24);
     }
 }
-void ref_fp_inv(uint64_t *out, const uint64_t *a, size_t n)
+void REFN(fp_inv)(uint64_t *out, const uint64_t *a, size_t n)
 {
     for (size_t i = 0; i < n; ++i) {
         Fr r = el_from<Fr>(a + 3 * i).inverse();
@@ -121,14 +127,14 @@ void ref_fp_inv(uint64_t *out, const uint64_t *a, size_t n)
     }
 }
 /* Montgomery limbs of the small integer v, of the multiplicative generator, of the subgroup generator */
-void ref_fp_from_u64(uint64_t *out, uint64_t v) { Fr r(v); std::memcpy(out, &r, 24); }
-void ref_fp_generator(uint64_t *out) { Fr r = Fr::multiplicative_generator; std::memcpy(out, &r, 24); }
-void ref_fp_subgroup_generator(uint64_t *out, uint32_t logn)
+void REFN(fp_from_u64)(uint64_t *out, uint64_t v) { Fr r(v); std::memcpy(out, &r, 24); }
+void REFN(fp_generator)(uint64_t *out) { Fr r = Fr::multiplicative_generator; std::memcpy(out, &r, 24); }
+void REFN(fp_subgroup_generator)(uint64_t *out, uint32_t logn)
 {
     multiplicative_subgroup<Fr> s((size_t)1 << logn);
     Fr r = s.generator(); std::memcpy(out, &r, 24);
 }
-void ref_fp_params(uint64_t *mod, uint64_t *r2, uint64_t *inv, uint32_t *s)
+void REFN(fp_params)(uint64_t *mod, uint64_t *r2, uint64_t *inv, uint32_t *s)
 {
     std::memcpy(mod, Fr::mod.data, 24);
     std::memcpy(r2, Fr::Rsquared.data, 24);
@@ -142,34 +148,34 @@ static field_subset<G> make_subspace(uint32_t m, const uint64_t *basis, const ui
     return field_subset<G>(affine_subspace<G>(b, el_from<G>(shift)));
 }
 
-void ref_additive_fft(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs,
+void REFN(additive_fft)(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs,
                       uint32_t m, const uint64_t *basis, const uint64_t *shift)
 {
     vec_to(out, FFT_over_field_subset<G>(vec_from<G>(coeffs, n_coeffs), make_subspace(m, basis, shift)));
 }
-void ref_additive_ifft(uint64_t *out, const uint64_t *evals,
+void REFN(additive_ifft)(uint64_t *out, const uint64_t *evals,
                        uint32_t m, const uint64_t *basis, const uint64_t *shift)
 {
     vec_to(out, IFFT_over_field_subset<G>(vec_from<G>(evals, (size_t)1 << m), make_subspace(m, basis, shift)));
 }
-void ref_naive_fft_gf192(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs,
+void REFN(naive_fft_gf192)(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs,
                          uint32_t m, const uint64_t *basis, const uint64_t *shift)
 {
     vec_to(out, naive_FFT<G>(vec_from<G>(coeffs, n_coeffs), make_subspace(m, basis, shift)));
 }
-void ref_mult_fft(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs, uint32_t logn, const uint64_t *shift)
+void REFN(mult_fft)(uint64_t *out, const uint64_t *coeffs, size_t n_coeffs, uint32_t logn, const uint64_t *shift)
 {
     field_subset<Fr> dom((size_t)1 << logn, el_from<Fr>(shift));
     vec_to(out, FFT_over_field_subset<Fr>(vec_from<Fr>(coeffs, n_coeffs), dom));
 }
-void ref_mult_ifft(uint64_t *out, const uint64_t *evals, uint32_t logn, const uint64_t *shift)
+void REFN(mult_ifft)(uint64_t *out, const uint64_t *evals, uint32_t logn, const uint64_t *shift)
 {
     field_subset<Fr> dom((size_t)1 << logn, el_from<Fr>(shift));
     vec_to(out, IFFT_over_field_subset<Fr>(vec_from<Fr>(evals, (size_t)1 << logn), dom));
 }
 
 /* ---- FRI fold ---- */
-void ref_fri_fold_additive(uint64_t *out, const uint64_t *f, uint32_t m, const uint64_t *basis,
+void REFN(fri_fold_additive)(uint64_t *out, const uint64_t *f, uint32_t m, const uint64_t *basis,
                            const uint64_t *shift, uint32_t eta, const uint64_t *x)
 {
     auto fi = std::make_shared<std::vector<G>>(vec_from<G>(f, (size_t)1 << m));
@@ -177,7 +183,7 @@ void ref_fri_fold_additive(uint64_t *out, const uint64_t *f, uint32_t m, const u
                                                      (size_t)1 << eta, el_from<G>(x));
     vec_to(out, *r);
 }
-void ref_fri_fold_mult(uint64_t *out, const uint64_t *f, uint32_t logn,
+void REFN(fri_fold_mult)(uint64_t *out, const uint64_t *f, uint32_t logn,
                        const uint64_t *shift, uint32_t eta, const uint64_t *x)
 {
     auto fi = std::make_shared<std::vector<Fr>>(vec_from<Fr>(f, (size_t)1 << logn));
@@ -209,7 +215,7 @@ static void merkle_build(uint8_t *nodes_out, uint8_t *salts_out, const uint64_t 
     }
 }
 extern "C" {
-void ref_merkle_build(uint8_t *nodes_out, uint8_t *salts_out, const uint64_t *const *oracles,
+void REFN(merkle_build)(uint8_t *nodes_out, uint8_t *salts_out, const uint64_t *const *oracles,
                       size_t n_oracles, size_t n_elems, size_t coset, int field_kind, int zk, size_t security)
 {
     if (field_kind == 2) merkle_build<Fr>(nodes_out, salts_out, oracles, n_oracles, n_elems, coset, zk, security);
@@ -217,7 +223,7 @@ void ref_merkle_build(uint8_t *nodes_out, uint8_t *salts_out, const uint64_t *co
 }
 
 /* ---- hashchain ---- */
-void ref_hashchain_demo(uint64_t *squeezed /*2 elems*/, uint64_t *positions /*3*/, const uint8_t *absorbed32)
+void REFN(hashchain_demo)(uint64_t *squeezed /*2 elems*/, uint64_t *positions /*3*/, const uint8_t *absorbed32)
 {
     blake2b_hashchain<G, binary_hash_digest> hc(128);
     hc.absorb(binary_hash_digest((const char *)absorbed32, 32));
@@ -260,10 +266,10 @@ extern "C" {
 /* Runs generate_r1cs_example<gf192>(2^log_n, k, 2^log_n - 1) with the deterministic RNG seeded by
    `seed`, then aurora_snark_prover (+verifier if verify != 0).  Returns prover seconds; writes the
    canonical dump into buf (up to cap bytes) and its length into *len; *accepted = verifier bit. */
-double ref_aurora_gf192(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
+double REFN(aurora_gf192)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
                         uint64_t seed, int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)
 {
-    ref_init();
+    REFN(init)();
     b200_shim_randombytes_seed(seed);
     const size_t n = (size_t)1 << log_n;
     r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, n - 1);

@@ -218,18 +218,29 @@ class Oracle:
 
 
 class Reference:
-    """The unmodified reference (oracle/_ref/libiopref.so), when present."""
+    """The unmodified reference (oracle/_ref/libiopref.so), when present.
+    With gpu=True: the same reference prover built with the B200 adapter shadowing its three hot-path
+    headers (oracle/_ref/libiopref_gpu.so, `make -C oracle refgpu`) — the drop-in integration build."""
+    PREFIX = "ref_"
+    LIBNAME = "libiopref.so"
 
-    @staticmethod
-    def path():
-        return os.path.join(ORACLE_DIR, "_ref", "libiopref.so")
+    @classmethod
+    def path(cls):
+        return os.path.join(ORACLE_DIR, "_ref", cls.LIBNAME)
 
-    @staticmethod
-    def available():
-        return os.path.exists(Reference.path())
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.path())
 
     def __init__(self):
-        self.lib = C.CDLL(Reference.path())
+        real = C.CDLL(self.path())
+        prefix = self.PREFIX
+
+        class _Renamed:
+            def __getattr__(self, name):
+                return getattr(real, prefix + name[4:]) if name.startswith("ref_") else getattr(real, name)
+        self.lib = _Renamed()
+        self._real = real
         self.lib.ref_init()
         self.lib.ref_aurora_gf192.restype = C.c_double
 
@@ -349,3 +360,9 @@ class Reference:
                                          C.c_int(int(verify)), _b(buf), C.c_size_t(cap),
                                          C.byref(ln), C.byref(acc))
         return secs, buf[:ln.value].tobytes(), acc.value
+
+
+class ReferenceGpu(Reference):
+    """Reference prover + B200 drop-in (needs a CUDA device at call time)."""
+    PREFIX = "refgpu_"
+    LIBNAME = "libiopref_gpu.so"
