@@ -248,6 +248,117 @@ __global__ void __launch_bounds__(1024) merkle_top_kernel(uint64_t *nodes, size_
     }
 }
 
+
+/* ---------------------------------------------------------------------------------------------- */
+/* fast path (32-byte digests): one thread owns 8 consecutive leaves / nodes and the 3 levels above
+   them (15 / 7 compressions, all lanes busy, no shared memory).                                  */
+__device__ __forceinline__ void two_to_one_32(uint64_t out[4], const uint64_t l[4], const uint64_t r[4])
+{
+    uint64_t h[8];
+    blake2b_init(h, 32);
+    uint64_t m[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { m[t] = l[t]; m[4 + t] = r[t]; }
+#pragma unroll
+    for (int t = 8; t < 16; ++t) m[t] = 0;
+    blake2b_compress(h, m, 64, true);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) out[t] = h[t];
+}
+
+__device__ __forceinline__ void store_digest32(uint64_t *nodes, size_t heap_index, const uint64_t d[4])
+{
+    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(nodes + heap_index * 4);
+    p[0] = make_ulonglong2(d[0], d[1]);
+    p[1] = make_ulonglong2(d[2], d[3]);
+}
+
+/* reduce 8 digests held in registers through three levels; `width` = nodes of the level of d[],
+   `first` = index of d[0] within that level */
+__device__ __forceinline__ void reduce8_32(uint64_t *nodes, uint64_t d[8][4], size_t width, size_t first)
+{
+    uint64_t e[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { two_to_one_32(e[q], d[2 * q], d[2 * q + 1]); store_digest32(nodes, (width >> 1) - 1 + (first >> 1) + q, e[q]); }
+    uint64_t f[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { two_to_one_32(f[q], e[2 * q], e[2 * q + 1]); store_digest32(nodes, (width >> 2) - 1 + (first >> 2) + q, f[q]); }
+    uint64_t g[4];
+    two_to_one_32(g, f[0], f[1]);
+    store_digest32(nodes, (width >> 3) - 1 + (first >> 3), g);
+}
+
+__global__ void __launch_bounds__(128) merkle_leaf8_kernel(const LeafParams P)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t * 8 >= P.leaves) return;
+    uint64_t d[8][4];
+    const size_t n_words = (size_t)3 * P.n_oracles * P.coset;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        const size_t i = t * 8 + q;
+        uint64_t h[8];
+        blake2b_init(h, 32);
+        /* stream the slice: for oracle k, for j < coset, 3 limbs (uniform control flow across the warp) */
+        uint32_t k = 0, j = 0, limb = 0;
+        const uint64_t *base = P.oracle_table ? P.oracle_table[0] : P.oracles[0];
+        size_t pos = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? i : i * P.coset;
+        const size_t jstep = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? P.leaves : 1;
+        size_t done = 0;
+        for (;;) {
+            const size_t remaining = n_words - done;
+            const bool last = remaining <= 16;
+            uint64_t m[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                uint64_t v = 0;
+                if ((size_t)w < remaining) {
+                    v = __ldg(base + (pos + (size_t)j * jstep) * 3 + limb);
+                    if (++limb == 3) {
+                        limb = 0;
+                        if (++j == P.coset) { j = 0; ++k; if (k < P.n_oracles) base = P.oracle_table ? P.oracle_table[k] : P.oracles[k]; }
+                    }
+                }
+                m[w] = v;
+            }
+            done += last ? remaining : 16;
+            blake2b_compress(h, m, (uint64_t)done * 8, last);
+            if (last) break;
+        }
+        if (P.salts) {                                  /* zk: H(H(leaf) || salt)  (blake2b.tcc:127-136) */
+            const uint64_t *salt = P.salts + i * P.salt_words;
+            uint64_t m[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                uint64_t v = 0;
+                if (w < 4) v = h[w];
+                else if ((uint32_t)(w - 4) < P.salt_words) v = salt[w - 4];
+                m[w] = v;
+            }
+            blake2b_init(h, 32);
+            blake2b_compress(h, m, (uint64_t)(4 + P.salt_words) * 8, true);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) d[q][w] = h[w];
+        store_digest32(P.nodes, P.leaves - 1 + i, h);
+    }
+    reduce8_32(P.nodes, d, P.leaves, t * 8);
+}
+
+__global__ void __launch_bounds__(128) merkle_reduce8_kernel(uint64_t *nodes, size_t width)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t * 8 >= width) return;
+    uint64_t d[8][4];
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(nodes + (width - 1 + t * 8) * 4);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 a = src[2 * q], b = src[2 * q + 1];
+        d[q][0] = a.x; d[q][1] = a.y; d[q][2] = b.x; d[q][3] = b.y;
+    }
+    reduce8_32(nodes, d, width, t * 8);
+}
+
 int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset,
                  int kind, const uint8_t *salts, size_t salt_len, size_t digest_len, b200_bytes nodes)
 {
@@ -282,21 +393,33 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
         B200_CUDA(c, cudaMemcpyAsync(ds, salts, leaves * salt_len, cudaMemcpyHostToDevice, c->stream));
         P.salts = (const uint64_t *)ds; P.salt_words = (uint32_t)(salt_len / 8);
     }
-    /* fused levels: a CTA of 256 leaves owns 8 levels above them */
-    uint32_t fused = 0;
-    while (fused < 8 && (leaves >> (fused + 1)) >= 1 && (MERKLE_CTA >> (fused + 1)) >= 1 && ((size_t)MERKLE_CTA <= leaves)) ++fused;
-    if (leaves < MERKLE_CTA) fused = 0;
-    P.fused_levels = fused;
-    const unsigned blocks = (unsigned)((leaves + MERKLE_CTA - 1) / MERKLE_CTA);
-    merkle_leaf_kernel<<<blocks, MERKLE_CTA, 0, c->stream>>>(P);
-    B200_LAUNCH_CHECK(c);
-    /* remaining levels */
-    size_t width = leaves >> fused;   /* nodes in the highest level already computed */
-    while (width > 2048) {
-        const size_t count = width >> 1, first = count - 1;
-        merkle_level_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(P.nodes, first, count, P.digest_words, P.digest_len);
+    size_t width;   /* nodes in the highest level already computed */
+    if (digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
+        /* fast path: 8 leaves + 3 levels per thread, then 3 levels per launch */
+        const size_t threads = leaves / 8;
+        merkle_leaf8_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(P);
         B200_LAUNCH_CHECK(c);
-        width = count;
+        width = leaves >> 3;
+        while (width > 2048) {
+            const size_t th = width / 8;
+            merkle_reduce8_kernel<<<(unsigned)((th + 127) / 128), 128, 0, c->stream>>>(P.nodes, width);
+            B200_LAUNCH_CHECK(c);
+            width >>= 3;
+        }
+    } else {
+        /* generic path: a CTA of 256 leaves owns the 8 levels above them */
+        uint32_t fused = (leaves >= MERKLE_CTA) ? 8 : 0;
+        P.fused_levels = fused;
+        const unsigned blocks = (unsigned)((leaves + MERKLE_CTA - 1) / MERKLE_CTA);
+        merkle_leaf_kernel<<<blocks, MERKLE_CTA, 0, c->stream>>>(P);
+        B200_LAUNCH_CHECK(c);
+        width = leaves >> fused;
+        while (width > 2048) {
+            const size_t count = width >> 1, first = count - 1;
+            merkle_level_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(P.nodes, first, count, P.digest_words, P.digest_len);
+            B200_LAUNCH_CHECK(c);
+            width = count;
+        }
     }
     if (width > 1) {
         merkle_top_kernel<<<1, 1024, 0, c->stream>>>(P.nodes, width, P.digest_words, P.digest_len);
