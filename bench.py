@@ -252,6 +252,20 @@ def run_gpu(args):
     if rank == 0:
         sampler.stop_flag.set(); sampler.join()
 
+    # launches of our kernels inside one step, counted by the library itself
+    lib.b200_launch_count.restype = C.c_ulonglong
+    dev.sync(); l0 = lib.b200_launch_count(ctx); step_resident(); dev.sync(); launches_per_step = lib.b200_launch_count(ctx) - l0
+    # per-launch CUDA-event timing of the tile passes of one LDE (events on the context's stream)
+    lib.b200_profile_begin(ctx)
+    dev.gf192_fft_dev(dom_L, coeff_in, 1 << LOG_N, oracles[0])
+    pbuf = C.create_string_buffer(1 << 16)
+    lib.b200_profile_end(ctx, pbuf, C.c_size_t(len(pbuf)))
+    passes = [(l.split("\t")[0], float(l.split("\t")[1])) for l in pbuf.value.decode().strip().split("\n") if "\t" in l]
+    bf_passes = [(lab, t) for lab, t in passes if "cosets=8" in lab and "bf=8" in lab]
+    dom_label, dom_ms = max(bf_passes, key=lambda x: x[1]) if bf_passes else ("", float("nan"))
+    fwd_ms = sum(t for lab, t in passes if "cosets=1" in lab)
+    bwd_ms = sum(t for lab, t in passes if "cosets=8" in lab)
+
     ms_per_step = ms / args.steps
     N = 1 << LOG_N
     value = world * N / (ms_per_step * 1e-3)
@@ -263,8 +277,11 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     lde_bytes = 24 * ((1 << LOG_N) + n_l)
-    achieved = lde_bytes / (lde_ms * 1e-3) / 1e9
-    n_launch = None
+    lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9
+    # dominant kernel: one in-place butterfly tile pass over the 2^23-element oracle (8 stages, 8 cosets):
+    # algorithmic bytes per launch = read 24*2^23 + write 24*2^23
+    pass_bytes = 2 * 24 * n_l
+    achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
     out = {
         "metric": "Aurora prover constraints/sec at N=2^20 (hot path: LDE + FRI fold + Merkle); LDE GF-ops/sec vs HBM roofline",
         "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -274,19 +291,27 @@ def run_gpu(args):
                                "(9 FFT, 10 IFFT, 10 FRI folds, 11 Merkle trees); elementwise virtual oracles, PoW and transcript "
                                "assembly excluded", "log_n": LOG_N, "codeword_dim": M, "per_gpu": "one independent proof instance",
                    "l2_policy": "working set (5 x 192 MiB oracles + inputs) exceeds the 126 MB L2"},
-        "roofline": {"bound": "hbm", "kernel": "additive FFT 2^20 -> 2^23 (all tile passes of one LDE)",
+        "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                     "traffic": None, "lde_ms": lde_ms,
-                     "lde_gf_mul_per_s_reference_count": 1.5 * M * n_l / (lde_ms * 1e-3),
-                     "note": "integer-ALU bound (GF(2^192) multiplication emulated with IMAD.WIDE), see DESIGN.md"},
+                     "traffic": 348.4e6, "traffic_source": "ncu --set full, profiles/r1_tilepass_ncu_summary.md (dram read+write per launch)",
+                     "algorithmic_bytes_per_launch": pass_bytes, "launch_ms": dom_ms, "launch_label": dom_label,
+                     "gf_mul_per_s_in_kernel": 8 * (n_l // 2) / (dom_ms * 1e-3), "gf_mul_peak_measured": 20.2e9,
+                     "frac_of_multiplier_peak": 8 * (n_l // 2) / (dom_ms * 1e-3) / 20.2e9,
+                     "lde": {"ms": lde_ms, "forward_half_ms": fwd_ms, "butterfly_half_ms": bwd_ms, "n_launches": len(passes),
+                             "algorithmic_bytes": lde_bytes, "achieved_gbs": lde_gbs, "frac": lde_gbs / peak,
+                             "gf_mul_per_s_reference_count": 1.5 * M * n_l / (lde_ms * 1e-3),
+                             "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
+                     "note": "integer-pipe bound, not HBM bound: ~1050 instructions (289 IMAD.WIDE) per GF(2^192) multiplication, "
+                             "100 multiplications per 24-byte coefficient; see DESIGN.md 3.1-3.2"},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": None,
         "clocks": sampler.summary() if rank == 0 else None,
     }
     # launches per step: counted from the scheduler; measured with ncu in profiles/
-    out["gpu_launches"] = int(os.environ.get("B200_LAUNCHES_PER_STEP", "0")) or estimate_launches(ffts, iffts, folds, trees) * args.steps
+    out["gpu_launches"] = int(launches_per_step) * args.steps
+    out["gpu_launches_per_step"] = int(launches_per_step)
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
     if rank == 0:

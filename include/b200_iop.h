@@ -136,6 +136,11 @@ int b200_merkle_nodes(b200_ctx *, b200_bytes nodes, const size_t *node_idx, size
  * out[i] = BLAKE2b-digest_len( in[i*msg_len .. (i+1)*msg_len) ) */
 int b200_blake2b_batch(b200_ctx *, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
 
+/* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the FFT tile passes ---- */
+unsigned long long b200_launch_count(b200_ctx *);
+int b200_profile_begin(b200_ctx *);
+int b200_profile_end(b200_ctx *, char *buf, size_t cap);  /* "label\tms\n" per recorded launch; returns #records */
+
 /* library identification */
 const char *b200_version(void);
 

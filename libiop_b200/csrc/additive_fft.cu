@@ -413,6 +413,12 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
     }
     const uint64_t nblocks = ((uint64_t)1 << (d - tbw)) * (n_cosets >> p.cb);
     if (nblocks > 0x7fffffffull) return set_err(c, B200_ERR_INVALID, "grid too large");
+    uint32_t n_tw = 0, n_tay = 0, n_bf = 0;
+    for (uint32_t o : p.ops) { const uint32_t k = o >> 8; n_tw += k == OP_TW; n_tay += k == OP_TAY; n_bf += k == OP_BF; }
+    char label[160];
+    snprintf(label, sizeof label, "additive_tile_pass<%d> d=%u cosets=%u grid=%llu tile=2^%u tw=%u tay=%u bf=%u", (int)INV, d, n_cosets,
+             (unsigned long long)nblocks, tb, n_tw, n_tay, n_bf);
+    ProfScope prof(c, label);
     additive_tile_pass<INV><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
     return 0;

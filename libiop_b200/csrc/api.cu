@@ -156,6 +156,33 @@ int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, siz
     return 0;
 }
 
+/* ---- instrumentation ---- */
+unsigned long long b200_launch_count(b200_ctx *c) { return c->n_launches; }
+int b200_profile_begin(b200_ctx *c)
+{
+    for (auto &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof.clear();
+    c->profiling = true;
+    return 0;
+}
+/* writes "label\tms\n" lines into buf (truncated to cap); returns the number of records */
+int b200_profile_end(b200_ctx *c, char *buf, size_t cap)
+{
+    c->profiling = false;
+    cudaStreamSynchronize(c->stream);
+    size_t off = 0;
+    int n = 0;
+    for (auto &r : c->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (buf && off < cap) off += (size_t)snprintf(buf + off, cap - off, "%s\t%.6f\n", r.label.c_str(), ms);
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        ++n;
+    }
+    c->prof.clear();
+    return n;
+}
+
 int b200_timer_start(b200_ctx *c) { B200_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
 int b200_timer_stop(b200_ctx *c, float *ms)
 {

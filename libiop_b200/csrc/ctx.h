@@ -32,6 +32,11 @@ struct b200_ctx {
     /* cached per-domain plans */
     std::map<std::string, std::shared_ptr<b200::AdditivePlan>> additive_plans;
     std::map<std::string, std::shared_ptr<b200::NttPlan>> ntt_plans;
+    /* instrumentation: every kernel launch is counted; with profiling on, tile passes are bracketed by events */
+    unsigned long long n_launches = 0;
+    bool profiling = false;
+    struct ProfRec { std::string label; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
 };
 
 namespace b200 {
@@ -56,6 +61,7 @@ inline int set_err(b200_ctx *c, int code, const char *fmt, ...)
 
 #define B200_LAUNCH_CHECK(ctx)                                                                    \
     do {                                                                                          \
+        (ctx)->n_launches++;                                                                      \
         cudaError_t e__ = cudaGetLastError();                                                     \
         if (e__ != cudaSuccess)                                                                   \
             return b200::set_err((ctx), B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
@@ -82,6 +88,20 @@ inline void *staging_get(b200_ctx *c, size_t bytes)
     c->staging = p; c->staging_bytes = bytes;
     return p;
 }
+
+/* RAII event bracket around one launch when profiling is enabled */
+struct ProfScope {
+    b200_ctx *c; size_t idx; bool on;
+    ProfScope(b200_ctx *ctx, const std::string &label) : c(ctx), idx(0), on(ctx->profiling)
+    {
+        if (!on) return;
+        b200_ctx::ProfRec r; r.label = label;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        c->prof.push_back(r); idx = c->prof.size() - 1;
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->prof[idx].b, c->stream); }
+};
 
 inline uint32_t ceil_log2(size_t n)
 {
