@@ -31,6 +31,8 @@
 #include "libiop/bcs/hashing/hash_enum.hpp"
 #include "libiop/bcs/pow.hpp"
 #include "libiop/snark/aurora_snark.hpp"
+#include "libiop/snark/fractal_snark.hpp"
+#include "libiop/snark/ligero_snark.hpp"
 #include "libiop/relations/examples/r1cs_examples.hpp"
 
 #ifdef B200_GPU_INTEGRATION
@@ -291,6 +293,127 @@ double REFN(aurora_gf192)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32
             *accepted = aurora_snark_verifier<G, binary_hash_digest>(
                 ex.constraint_system_, ex.primary_input_, proof, params) ? 1 : 0;
     }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+} /* extern "C" */
+
+/* ---- deterministic R1CS instances for both field kinds ----------------------------------------
+   Same shape as generate_r1cs_example (libiop/relations/examples/r1cs_examples.tcc:23-78): constraint i is
+   z[i mod m] * z[(i+7) mod m] = c_i * z[(2i+1) mod m]; the assignment comes from a seeded xorshift64 instead of
+   FieldT::random_element() because Fp_model draws from std::random_device (bigint.tcc:194-206), which cannot be
+   seeded — the CPU and the GPU-integrated builds must see the same instance. */
+static uint64_t xs64(uint64_t &s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static void det_elem(G &e, uint64_t &s) { e = G(xs64(s), xs64(s), xs64(s)); }
+static void det_elem(Fr &e, uint64_t &s)
+{
+    e = Fr((long)(xs64(s) >> 1), true) * Fr((long)(xs64(s) >> 1), true) + Fr((long)(xs64(s) >> 1), true);
+    e = e * e * Fr((long)(xs64(s) >> 1), true) + e;
+}
+template<typename F>
+static r1cs_example<F> det_example(size_t num_constraints, size_t num_inputs, size_t num_variables, uint64_t seed)
+{
+    uint64_t st = seed ? seed : 0x9E3779B97F4A7C15ull;
+    r1cs_constraint_system<F> cs;
+    cs.primary_input_size_ = num_inputs;
+    cs.auxiliary_input_size_ = num_variables - num_inputs;
+    std::vector<F> z(num_variables);
+    for (auto &e : z) det_elem(e, st);
+    for (size_t i = 0; i < num_constraints; ++i) {
+        linear_combination<F> A, B, C;
+        const size_t a = i % num_variables, b = (i + 7) % num_variables, c = (2 * i + 1) % num_variables;
+        A.add_term(a + 1, F::one());
+        B.add_term(b + 1, F::one());
+        const F ab = z[a] * z[b];
+        if (z[c].is_zero()) C.add_term(0, ab); else C.add_term(c + 1, ab * z[c].inverse());
+        cs.add_constraint(r1cs_constraint<F>(A, B, C));
+    }
+    r1cs_primary_input<F> primary(z.begin(), z.begin() + num_inputs);
+    r1cs_auxiliary_input<F> aux(z.begin() + num_inputs, z.end());
+    return r1cs_example<F>(std::move(cs), std::move(primary), std::move(aux));
+}
+
+template<typename T>
+static void finish_dump(const T &proof, uint8_t *buf, size_t cap, size_t *len)
+{
+    std::vector<uint8_t> o;
+    dump_transcript(o, proof);
+    if (len) *len = o.size();
+    if (buf && o.size() <= cap) std::memcpy(buf, o.data(), o.size());
+}
+
+extern "C" {
+
+/* Aurora over the multiplicative edwards_Fr domains (README.md:160-164 `--is_multiplicative 1 --field_size=181`), non-zk */
+double REFN(aurora_edwards)(uint32_t log_n, uint32_t k_inputs, uint32_t rs_extra, uint32_t fri_loc, uint64_t seed,
+                            int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)
+{
+    REFN(init)();
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<Fr> ex = det_example<Fr>(n, k_inputs, n - 1, seed);
+    aurora_snark_parameters<Fr, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic, blake2b_type,
+        (size_t)fri_loc, (size_t)rs_extra, false, multiplicative_coset_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto proof = aurora_snark_prover<Fr, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+    const auto t1 = std::chrono::steady_clock::now();
+    finish_dump(proof, buf, cap, len);
+    if (accepted) *accepted = verify ? (aurora_snark_verifier<Fr, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, proof, params) ? 1 : 0) : -1;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* Fractal over edwards_Fr (BASELINE config 3 shape; instrument_fractal_snark.cpp:86-180: rho = 3, localization 2, k = 0) */
+double REFN(fractal_edwards)(uint32_t log_n, uint32_t rs_extra, uint32_t fri_loc, uint64_t seed, int verify,
+                             uint8_t *buf, size_t cap, size_t *len, int *accepted, double *indexer_secs)
+{
+    REFN(init)();
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<Fr> ex = det_example<Fr>(n, 0, n - 1, seed);
+    fractal_snark_parameters<Fr, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic, blake2b_type,
+        (size_t)fri_loc, (size_t)rs_extra, false, multiplicative_coset_type,
+        std::make_shared<r1cs_constraint_system<Fr>>(ex.constraint_system_));
+    const auto ti0 = std::chrono::steady_clock::now();
+    std::pair<bcs_prover_index<Fr, binary_hash_digest>, bcs_verifier_index<Fr, binary_hash_digest>> index =
+        fractal_snark_indexer(params);
+    const auto ti1 = std::chrono::steady_clock::now();
+    if (indexer_secs) *indexer_secs = std::chrono::duration<double>(ti1 - ti0).count();
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto proof = fractal_snark_prover<Fr, binary_hash_digest>(index.first, ex.primary_input_, ex.auxiliary_input_, params);
+    const auto t1 = std::chrono::steady_clock::now();
+    finish_dump(proof, buf, cap, len);
+    /* the index roots are part of what the verifier trusts: append them so parity covers the indexer too */
+    if (buf && len) {
+        size_t off = *len;
+        for (auto &r : index.second.index_MT_roots_) { if (off + r.size() <= cap) std::memcpy(buf + off, r.data(), r.size()); off += r.size(); }
+        *len = off;
+    }
+    if (accepted) *accepted = verify ? (fractal_snark_verifier<Fr, binary_hash_digest>(index.second, ex.primary_input_, proof, params) ? 1 : 0) : -1;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* Ligero over GF(2^192) (BASELINE config 4 shape; instrument_ligero_snark.cpp:66-117: ratio 0.1, rho = 2) */
+double REFN(ligero_gf192)(uint32_t log_n, double height_width_ratio, uint32_t rs_extra, int make_zk, uint64_t seed, int verify,
+                          uint8_t *buf, size_t cap, size_t *len, int *accepted)
+{
+    REFN(init)();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = det_example<G>(n, 15, n - 1, seed);
+    ligero_snark_parameters<G, binary_hash_digest> params;
+    params.security_level_ = 128;
+    params.LDT_reducer_soundness_type_ = LDT_reducer_soundness_type::optimistic_heuristic;
+    params.height_width_ratio_ = (float)height_width_ratio;
+    params.RS_extra_dimensions_ = rs_extra;
+    params.make_zk_ = make_zk != 0;
+    params.domain_type_ = affine_subspace_type;
+    params.bcs_params_ = default_bcs_params<G, binary_hash_digest>(blake2b_type, 128, log_n);
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto proof = ligero_snark_prover<G, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+    const auto t1 = std::chrono::steady_clock::now();
+    finish_dump(proof, buf, cap, len);
+    if (accepted) *accepted = verify ? (ligero_snark_verifier<G, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, proof, params) ? 1 : 0) : -1;
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

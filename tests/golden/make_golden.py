@@ -79,6 +79,18 @@ def main():
         assert acc == 1
         fps.append(f"{log_n},{int(zk)},{len(dump)},{hashlib.sha256(dump).hexdigest()}")
     g["aurora_fingerprints"] = np.array(fps)
+    # the other prover entry points (deterministic instances, see oracle/ref_shim/ref_api.cpp det_example)
+    other = []
+    for log_n in (10, 12):
+        secs, dump, acc = r.aurora_edwards(log_n); assert acc == 1
+        other.append(f"aurora_edwards,{log_n},0,{len(dump)},{hashlib.sha256(dump).hexdigest()}")
+        secs, dump, acc, _ = r.fractal_edwards(log_n); assert acc == 1
+        other.append(f"fractal_edwards,{log_n},0,{len(dump)},{hashlib.sha256(dump).hexdigest()}")
+    for log_n, zk in ((12, False), (14, False), (10, True)):
+        secs, dump, acc = r.ligero_gf192(log_n, make_zk=zk); assert acc == 1
+        other.append(f"ligero_gf192,{log_n},{int(zk)},{len(dump)},{hashlib.sha256(dump).hexdigest()}")
+    g["prover_fingerprints"] = np.array(other)
+    fps = fps + other
     out = os.path.join(os.path.dirname(__file__), "hotpath_golden.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes;", *fps, sep="\n")

@@ -242,7 +242,8 @@ class Reference:
         self.lib = _Renamed()
         self._real = real
         self.lib.ref_init()
-        self.lib.ref_aurora_gf192.restype = C.c_double
+        for fn in ("ref_aurora_gf192", "ref_aurora_edwards", "ref_fractal_edwards", "ref_ligero_gf192"):
+            getattr(self.lib, fn).restype = C.c_double
 
     def seed(self, s):
         self.lib.ref_seed(C.c_uint64(s))
@@ -360,6 +361,28 @@ class Reference:
                                          C.c_int(int(verify)), _b(buf), C.c_size_t(cap),
                                          C.byref(ln), C.byref(acc))
         return secs, buf[:ln.value].tobytes(), acc.value
+
+    def _run(self, fn, args, cap=1 << 27):
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(); acc = C.c_int()
+        extra = []
+        secs = fn(*args, _b(buf), C.c_size_t(cap), C.byref(ln), C.byref(acc), *extra)
+        return secs, buf[:ln.value].tobytes(), acc.value
+
+    def aurora_edwards(self, log_n, k_inputs=31, rs_extra=3, fri_loc=2, seed=0x9E3779B97F4A7C15, verify=True):
+        return self._run(self.lib.ref_aurora_edwards, (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_uint32(rs_extra),
+                                                       C.c_uint32(fri_loc), C.c_uint64(seed), C.c_int(int(verify))))
+
+    def fractal_edwards(self, log_n, rs_extra=3, fri_loc=2, seed=0x9E3779B97F4A7C15, verify=True, cap=1 << 27):
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(); acc = C.c_int(); idx = C.c_double()
+        secs = self.lib.ref_fractal_edwards(C.c_uint32(log_n), C.c_uint32(rs_extra), C.c_uint32(fri_loc), C.c_uint64(seed),
+                                            C.c_int(int(verify)), _b(buf), C.c_size_t(cap), C.byref(ln), C.byref(acc), C.byref(idx))
+        return secs, buf[:ln.value].tobytes(), acc.value, idx.value
+
+    def ligero_gf192(self, log_n, ratio=0.1, rs_extra=2, make_zk=False, seed=0x9E3779B97F4A7C15, verify=True):
+        return self._run(self.lib.ref_ligero_gf192, (C.c_uint32(log_n), C.c_double(ratio), C.c_uint32(rs_extra), C.c_int(int(make_zk)),
+                                                     C.c_uint64(seed), C.c_int(int(verify))))
 
 
 class ReferenceGpu(Reference):

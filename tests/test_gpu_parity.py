@@ -329,3 +329,30 @@ def test_reference_prover_with_b200_dropin_is_bit_exact(golden, log_n, zk):
         r = Reference()
         _, cpu_dump, cpu_ok = r.aurora_gf192(log_n, make_zk=zk, verify=False)
         assert cpu_dump == dump
+
+
+@pytest.mark.parametrize("which,log_n,zk", [("aurora_edwards", 10, False), ("aurora_edwards", 12, False),
+                                            ("fractal_edwards", 10, False), ("fractal_edwards", 12, False),
+                                            ("ligero_gf192", 12, False), ("ligero_gf192", 14, False), ("ligero_gf192", 10, True)])
+def test_other_reference_provers_with_b200_dropin_are_bit_exact(golden, which, log_n, zk):
+    """fractal_snark_indexer/prover over edwards_Fr (multiplicative NTT path), ligero_snark_prover over GF(2^192)
+    (hundreds of small LDEs + one wide-leaf Merkle tree) and Aurora over edwards_Fr, all UNMODIFIED reference host
+    code with the B200 hot path dropped in: same transcript bytes as the CPU reference (fingerprints generated by
+    tests/golden/make_golden.py from oracle/_ref/libiopref.so), and the reference verifiers accept."""
+    import hashlib
+    from oracle_lib import ReferenceGpu
+    if not ReferenceGpu.available():
+        pytest.skip("oracle/_ref/libiopref_gpu.so not built (needs /root/reference at build time)")
+    g = ReferenceGpu()
+    if which == "aurora_edwards":
+        _, dump, acc = g.aurora_edwards(log_n)
+    elif which == "fractal_edwards":
+        _, dump, acc, _ = g.fractal_edwards(log_n)
+    else:
+        _, dump, acc = g.ligero_gf192(log_n, make_zk=zk)
+    assert acc == 1, "reference verifier rejected the GPU-built proof"
+    want = {}
+    for line in golden["prover_fingerprints"]:
+        w, n, z, ln, h = str(line).split(",")
+        want[(w, int(n), bool(int(z)))] = (int(ln), h)
+    assert (len(dump), hashlib.sha256(dump).hexdigest()) == want[(which, log_n, zk)]
