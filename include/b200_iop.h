@@ -136,6 +136,13 @@ int b200_merkle_nodes(b200_ctx *, b200_bytes nodes, const size_t *node_idx, size
  * out[i] = BLAKE2b-digest_len( in[i*msg_len .. (i+1)*msg_len) ) */
 int b200_blake2b_batch(b200_ctx *, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
 
+/* ---- proof of work ---------------------------------------------------------- */
+/* pow<FieldT, binary_hash_digest>::solve_pow (libiop/bcs/pow.tcc:87-102, acceptance pow.tcc:143-158), called at
+ * bcs_prover.tcc:52-59: first candidate, in the reference's order, whose BLAKE2b(challenge || candidate) has its last
+ * little-endian word & (2^pow_bitlen - 1) <= pow_upperbound.  challenge, pow_out: digest_len (= 32) host bytes. */
+int b200_pow_solve(b200_ctx *, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound,
+                   uint8_t *pow_out);
+
 /* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the FFT tile passes ---- */
 unsigned long long b200_launch_count(b200_ctx *);
 int b200_profile_begin(b200_ctx *);

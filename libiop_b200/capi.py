@@ -321,6 +321,11 @@ class B200:
                 self.free(b)
             self.free(nodes)
 
+    def pow_solve(self, challenge, pow_bitlen, pow_upperbound=0):
+        out = (C.c_uint8 * 32)()
+        self._chk(self.lib.b200_pow_solve(self.ctx, bytes(challenge), C.c_size_t(32), C.c_uint32(pow_bitlen), C.c_uint64(pow_upperbound), out))
+        return bytes(out)
+
     def blake2b_batch(self, msgs, msg_len, digest_len=32):
         n = len(msgs) // msg_len
         i = self.upload_bytes(msgs); o = self.alloc_bytes(n * digest_len)

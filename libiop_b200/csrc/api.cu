@@ -255,6 +255,11 @@ int b200_merkle_nodes(b200_ctx *c, b200_bytes nodes, const size_t *node_idx, siz
     return 0;
 }
 
+int b200_pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound, uint8_t *pow_out)
+{
+    return pow_solve(c, challenge, digest_len, pow_bitlen, pow_upperbound, pow_out);
+}
+
 int b200_blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out)
 {
     return blake2b_batch(c, in, msg_len, n_msgs, digest_len, out);

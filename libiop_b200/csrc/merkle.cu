@@ -428,6 +428,63 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
     return 0;
 }
 
+
+/* ---------------------------------------------------------------------------------------------- */
+/* proof-of-work grind: pow::solve_pow for binary digests (libiop/bcs/pow.tcc:87-102),
+   acceptance test verify_pow_internal (pow.tcc:143-158).  Candidates are tried in the reference's order —
+   the challenge itself, then the challenge with its last 8 bytes replaced by 0, 1, 2, ... — and the FIRST
+   hit in that order is returned (atomicMin over candidate indices, batches of 2^22 hashes).             */
+struct PowParams {
+    uint64_t chal[4];
+    uint64_t mask, upper;
+    uint64_t base;           /* first candidate counter of this batch */
+    unsigned long long *best; /* device: smallest accepted candidate index so far (index 0 = challenge itself) */
+};
+
+__global__ void __launch_bounds__(256) pow_grind_kernel(const PowParams P, uint64_t count)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint64_t idx = P.base + t;        /* candidate index; 0 = unmodified challenge, k >= 1 = last word k-1 */
+    uint64_t m[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = P.chal[i]; m[4 + i] = P.chal[i]; }
+    if (idx) m[7] = idx - 1;
+#pragma unroll
+    for (int i = 8; i < 16; ++i) m[i] = 0;
+    uint64_t h[8];
+    blake2b_init(h, 32);
+    blake2b_compress(h, m, 64, true);
+    if ((h[3] & P.mask) <= P.upper) atomicMin(P.best, (unsigned long long)idx);
+}
+
+int pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound, uint8_t *pow_out)
+{
+    if (digest_len != 32) return set_err(c, B200_ERR_INVALID, "proof of work is implemented for 32-byte BLAKE2b digests");
+    if (pow_bitlen >= 31) return set_err(c, B200_ERR_INVALID, "pow_bitlen must be < 31 (pow.tcc:149 uses an int shift)");
+    PowParams P;
+    memcpy(P.chal, challenge, 32);
+    P.mask = ((uint64_t)1 << pow_bitlen) - 1; P.upper = pow_upperbound;
+    unsigned long long *best = (unsigned long long *)scratch_get(c, 3, 64);
+    if (!best) return set_err(c, B200_ERR_NOMEM, "cannot allocate PoW result");
+    P.best = best;
+    const unsigned long long none = ~0ull;
+    B200_CUDA(c, cudaMemcpyAsync(best, &none, sizeof none, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t batch = (uint64_t)1 << 22;
+    unsigned long long found = none;
+    for (uint64_t base = 0; found == none; base += batch) {
+        if (base > ((uint64_t)1 << 40)) return set_err(c, B200_ERR_LOGIC, "proof of work not found after 2^40 hashes");
+        P.base = base;
+        pow_grind_kernel<<<(unsigned)(batch / 256), 256, 0, c->stream>>>(P, batch);
+        B200_LAUNCH_CHECK(c);
+        B200_CUDA(c, cudaMemcpyAsync(&found, best, sizeof found, cudaMemcpyDeviceToHost, c->stream));
+        B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    memcpy(pow_out, challenge, 32);
+    if (found) { const uint64_t k = found - 1; memcpy(pow_out + 24, &k, 8); }
+    return 0;
+}
+
 struct BatchParams { const uint64_t *in; uint64_t *out; size_t msg_words, n; uint32_t digest_len, dw; };
 __global__ void blake2b_batch_kernel(const BatchParams P)
 {

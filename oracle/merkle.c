@@ -109,3 +109,24 @@ uint64_t orc_hashchain_squeeze_position(orc_hashchain *hc, uint64_t range)
                 (const uint8_t *)&hc->squeeze_index, 8);        /* blake2b.cpp:50-74 */
     return r % range;
 }
+
+/* pow::solve_pow_internal for binary digests (libiop/bcs/pow.tcc:87-102) with verify_pow_internal (pow.tcc:143-158).
+   Returns the number of hashes tried. */
+uint64_t orc_pow_solve(uint8_t *pow_out, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound)
+{
+    uint8_t buf[128], hash[64];
+    memcpy(pow_out, challenge, digest_len);
+    const size_t num_words = digest_len / 8;
+    uint64_t pow_int = 0, tries = 0;
+    for (;;) {
+        memcpy(buf, challenge, digest_len);
+        memcpy(buf + digest_len, pow_out, digest_len);
+        orc_blake2b(hash, digest_len, buf, 2 * digest_len, NULL, 0);     /* node_hasher(challenge, pow) */
+        ++tries;
+        uint64_t lsw;
+        memcpy(&lsw, hash + (num_words - 1) * 8, 8);
+        if ((lsw & (uint64_t)((1 << pow_bitlen) - 1)) <= pow_upperbound) return tries;
+        memcpy(pow_out + (num_words - 1) * 8, &pow_int, 8);
+        pow_int += 1;
+    }
+}

@@ -107,6 +107,8 @@ void   orc_hashchain_absorb(orc_hashchain *hc);                     /* input is 
 void   orc_hashchain_squeeze_gf192(orc_hashchain *hc, f192 *out, size_t n);
 void   orc_hashchain_squeeze_fp(orc_hashchain *hc, const orc_fp_params *P, f192 *out, size_t n);
 uint64_t orc_hashchain_squeeze_position(orc_hashchain *hc, uint64_t range);
+/* pow::solve_pow (pow.tcc:87-102,143-158); returns hashes tried */
+uint64_t orc_pow_solve(uint8_t *pow_out, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
  */
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -79,8 +80,9 @@ void REFN(init)(void)
 {
     static bool done = false;
     if (!done) { libff::edwards_pp::init_public_params(); done = true; }
-    libff::inhibit_profiling_info = true;
-    libff::inhibit_profiling_counters = true;
+    const bool prof = std::getenv("B200_REF_PROFILE") != nullptr;   /* libff::enter_block timers */
+    libff::inhibit_profiling_info = !prof;
+    libff::inhibit_profiling_counters = !prof;
 }
 
 void REFN(seed)(uint64_t seed) { b200_shim_randombytes_seed(seed); }
@@ -222,6 +224,18 @@ void REFN(merkle_build)(uint8_t *nodes_out, uint8_t *salts_out, const uint64_t *
 {
     if (field_kind == 2) merkle_build<Fr>(nodes_out, salts_out, oracles, n_oracles, n_elems, coset, zk, security);
     else merkle_build<G>(nodes_out, salts_out, oracles, n_oracles, n_elems, coset, zk, security);
+}
+
+/* ---- proof of work (pow.tcc:87-158) ---- */
+void REFN(pow_solve)(uint8_t *pow_out, const uint8_t *challenge, size_t work_parameter, size_t cost_per_hash,
+                     uint32_t *bitlen_out, uint64_t *upper_out)
+{
+    const pow_parameters params(work_parameter, cost_per_hash);
+    const libiop::pow<G, binary_hash_digest> p(params, 32);
+    const binary_hash_digest sol = p.solve_pow(blake2b_two_to_one_hash, binary_hash_digest((const char *)challenge, 32));
+    std::memcpy(pow_out, sol.data(), 32);
+    if (bitlen_out) *bitlen_out = (uint32_t)params.pow_bitlen();
+    if (upper_out) *upper_out = params.pow_upperbound();
 }
 
 /* ---- hashchain ---- */

@@ -70,6 +70,13 @@ def main():
         nodes, salts = r.merkle_build(orc, cs, kind, zk=True)
         g[f"mt{i}_zk_nodes"] = np.frombuffer(nodes, dtype=np.uint8)
         g[f"mt{i}_zk_salts"] = np.frombuffer(salts, dtype=np.uint8)
+    # proof of work (pow.tcc:87-158): (challenge, work parameter) -> solution
+    pw = []
+    for i, work in enumerate((8, 12, 16, 18)):
+        ch = hashlib.sha256(b"pow-challenge-%d" % i).digest()
+        sol, bitlen, upper = r.pow_solve(ch, work)
+        pw.append(f"{ch.hex()},{bitlen},{upper},{sol.hex()}")
+    g["pow_vectors"] = np.array(pw)
     sq, pos = r.hashchain_demo()
     g["hashchain_squeeze"] = sq; g["hashchain_positions"] = pos
     # whole-prover fingerprints (sha256 of the canonical transcript dump)

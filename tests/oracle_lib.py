@@ -201,6 +201,12 @@ class Oracle:
         assert rc == 0
         return bytes(out)
 
+    def pow_solve(self, challenge, pow_bitlen, pow_upperbound=0):
+        out = (C.c_uint8 * 32)()
+        self.lib.orc_pow_solve.restype = C.c_uint64
+        tries = self.lib.orc_pow_solve(out, bytes(challenge), C.c_size_t(32), C.c_uint32(pow_bitlen), C.c_uint64(pow_upperbound))
+        return bytes(out), tries
+
     def merkle_build(self, oracles, coset_size, domain_kind, salts=None, salt_len=32, digest_len=32):
         oracles = [np.ascontiguousarray(o).reshape(-1, 3) for o in oracles]
         n = len(oracles[0])
@@ -346,6 +352,11 @@ class Reference:
                                   C.c_size_t(coset_size), C.c_int(field_kind), C.c_int(1 if zk else 0),
                                   C.c_size_t(security))
         return nodes.tobytes(), (salts.tobytes() if zk else None)
+
+    def pow_solve(self, challenge, work_parameter, cost_per_hash=1):
+        out = (C.c_uint8 * 32)(); bl = C.c_uint32(); ub = C.c_uint64()
+        self.lib.ref_pow_solve(out, bytes(challenge), C.c_size_t(work_parameter), C.c_size_t(cost_per_hash), C.byref(bl), C.byref(ub))
+        return bytes(out), bl.value, ub.value
 
     def hashchain_demo(self, absorbed=b"\x00" * 32):
         sq = elems(2); pos = np.zeros(3, dtype=np.uint64)

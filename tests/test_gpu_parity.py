@@ -356,3 +356,19 @@ def test_other_reference_provers_with_b200_dropin_are_bit_exact(golden, which, l
         w, n, z, ln, h = str(line).split(",")
         want[(w, int(n), bool(int(z)))] = (int(ln), h)
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == want[(which, log_n, zk)]
+
+
+# ------------------------------------------------------------------ proof of work
+def test_pow_solve(dev, oracle, golden):
+    """b200_pow_solve returns the FIRST accepted candidate in the reference's order (pow.tcc:87-102)."""
+    for line in golden["pow_vectors"]:
+        ch, bl, ub, sol = str(line).split(",")
+        assert dev.pow_solve(bytes.fromhex(ch), int(bl), int(ub)).hex() == sol
+    rng = np.random.default_rng(12)
+    for bitlen in (0, 1, 5, 10, 14, 20, 23):
+        ch = rng.bytes(32)
+        want, tries = oracle.pow_solve(ch, bitlen, 0)
+        got = dev.pow_solve(ch, bitlen, 0)
+        assert got == want, (bitlen, tries)
+        h = hashlib.blake2b(ch + got, digest_size=32).digest()
+        assert int.from_bytes(h[24:], "little") & ((1 << bitlen) - 1) == 0

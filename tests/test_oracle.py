@@ -219,3 +219,13 @@ def test_oracle_equals_reference_when_built(oracle, reference):
     basis, shift = rand_elems(rng, m), rand_elems(rng, 1)[0]
     c = rand_elems(rng, 300)
     assert (oracle.additive_fft(c, m, basis, shift) == reference.additive_fft(c, m, basis, shift)).all()
+
+
+def test_pow_golden(oracle, golden):
+    """pow::solve_pow (pow.tcc:87-158): reference-generated (challenge, bit length) -> first accepted candidate."""
+    for line in golden["pow_vectors"]:
+        ch, bl, ub, sol = str(line).split(",")
+        got, tries = oracle.pow_solve(bytes.fromhex(ch), int(bl), int(ub))
+        assert got.hex() == sol
+    ch = hashlib.sha256(b"zero-bits").digest()
+    assert oracle.pow_solve(ch, 0, 0)[0] == ch          # the challenge itself is the first candidate
