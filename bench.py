@@ -266,6 +266,11 @@ def run_gpu(args):
     fwd_ms = sum(t for lab, t in passes if "cosets=1" in lab)
     bwd_ms = sum(t for lab, t in passes if "cosets=8" in lab)
 
+    # final transcript gather (the only exchange between ranks): each rank's 11 Merkle roots -> rank 0
+    from libiop_b200 import sharding
+    roots = b"".join(dev.download_bytes(nb, 32) for nb in node_bufs)
+    all_roots = sharding.gather_transcripts(roots)
+
     ms_per_step = ms / args.steps
     N = 1 << LOG_N
     value = world * N / (ms_per_step * 1e-3)
@@ -307,6 +312,8 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": None,
+        "transcript_gather": {"ranks": len(all_roots), "bytes_per_rank": len(roots),
+                              "distinct_instances": len(set(all_roots)) == len(all_roots)},
         "clocks": sampler.summary() if rank == 0 else None,
     }
     # launches per step: counted from the scheduler; measured with ncu in profiles/
@@ -314,6 +321,8 @@ def run_gpu(args):
     out["gpu_launches_per_step"] = int(launches_per_step)
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
+    if rank == 0 and args.dropin_log_n:
+        out["whole_prover_dropin"] = whole_prover_dropin(args.dropin_log_n)
     if rank == 0:
         print(json.dumps(out))
     dev.close()
@@ -374,6 +383,32 @@ def cpu_baseline(sample_log_n=14):
             "measured_constraints_per_s_at_sample": (1 << sample_log_n) / secs}
 
 
+def whole_prover_dropin(log_n):
+    """The UNMODIFIED reference aurora_snark_prover (host C++ of libiop) with this library dropped in under its three
+    hot-path headers (oracle/_ref/libiopref_gpu.so, built in the build container) next to the plain CPU reference
+    (oracle/_ref/libiopref.so) on the same instance: whole-prover seconds and transcript equality."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import hashlib
+        from oracle_lib import Reference, ReferenceGpu
+        if not (Reference.available() and ReferenceGpu.available()):
+            return {"unavailable": "oracle/_ref libraries were not built (need /root/reference at build time)"}
+        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)   # the reference printf()s its parameters
+        try:
+            g, r = ReferenceGpu(), Reference()
+            g.aurora_gf192(10, verify=False)
+            gs, gd, acc = g.aurora_gf192(log_n, verify=True)
+            cs, cd, _ = r.aurora_gf192(log_n, verify=False)
+        finally:
+            os.dup2(saved, 1); os.close(devnull); os.close(saved)
+        return {"log_n": log_n, "cpu_reference_prover_s": cs, "dropin_prover_s": gs, "bit_exact_transcript": cd == gd,
+                "transcript_sha256": hashlib.sha256(gd).hexdigest(), "reference_verifier_accepts": acc == 1,
+                "cpu_constraints_per_s": (1 << log_n) / cs, "dropin_constraints_per_s": (1 << log_n) / gs,
+                "note": "host-side IOP code (virtual oracles, transcript assembly) is the unmodified single-threaded reference"}
+    except Exception as e:  # never let the optional section break the bench line
+        return {"unavailable": repr(e)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -408,6 +443,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropin-log-n", type=int, default=18, help="also run the reference prover with the B200 drop-in at this size (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
