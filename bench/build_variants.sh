@@ -15,6 +15,10 @@ for v in "$@"; do
     t512)   build t512   -DB200_TILE_THREADS=512 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=1 ;;
     t256i2) build t256i2 -DB200_TILE_THREADS=256 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=2 ;;
     t512i2) build t512i2 -DB200_TILE_THREADS=512 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=2 ;;
+    notw)   build notw   -DB200_EXP_NOTW ;;
+    nosync) build nosync -DB200_EXP_NOSYNC ;;
+    nomul)  build nomul  -DB200_EXP_NOMUL ;;
+    base)   build base ;;
     t384)   build t384   -DB200_TILE_THREADS=384 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=1 ;;
   esac
 done

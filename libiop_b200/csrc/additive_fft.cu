@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(B200_TILE_THREADS, B200_TILE_MINBLOCKS) additi
     }
 
     for (uint32_t o = 0; o < P.n_ops; ++o) {
+#ifndef B200_EXP_NOSYNC
         __syncthreads();
+#else
+        if (o == 0) __syncthreads();
+#endif
         const uint32_t kind = P.ops[o] >> 8, bit = P.ops[o] & 0xffu;
         if (kind == OP_TW) {
             /* twist at depth j = bit: S[i] *= beta_j^(i >> j)     (fft.tcc:61-70 / 190-200) */
@@ -210,10 +214,14 @@ __global__ void __launch_bounds__(B200_TILE_THREADS, B200_TILE_MINBLOCKS) additi
                         L0[u] = insert_zero(kk, pos);
                         const uint32_t tix = global_index(L0[u]) & ((1u << jj) - 1u);
                         tw[u] = tau_s[(L0[u] >> tbw) * d + depth];
+#ifndef B200_EXP_NOTW
                         if (jj > 0) gf_addto(tw[u], ldg_elem(stab + (tix & 255u)));
                         if (jj > 8) gf_addto(tw[u], ldg_elem(stab + 256 + ((tix >> 8) & 255u)));
                         if (jj > 16) gf_addto(tw[u], ldg_elem(stab + 512 + ((tix >> 16) & 255u)));
                         if (jj > 24) gf_addto(tw[u], ldg_elem(stab + 768 + (tix >> 24)));
+#else
+                        tw[u].w[0] ^= tix;
+#endif
                         a[u] = t.ld(L0[u]); b[u] = t.ld(L0[u] | (1u << pos));
                         if (INV) gf_addto(b[u], a[u]);            /* fft.tcc:164 */
                     }
@@ -221,7 +229,11 @@ __global__ void __launch_bounds__(B200_TILE_THREADS, B200_TILE_MINBLOCKS) additi
 #pragma unroll
                 for (int u = 0; u < B200_ILP; ++u) {
                     if (act[u]) {
+#ifndef B200_EXP_NOMUL
                         gf_addto(a[u], gf_mul(b[u], tw[u]));      /* fft.tcc:116 / 165 */
+#else
+                        gf_addto(a[u], gf_add(b[u], tw[u]));
+#endif
                         if (!INV) gf_addto(b[u], a[u]);           /* fft.tcc:117 */
                         t.st(L0[u], a[u]); t.st(L0[u] | (1u << pos), b[u]);
                     }
