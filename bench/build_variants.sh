@@ -19,6 +19,8 @@ for v in "$@"; do
     nosync) build nosync -DB200_EXP_NOSYNC ;;
     nomul)  build nomul  -DB200_EXP_NOMUL ;;
     base)   build base ;;
+    s4)     build s4     -DB200_GF_SPACING=4 ;;
+    s5)     build s5     -DB200_GF_SPACING=5 ;;
     t384)   build t384   -DB200_TILE_THREADS=384 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=1 ;;
   esac
 done

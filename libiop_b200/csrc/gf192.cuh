@@ -29,7 +29,7 @@
 #endif
 
 #ifndef B200_GF_SPACING
-#define B200_GF_SPACING 5
+#define B200_GF_SPACING 4 /* measured on B200: LDE 2^20->2^23 6.54 ms (S=4) vs 8.06 ms (S=5) */
 #endif
 
 namespace b200 {
