@@ -7,7 +7,7 @@ mkdir -p $OUT
 build() { # name flags
   name=$1; shift
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr "$@" \
-    -shared -o $OUT/lib_$name.so api.cu additive_fft.cu ntt.cu fri.cu merkle.cu -cudart static -Xcompiler -nostdlib++ -Xlinker /usr/lib/x86_64-linux-gnu/libstdc++.so.6 &
+    -shared -o $OUT/lib_$name.so api.cu additive_fft.cu ntt.cu fri.cu merkle.cu elementwise.cu -cudart static -Xcompiler -nostdlib++ -Xlinker /usr/lib/x86_64-linux-gnu/libstdc++.so.6 &
 }
 for v in "$@"; do
   case $v in

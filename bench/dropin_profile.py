@@ -10,3 +10,8 @@ if which == "gpu":
     r.aurora_gf192(log_n, verify=False)
     os.environ["B200_REF_PROFILE"] = "1"
 r.aurora_gf192(log_n, verify=False)
+if which == "gpu":
+    import ctypes as C
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    r._real.refgpu_arena_stats(C.byref(a), C.byref(b), C.byref(c))
+    print(f"pinned arena: {a.value} slabs, {b.value / 2**30:.2f} GiB reserved, {c.value / 2**30:.2f} GiB free", flush=True)

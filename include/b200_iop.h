@@ -71,8 +71,11 @@ int b200_sync(b200_ctx *);
 void *b200_stream(b200_ctx *);                       /* cudaStream_t the context launches on */
 int b200_device_info(b200_ctx *, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
 
+/* Device buffers come from a caching allocator: b200_free keeps the block for the next b200_alloc of the same size
+ * (stream-ordered reuse, no synchronisation); b200_trim returns all cached blocks to the driver. */
 b200_buf b200_alloc(b200_ctx *, size_t n_elems);     /* 0 on failure */
 void b200_free(b200_ctx *, b200_buf);
+int b200_trim(b200_ctx *);
 b200_bytes b200_alloc_bytes(b200_ctx *, size_t n_bytes);
 void b200_free_bytes(b200_ctx *, b200_bytes);
 void *b200_host_alloc(b200_ctx *, size_t n_bytes);   /* pinned host memory for upload/download */
@@ -135,6 +138,41 @@ int b200_merkle_nodes(b200_ctx *, b200_bytes nodes, const size_t *node_idx, size
 /* blake2b_two_to_one_hash / blake2b_field_element_hash over a batch (blake2b.cpp:28-48, blake2b.tcc:141-160):
  * out[i] = BLAKE2b-digest_len( in[i*msg_len .. (i+1)*msg_len) ) */
 int b200_blake2b_batch(b200_ctx *, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
+
+/* ---- element-wise passes between the LDE, Merkle and FRI calls and point evaluation (N4) --------
+ * field = B200_FIELD_GF192 or B200_FIELD_FP (fp != NULL); every buffer holds n elements unless stated. */
+/* out[i] = sum_k coeffs[k] * vecs[k][i]: random linear combinations — multi_lincheck's f_combined_Mz
+ * (lincheck/basic_lincheck_aux.tcc:117-123), combined_LDT_virtual_oracle (ldt_reducer_aux.tcc:52-66). coeffs: k*3 host limbs. */
+int b200_vec_lincomb(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, size_t n, size_t k,
+                     const uint64_t *coeffs, const b200_buf *vecs);
+/* out[i] = a[i]*b[i] (+|-) c[i]*d[i]; b == 0: a[i]; c == 0: no second term; d == 0: c[i].  Covers fz = fw*Z + f_1v
+ * (r1cs_rs_iop.tcc:216-221), lincheck's combined*p1 - fz*p2 (basic_lincheck_aux.tcc:131-137), Az*Bz - Cz (rowcheck.tcc:61-82),
+ * f - (c*x^(|H|-1) + Z_H*h) (sumcheck.tcc:95-99). */
+int b200_vec_mul_add(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf b, b200_buf c,
+                     b200_buf d, int subtract, size_t n);
+/* out[i] = a[i] * table[(i >> shift) & mask] (a == 0: the table value itself): factors that repeat over cosets of H in L,
+ * e.g. Z_H^-1 in rowcheck (rowcheck.tcc:36-84: additive shift = log|H|, multiplicative shift = 0, mask = |L|/|H| - 1). */
+int b200_vec_mul_table(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf table,
+                       uint32_t shift, size_t mask, size_t n);
+/* GF(2^192): out[i] = prod_{k < n_factors} ( T_k[0] + sum_{j: bit j of i} T_k[1+j] ), i < 2^dim; tables = n_factors x (dim+1)
+ * host elements.  n_factors = 1 is all_subset_sums (algebra/utils.tcc:8-30) = any F2-affine function over an affine subspace
+ * (its elements, a vanishing / linearized polynomial, x^(2^e)); more factors give subspace_element_powers
+ * (algebra/exponentiation.tcc:22-54), one factor per set bit of the exponent. */
+int b200_gf192_subset_sum_products(b200_ctx *, b200_buf out, uint32_t dim, uint32_t n_factors, const uint64_t *tables);
+/* Fp: out[i] = a * r^i + add (add may be NULL): coset elements and their powers (exponentiation.tcc:56-72), X^|H| - h^|H| over
+ * a coset (vanishing_polynomial.tcc:115-165). */
+int b200_fp_geometric(b200_ctx *, const b200_fp_params *fp, b200_buf out, size_t n, const uint64_t a[3], const uint64_t r[3],
+                      const uint64_t add[3]);
+/* polynomial<FieldT>::evaluation_at_point (algebra/polynomials/polynomial.tcc:98-109): out = sum_i coeffs[i] * x^i (host result) */
+int b200_poly_eval(b200_ctx *, int field, const b200_fp_params *fp, b200_buf coeffs, size_t n, const uint64_t x[3], uint64_t out[3]);
+
+/* polynomial_over_vanishing_polynomial (algebra/polynomials/vanishing_polynomial.tcc:312-371,
+ * linearized_polynomial.tcc:238-291): P = Q*Z + R for the sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j]
+ * (pows[j] < deg; additive: the linearized vanishing polynomial of a subspace, multiplicative: y^deg - c).
+ * p: n_p > deg coefficients; q_out: n_p - deg; r_out: deg coefficients (0 = not wanted); lead_inv = lead^-1 (host). */
+int b200_poly_divide_sparse(b200_ctx *, int field, const b200_fp_params *fp, b200_buf p, size_t n_p, size_t deg,
+                            const uint64_t lead_inv[3], size_t n_terms, const uint64_t *coefs, const size_t *pows,
+                            b200_buf q_out, b200_buf r_out);
 
 /* ---- proof of work ---------------------------------------------------------- */
 /* pow<FieldT, binary_hash_digest>::solve_pow (libiop/bcs/pow.tcc:87-102, acceptance pow.tcc:143-158), called at

@@ -321,6 +321,100 @@ class B200:
                 self.free(b)
             self.free(nodes)
 
+    # ---- element-wise passes and point evaluation (N4); numpy in, numpy out ----
+    def _fpref(self, fp):
+        return C.byref(fp) if fp is not None else None
+
+    def vec_lincomb(self, field, fp, coeffs, vecs):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+        n = len(vecs[0]) if len(vecs) else 0
+        bufs = [self.upload(v) for v in vecs]
+        o = self.alloc(max(n, 1))
+        try:
+            arr = (C.c_uint64 * max(len(bufs), 1))(*bufs)
+            self._chk(self.lib.b200_vec_lincomb(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(o), C.c_size_t(n),
+                                                C.c_size_t(len(bufs)), coeffs.ctypes.data_as(_u64p), arr))
+            return self.download(o, n)
+        finally:
+            for b in bufs + [o]:
+                self.free(b)
+
+    def vec_mul_add(self, field, fp, a, b=None, c=None, d=None, subtract=False):
+        n = len(a)
+        bufs = [self.upload(v) if v is not None else 0 for v in (a, b, c, d)]
+        o = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_vec_mul_add(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(o), *[C.c_uint64(x) for x in bufs],
+                                                C.c_int(1 if subtract else 0), C.c_size_t(n)))
+            return self.download(o, n)
+        finally:
+            for b_ in bufs + [o]:
+                if b_:
+                    self.free(b_)
+
+    def vec_mul_table(self, field, fp, a, table, shift, mask, n=None):
+        n = len(a) if a is not None else n
+        da = self.upload(a) if a is not None else 0
+        dt = self.upload(table)
+        o = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_vec_mul_table(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(o), C.c_uint64(da), C.c_uint64(dt),
+                                                  C.c_uint32(shift), C.c_size_t(mask), C.c_size_t(n)))
+            return self.download(o, n)
+        finally:
+            for b_ in (da, dt, o):
+                if b_:
+                    self.free(b_)
+
+    def gf192_subset_sum_products(self, dim, tables):
+        """tables: (n_factors, dim+1, 3) — offset then basis, per factor."""
+        tables = np.ascontiguousarray(tables, dtype=np.uint64).reshape(-1, dim + 1, 3)
+        o = self.alloc(1 << dim)
+        try:
+            self._chk(self.lib.b200_gf192_subset_sum_products(self.ctx, C.c_uint64(o), C.c_uint32(dim), C.c_uint32(len(tables)),
+                                                              tables.ctypes.data_as(_u64p)))
+            return self.download(o, 1 << dim)
+        finally:
+            self.free(o)
+
+    def fp_geometric(self, fp, n, a, r, add=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.uint64)
+        addp = np.ascontiguousarray(add, dtype=np.uint64).ctypes.data_as(_u64p) if add is not None else None
+        o = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_fp_geometric(self.ctx, C.byref(fp), C.c_uint64(o), C.c_size_t(n), a.ctypes.data_as(_u64p),
+                                                 r.ctypes.data_as(_u64p), addp))
+            return self.download(o, n)
+        finally:
+            self.free(o)
+
+    def poly_eval(self, field, fp, coeffs, x):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        out = np.zeros(3, dtype=np.uint64)
+        d = self.upload(coeffs)
+        try:
+            self._chk(self.lib.b200_poly_eval(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(d), C.c_size_t(len(coeffs)),
+                                              x.ctypes.data_as(_u64p), out.ctypes.data_as(_u64p)))
+            return out
+        finally:
+            self.free(d)
+
+    def poly_divide_sparse(self, field, fp, p, deg, lead_inv, coefs, pows):
+        p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 3)
+        coefs = np.ascontiguousarray(coefs, dtype=np.uint64).reshape(-1, 3)
+        pows = np.ascontiguousarray(pows, dtype=np.uint64)
+        lead_inv = np.ascontiguousarray(lead_inv, dtype=np.uint64)
+        dp = self.upload(p); dq = self.alloc(len(p) - deg); dr = self.alloc(deg)
+        try:
+            self._chk(self.lib.b200_poly_divide_sparse(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(dp), C.c_size_t(len(p)),
+                                                       C.c_size_t(deg), lead_inv.ctypes.data_as(_u64p), C.c_size_t(len(coefs)),
+                                                       coefs.ctypes.data_as(_u64p), pows.ctypes.data_as(_szp), C.c_uint64(dq), C.c_uint64(dr)))
+            return self.download(dq, len(p) - deg), self.download(dr, deg)
+        finally:
+            for b_ in (dp, dq, dr):
+                self.free(b_)
+
     def pow_solve(self, challenge, pow_bitlen, pow_upperbound=0):
         out = (C.c_uint8 * 32)()
         self._chk(self.lib.b200_pow_solve(self.ctx, bytes(challenge), C.c_size_t(32), C.c_uint32(pow_bitlen), C.c_uint64(pow_upperbound), out))

@@ -2,6 +2,7 @@
  * api.cu — C ABI of libb200iop.so (declared in include/b200_iop.h): context, memory, and thin
  * forwarding to the kernels.  No CPU fallback: every compute entry point launches CUDA kernels.
  */
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -34,6 +35,8 @@ b200_ctx *b200_ctx_create(int device)
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError(); delete c; return nullptr;
     }
+    const char *tr = getenv("B200_TRACE");
+    c->trace = tr && tr[0] == '1';
     return c;
 }
 
@@ -43,6 +46,8 @@ void b200_ctx_destroy(b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     plans_clear(c);
+    b200_trim(c);
+    for (auto &kv : c->live_blocks) cudaFree(kv.first);
     for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -70,23 +75,50 @@ int b200_device_info(b200_ctx *c, int *sm_count, size_t *total_mem, int *cc_majo
     return 0;
 }
 
+int b200_trim(b200_ctx *c)
+{
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto &kv : c->free_blocks) cudaFree(kv.second);
+    c->free_blocks.clear();
+    c->cached_bytes = 0;
+    return 0;
+}
 b200_buf b200_alloc(b200_ctx *c, size_t n_elems) { return b200_alloc_bytes(c, n_elems * 24); }
 void b200_free(b200_ctx *c, b200_buf b) { b200_free_bytes(c, b); }
 b200_bytes b200_alloc_bytes(b200_ctx *c, size_t n_bytes)
 {
-    void *p = nullptr;
-    if (cudaMalloc(&p, n_bytes ? n_bytes : 8) != cudaSuccess) {
-        cudaGetLastError();
-        set_err(c, B200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", n_bytes);
-        return 0;
+    B200_TRACE_SCOPE(c, "alloc", n_bytes);
+    const size_t want = ((n_bytes ? n_bytes : 8) + 511) & ~(size_t)511;
+    auto hit = c->free_blocks.find(want);
+    if (hit != c->free_blocks.end()) {
+        void *p = hit->second;
+        c->free_blocks.erase(hit);
+        c->cached_bytes -= want;
+        c->live_blocks[p] = want;
+        return (b200_bytes)(uintptr_t)p;
     }
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        b200_trim(c);                                   /* give the cached blocks back and retry once */
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            set_err(c, B200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", n_bytes);
+            return 0;
+        }
+    }
+    c->live_blocks[p] = want;
     return (b200_bytes)(uintptr_t)p;
 }
 void b200_free_bytes(b200_ctx *c, b200_bytes b)
 {
     if (!b) return;
-    cudaStreamSynchronize(c->stream);
-    cudaFree((void *)(uintptr_t)b);
+    void *p = (void *)(uintptr_t)b;
+    auto it = c->live_blocks.find(p);
+    if (it == c->live_blocks.end()) { cudaStreamSynchronize(c->stream); cudaFree(p); return; }   /* not ours: plain release */
+    c->free_blocks.emplace(it->second, p);
+    c->cached_bytes += it->second;
+    c->live_blocks.erase(it);
 }
 void *b200_host_alloc(b200_ctx *c, size_t n_bytes)
 {
@@ -102,22 +134,26 @@ void b200_host_free(b200_ctx *, void *p) { if (p) cudaFreeHost(p); }
 
 int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *src, size_t n_elems)
 {
+    B200_TRACE_SCOPE(c, "upload", n_elems * 24);
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, src, n_elems * 24, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems)
 {
+    B200_TRACE_SCOPE(c, "download", n_elems * 24);
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + src_offset * 24, n_elems * 24, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_bytes)
 {
+    B200_TRACE_SCOPE(c, "upload_bytes", n_bytes);
     B200_CUDA(c, cudaMemcpyAsync((void *)(uintptr_t)dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes)
 {
+    B200_TRACE_SCOPE(c, "download_bytes", n_bytes);
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + offset, n_bytes, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -194,21 +230,29 @@ int b200_timer_stop(b200_ctx *c, float *ms)
 
 int b200_gf192_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
 {
+    B200_TRACE_SCOPE(c, "gf192_fft", (size_t)1 << L->dim);
     return additive_fft(c, L, coeffs, n_coeffs, evals_out);
 }
 int b200_gf192_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
 {
+    B200_TRACE_SCOPE(c, "gf192_ifft", (size_t)1 << H->dim);
     return additive_ifft(c, H, evals, coeffs_out);
 }
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { return gf192_mul_vec(c, out, a, b, n); }
-int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n) { return gf192_inv_vec(c, out, a, n); }
+int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
+{
+    B200_TRACE_SCOPE(c, "gf192_inv", n);
+    return gf192_inv_vec(c, out, a, n);
+}
 
 int b200_fp_ntt(b200_ctx *c, const b200_fp_params *P, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
 {
+    B200_TRACE_SCOPE(c, "fp_ntt", (size_t)1 << L->dim);
     return fp_ntt(c, P, L, coeffs, n_coeffs, evals_out);
 }
 int b200_fp_intt(b200_ctx *c, const b200_fp_params *P, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
 {
+    B200_TRACE_SCOPE(c, "fp_intt", (size_t)1 << H->dim);
     return fp_intt(c, P, H, evals, coeffs_out);
 }
 int b200_fp_mul(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 0, out, a, b, n); }
@@ -219,12 +263,14 @@ int b200_fp_inv(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, 
 int b200_fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_domain *L_i, uint32_t eta,
                   const uint64_t x_i[3], b200_buf f_i, b200_buf f_next_out)
 {
+    B200_TRACE_SCOPE(c, "fri_fold", (size_t)1 << L_i->dim);
     return fri_fold(c, field, fp, L_i, eta, x_i, f_i, f_next_out);
 }
 
 int b200_merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset_size,
                       int domain_kind, const uint8_t *zk_salts_host, size_t salt_len, size_t digest_len, b200_bytes nodes_out)
 {
+    B200_TRACE_SCOPE(c, "merkle_build", n_elems * n_oracles);
     return merkle_build(c, oracles, n_oracles, n_elems, coset_size, domain_kind, zk_salts_host, salt_len, digest_len, nodes_out);
 }
 int b200_merkle_root(b200_ctx *c, b200_bytes nodes, uint8_t *root_out, size_t digest_len)
@@ -257,6 +303,7 @@ int b200_merkle_nodes(b200_ctx *c, b200_bytes nodes, const size_t *node_idx, siz
 
 int b200_pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound, uint8_t *pow_out)
 {
+    B200_TRACE_SCOPE(c, "pow_solve", pow_bitlen);
     return pow_solve(c, challenge, digest_len, pow_bitlen, pow_upperbound, pow_out);
 }
 

@@ -1,6 +1,7 @@
 /* ctx.h — internal context shared by the translation units of libb200iop.so */
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,6 +27,13 @@ struct b200_ctx {
     /* grow-only device scratch (work arrays of the FFTs), keyed by slot */
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    /* caching device allocator behind b200_alloc / b200_free: freed blocks are kept in exact-size bins and handed out
+       again (a prover allocates and releases the same few work-array sizes hundreds of times; cudaMalloc/cudaFree cost
+       milliseconds each and cudaFree synchronises the device).  Reuse is safe without synchronisation because every
+       use of a block is ordered on the context's single stream. */
+    std::multimap<size_t, void *> free_blocks;
+    std::map<void *, size_t> live_blocks;
+    size_t cached_bytes = 0;
     /* pinned staging for small host<->device transfers */
     void *staging = nullptr;
     size_t staging_bytes = 0;
@@ -34,6 +42,7 @@ struct b200_ctx {
     std::map<std::string, std::shared_ptr<b200::NttPlan>> ntt_plans;
     /* instrumentation: every kernel launch is counted; with profiling on, tile passes are bracketed by events */
     unsigned long long n_launches = 0;
+    bool trace = false;   /* B200_TRACE=1: every C-ABI compute/transfer call prints its synchronised wall time to stderr */
     bool profiling = false;
     struct ProfRec { std::string label; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -102,6 +111,24 @@ struct ProfScope {
     }
     ~ProfScope() { if (on) cudaEventRecord(c->prof[idx].b, c->stream); }
 };
+
+/* B200_TRACE=1 scope: prints "b200 <name> <detail> <ms>" with the stream drained on both sides */
+struct ApiTrace {
+    b200_ctx *c; const char *name; size_t detail; std::chrono::steady_clock::time_point t0;
+    ApiTrace(b200_ctx *ctx, const char *n, size_t d) : c(ctx), name(n), detail(d)
+    {
+        if (c && c->trace) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
+    }
+    ~ApiTrace()
+    {
+        if (c && c->trace) {
+            cudaStreamSynchronize(c->stream);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            fprintf(stderr, "b200 %-28s %12zu %10.3f ms\n", name, detail, ms);
+        }
+    }
+};
+#define B200_TRACE_SCOPE(ctx, name, detail) b200::ApiTrace trace_scope__((ctx), (name), (size_t)(detail))
 
 inline uint32_t ceil_log2(size_t n)
 {

@@ -1,0 +1,40 @@
+/*
+ * b200_dropin_common.hpp — shared helpers of the drop-in overrides (libiop_b200/dropin/libiop/...).
+ *
+ * Each override file shadows one reference .tcc on the include path: it includes the reference's own file unmodified
+ * from where it lies and then explicitly specialises individual member functions for the field types the B200 library
+ * serves (libff::gf192, libff::edwards_Fr).  No reference source is copied; every other field keeps the CPU code.
+ */
+#ifndef B200_DROPIN_COMMON_HPP_
+#define B200_DROPIN_COMMON_HPP_
+#include <memory>
+#include <vector>
+
+#include "b200_ref_traits.hpp"
+#include "libiop_b200/host/b200_elementwise.hpp"
+#include "libiop_b200/host/b200_hotpath.hpp"
+
+namespace libiop {
+namespace b200_glue {
+
+/* device copy of a host vector (asynchronous: the vector outlives the next synchronising call in every caller) */
+template<typename FieldT>
+libiop_b200::device_buffer to_device(const std::vector<FieldT> &v)
+{
+    libiop_b200::device_buffer b(v.size());
+    b.upload_async(v);
+    return b;
+}
+
+template<typename FieldT>
+std::shared_ptr<std::vector<FieldT>> to_host(const libiop_b200::device_buffer &b, std::size_t n)
+{
+    return std::make_shared<std::vector<FieldT>>(b.template download<FieldT>(n));
+}
+
+} // namespace b200_glue
+} // namespace libiop
+
+/* stamps `MACRO(FIELD)` for every field the B200 library serves */
+#define B200_FOR_EACH_FIELD(MACRO) MACRO(libff::gf192) MACRO(libff::edwards_Fr)
+#endif

@@ -1,0 +1,38 @@
+/* Shadow of libiop/protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc for the drop-in build.
+   fz_virtual_oracle::evaluated_contents (r1cs_rs_iop.tcc:181-226): f_z = f_w * Z_{1,v} + f_{1,v} over the codeword
+   domain.  On the B200: Z_{1,v} over L is generated on the device from dim(L)+1 host values, f_{1,v} is LDE'd on the
+   device from its |1,v| coefficients, and one fused pass forms the result; only f_w goes up and f_z comes down. */
+#include "b200_dropin_common.hpp"
+#include B200_REF_FILE(libiop/protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc)
+
+namespace libiop {
+#define B200_FZ_SPECIALISE(FIELD)                                                                                          \
+template<> inline std::shared_ptr<std::vector<FIELD>> fz_virtual_oracle<FIELD>::evaluated_contents(                        \
+    const std::vector<std::shared_ptr<std::vector<FIELD>>> &constituent_oracle_evaluations) const                          \
+{                                                                                                                          \
+    libff::enter_block("fz evaluated contents");                                                                           \
+    if (constituent_oracle_evaluations.size() != 1)                                                                        \
+        throw std::invalid_argument("fz_virtual_oracle has one constituent oracle.");                                      \
+    if (this->primary_input_.size() != this->primary_input_size_)                                                          \
+        throw std::logic_error("Evaluation requested before primary_input is set.");                                       \
+    const std::shared_ptr<std::vector<FIELD>> &fw = constituent_oracle_evaluations[0];                                     \
+    const std::size_t n = this->codeword_domain_.num_elements();                                                           \
+    if (fw->size() != n)                                                                                                   \
+        throw std::invalid_argument("Provided fw evaluations don't match the declared codeword domain size.");             \
+    using namespace libiop_b200;                                                                                           \
+    device_buffer d_fw = b200_glue::to_device(*fw), d_Z(n), d_f1v(n), d_out(n);                                            \
+    const vanishing_polynomial<FIELD> input_vp(this->input_variable_domain_);                                              \
+    vanishing_polynomial_over_domain<FIELD>(d_Z, input_vp, this->codeword_domain_);                                        \
+    std::vector<FIELD> f_1v_evaluations({ FIELD::one() });                                                                 \
+    f_1v_evaluations.insert(f_1v_evaluations.end(), this->primary_input_.begin(), this->primary_input_.end());             \
+    const std::vector<FIELD> f_1v_coefficients = IFFT_over_field_subset<FIELD>(f_1v_evaluations, this->input_variable_domain_); \
+    device_buffer d_c = b200_glue::to_device(f_1v_coefficients);                                                           \
+    FFT_over_field_subset_device<FIELD>(d_c, f_1v_coefficients.size(), this->codeword_domain_, d_f1v);                     \
+    vec_mul_add<FIELD>(d_out, d_fw, &d_Z, &d_f1v, nullptr, false, n);                                                      \
+    std::shared_ptr<std::vector<FIELD>> result = b200_glue::to_host<FIELD>(d_out, n);                                      \
+    libff::leave_block("fz evaluated contents");                                                                           \
+    return result;                                                                                                         \
+}
+B200_FOR_EACH_FIELD(B200_FZ_SPECIALISE)
+#undef B200_FZ_SPECIALISE
+} // namespace libiop

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/b200_iop.h"
+#include "b200_pinned_arena.hpp"
 
 namespace libiop_b200 {
 
@@ -69,10 +70,18 @@ public:
             throw_status(context(), b200_upload(context(), buf_, offset, reinterpret_cast<const uint64_t *>(v.data()), v.size()));
         throw_status(context(), b200_sync(context()));
     }
+    /* stream-ordered upload without the trailing synchronisation: `v` must stay alive and unmodified until the next
+       synchronising call on the context (download, b200_sync) */
+    template<typename FieldT> void upload_async(const std::vector<FieldT> &v, std::size_t offset = 0)
+    {
+        static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+        if (!v.empty())
+            throw_status(context(), b200_upload(context(), buf_, offset, reinterpret_cast<const uint64_t *>(v.data()), v.size()));
+    }
     template<typename FieldT> std::vector<FieldT> download(std::size_t n, std::size_t offset = 0) const
     {
         static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
-        std::vector<FieldT> v(n);
+        std::vector<FieldT> v = make_uninitialized_vector<FieldT>(n);   /* every element is overwritten below */
         if (n) throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(v.data()), buf_, offset, n));
         return v;
     }

@@ -1,0 +1,198 @@
+/*
+ * b200_elementwise.hpp — C++ face of the element-wise device passes (include/b200_iop.h, "element-wise passes"):
+ * the building blocks of the reference's virtual-oracle evaluations over device buffers, plus the
+ * domain-derived vectors they need (elements of L, a vanishing polynomial over L, powers of the elements of L),
+ * produced on the device from O(dim) host values instead of being materialised by host loops
+ * (algebra/utils.tcc:8-30, algebra/exponentiation.tcc:3-88, algebra/polynomials/vanishing_polynomial.tcc:98-165).
+ *
+ * Generic over the field type (field_traits<FieldT>) and over anything with the reference's field_subset /
+ * polynomial method names.  Host arithmetic on the handful of table entries uses FieldT's own operators.
+ */
+#ifndef LIBIOP_B200_ELEMENTWISE_HPP_
+#define LIBIOP_B200_ELEMENTWISE_HPP_
+
+#include <cstring>
+#include <list>
+#include <utility>
+#include <vector>
+
+#include "b200_device.hpp"
+#include "b200_fields.hpp"
+
+namespace libiop_b200 {
+
+template<typename FieldT> inline const uint64_t *limbs(const FieldT &x) { return reinterpret_cast<const uint64_t *>(&x); }
+
+template<typename FieldT> inline FieldT field_pow(FieldT base, std::size_t e)
+{
+    FieldT r = FieldT::one();
+    while (e) { if (e & 1) r *= base; base *= base; e >>= 1; }
+    return r;
+}
+
+/* out[i] = sum_k coeffs[k] * vecs[k][i] */
+template<typename FieldT>
+void vec_lincomb(device_buffer &out, std::size_t n, const std::vector<FieldT> &coeffs, const std::vector<const device_buffer *> &vecs)
+{
+    static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    std::vector<b200_buf> h;
+    for (auto *v : vecs) h.push_back(v->get());
+    throw_status(context(), b200_vec_lincomb(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), out.get(), n, h.size(),
+                                             reinterpret_cast<const uint64_t *>(coeffs.data()), h.data()));
+}
+
+/* out = a*b (+|-) c*d with absent operands (nullptr) read as "one" (b, d) or "no second term" (c) */
+template<typename FieldT>
+void vec_mul_add(device_buffer &out, const device_buffer &a, const device_buffer *b, const device_buffer *c, const device_buffer *d,
+                 bool subtract, std::size_t n)
+{
+    throw_status(context(), b200_vec_mul_add(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), out.get(), a.get(),
+                                             b ? b->get() : 0, c ? c->get() : 0, d ? d->get() : 0, subtract ? 1 : 0, n));
+}
+
+/* out[i] = a[i] * table[(i >> shift) & mask] */
+template<typename FieldT>
+void vec_mul_table(device_buffer &out, const device_buffer *a, const std::vector<FieldT> &table, unsigned shift, std::size_t mask, std::size_t n)
+{
+    device_buffer t(table.size());
+    t.upload(table);
+    throw_status(context(), b200_vec_mul_table(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), out.get(),
+                                               a ? a->get() : 0, t.get(), shift, mask, n));
+    throw_status(context(), b200_sync(context()));   /* t is released on return */
+}
+
+/* One F2-affine function over an affine subspace, given by its values at the shift and at shift + basis[j]:
+   table = { f(shift), f(shift + basis[0]) - f(shift), ... }.  `scale` multiplies the whole function. */
+template<typename FieldT, typename DomainT, typename Fn>
+std::vector<FieldT> affine_function_table(const DomainT &domain, Fn f, const FieldT &scale)
+{
+    const FieldT at_shift = f(domain.shift());
+    std::vector<FieldT> t;
+    t.reserve(domain.dimension() + 1);
+    t.push_back(at_shift * scale);
+    for (const FieldT &b : domain.basis()) t.push_back((f(domain.shift() + b) - at_shift) * scale);
+    return t;
+}
+
+/* out[i] = prod_k (affine function k)(element i of the subspace): b200_gf192_subset_sum_products */
+template<typename FieldT>
+void subspace_function_product(device_buffer &out, std::size_t dim, const std::vector<std::vector<FieldT>> &tables)
+{
+    std::vector<FieldT> flat;
+    for (auto &t : tables) flat.insert(flat.end(), t.begin(), t.end());
+    throw_status(context(), b200_gf192_subset_sum_products(context(), out.get(), (uint32_t)dim, (uint32_t)tables.size(),
+                                                           reinterpret_cast<const uint64_t *>(flat.data())));
+}
+
+/* out[i] = a * r^i + add over n positions (prime field) */
+template<typename FieldT>
+void geometric_sequence(device_buffer &out, std::size_t n, const FieldT &a, const FieldT &r, const FieldT &add)
+{
+    throw_status(context(), b200_fp_geometric(context(), field_traits<FieldT>::fp(), out.get(), n, limbs(a), limbs(r), limbs(add)));
+}
+
+/* scale * x^exponent for every element x of the domain, in domain order
+   (subset_element_powers, algebra/exponentiation.tcc:74-86, times a constant) */
+template<typename FieldT, typename DomainT>
+void domain_element_powers(device_buffer &out, const DomainT &domain, std::size_t exponent, const FieldT &scale)
+{
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        std::vector<std::vector<FieldT>> tables;
+        for (std::size_t bit = 0; bit < 8 * sizeof(exponent); ++bit) {
+            if (!((exponent >> bit) & 1)) continue;
+            /* x -> x^(2^bit) is F2-linear */
+            tables.push_back(affine_function_table<FieldT>(domain,
+                [bit](FieldT x) { for (std::size_t s = 0; s < bit; ++s) x *= x; return x; },
+                tables.empty() ? scale : FieldT::one()));
+        }
+        if (tables.empty())   /* exponent 0: the constant `scale` */
+            tables.push_back(affine_function_table<FieldT>(domain, [](FieldT) { return FieldT::one(); }, scale));
+        subspace_function_product<FieldT>(out, domain.dimension(), tables);
+    } else {
+        geometric_sequence<FieldT>(out, domain.num_elements(), scale * field_pow(domain.shift(), exponent),
+                                   field_pow(domain.generator(), exponent), FieldT::zero());
+    }
+}
+
+/* Z(x) for every element x of the domain, Z a vanishing polynomial of a subset H of the same kind
+   (vanishing_polynomial::evaluations_over_field_subset, vanishing_polynomial.tcc:98-165):
+   additive: Z is F2-affine; multiplicative: Z = X^|H| - const. */
+template<typename FieldT, typename DomainT, typename VanishingT>
+void vanishing_polynomial_over_domain(device_buffer &out, const VanishingT &Z, const DomainT &domain)
+{
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        subspace_function_product<FieldT>(out, domain.dimension(),
+            { affine_function_table<FieldT>(domain, [&Z](const FieldT &x) { return Z.evaluation_at_point(x); }, FieldT::one()) });
+    } else {
+        const std::size_t deg = Z.degree();
+        const FieldT a = field_pow(domain.shift(), deg);
+        geometric_sequence<FieldT>(out, domain.num_elements(), a, field_pow(domain.generator(), deg), Z.evaluation_at_point(domain.shift()) - a);
+    }
+}
+
+/* polynomial::evaluation_at_point on the device (coefficients resident in `coeffs`) */
+template<typename FieldT>
+FieldT poly_eval(const device_buffer &coeffs, std::size_t n, const FieldT &x)
+{
+    FieldT r;
+    throw_status(context(), b200_poly_eval(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), coeffs.get(), n, limbs(x),
+                                           reinterpret_cast<uint64_t *>(&r)));
+    return r;
+}
+
+/* P = Q*Z + R for a sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j] (b200_poly_divide_sparse);
+   returns {Q, R} with |Q| = |P| - deg and |R| = deg.  Requires |P| > deg. */
+template<typename FieldT>
+std::pair<std::vector<FieldT>, std::vector<FieldT>> poly_divide_sparse(const std::vector<FieldT> &P, std::size_t deg, const FieldT &lead,
+                                                                       const std::vector<FieldT> &coefs, const std::vector<std::size_t> &pows)
+{
+    device_buffer d_p(P.size()), d_q(P.size() - deg), d_r(deg);
+    d_p.upload_async(P);
+    const FieldT lead_inv = lead.inverse();
+    throw_status(context(), b200_poly_divide_sparse(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), d_p.get(), P.size(), deg,
+                                                    limbs(lead_inv), coefs.size(), reinterpret_cast<const uint64_t *>(coefs.data()),
+                                                    pows.data(), d_q.get(), d_r.get()));
+    std::vector<FieldT> q = d_q.template download<FieldT>(P.size() - deg);
+    std::vector<FieldT> r = d_r.template download<FieldT>(deg);
+    return std::make_pair(std::move(q), std::move(r));
+}
+
+/*
+ * Small cache of device copies of immutable host vectors, keyed by (address, length) and validated by a sample of
+ * the contents (first, last and 30 strided elements) so that a recycled allocation is never mistaken for the vector
+ * it replaced.  Used for polynomial coefficient vectors that are evaluated at many points
+ * (bcs_prover::get_transcript -> multi_lincheck_virtual_oracle::evaluation_at_point, basic_lincheck_aux.tcc:160-161).
+ */
+template<typename FieldT>
+class device_vector_cache {
+    struct entry { const FieldT *ptr; std::size_t n; std::vector<FieldT> sample; device_buffer buf; };
+    std::list<entry> entries_;
+    std::size_t max_entries_;
+    static std::vector<FieldT> sample_of(const FieldT *p, std::size_t n)
+    {
+        std::vector<FieldT> s;
+        const std::size_t k = n < 32 ? n : 32;
+        for (std::size_t i = 0; i < k; ++i) s.push_back(p[(k > 1) ? (i * (n - 1)) / (k - 1) : 0]);
+        return s;
+    }
+public:
+    explicit device_vector_cache(std::size_t max_entries) : max_entries_(max_entries) {}
+    const device_buffer &get(const std::vector<FieldT> &v)
+    {
+        const std::vector<FieldT> s = sample_of(v.data(), v.size());
+        for (auto it = entries_.begin(); it != entries_.end(); ++it) {
+            if (it->ptr == v.data() && it->n == v.size() && std::memcmp(it->sample.data(), s.data(), s.size() * sizeof(FieldT)) == 0) {
+                entries_.splice(entries_.begin(), entries_, it);
+                return entries_.front().buf;
+            }
+        }
+        if (entries_.size() >= max_entries_) entries_.pop_back();
+        entries_.emplace_front(entry{v.data(), v.size(), s, device_buffer(v.size())});
+        entries_.front().buf.upload(v);
+        return entries_.front().buf;
+    }
+    void clear() { entries_.clear(); }
+};
+
+} // namespace libiop_b200
+#endif

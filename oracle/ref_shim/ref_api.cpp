@@ -37,6 +37,16 @@
 #include "libiop/relations/examples/r1cs_examples.hpp"
 
 #ifdef B200_GPU_INTEGRATION
+/* the drop-in build serves the process's large blocks (the prover's oracles) from page-locked memory */
+#include "libiop_b200/host/b200_device.hpp"
+B200_DEFINE_PINNED_OPERATOR_NEW
+extern "C" void refgpu_arena_stats(uint64_t *slabs, uint64_t *reserved_bytes, uint64_t *free_bytes)
+{
+    libiop_b200::pinned_arena *a = libiop_b200::pinned_new_detail::arena();
+    *slabs = a ? a->slab_count() : 0;
+    *reserved_bytes = a ? a->reserved_bytes() : 0;
+    *free_bytes = a ? a->free_bytes() : 0;
+}
 #define REFN(name) refgpu_##name
 #else
 #define REFN(name) ref_##name

@@ -1,0 +1,231 @@
+"""GPU parity tests for the element-wise passes between the LDE / Merkle / FRI calls and
+polynomial evaluation at a point (N4), through the C ABI.  The checker restates the reference's scalar loops with the
+oracle's field arithmetic (oracle/gf192.c, oracle/fp.c); bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle_lib import el, rand_elems, standard_basis
+
+pytestmark = pytest.mark.gpu
+
+GF, FP = 1, 2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import libiop_b200 as L
+    d = L.B200(0)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def fp():
+    import libiop_b200 as L
+    return L.FpParams.edwards_fr()
+
+
+def bcast(e, n):
+    return np.broadcast_to(np.asarray(e, dtype=np.uint64).reshape(1, 3), (n, 3)).copy()
+
+
+class GfOps:
+    def __init__(self, o): self.o = o
+    def mul(self, a, b): return self.o.gf192_mul(a, b)
+    def add(self, a, b): return a ^ b
+    def sub(self, a, b): return a ^ b
+    def rand(self, rng, n): return rand_elems(rng, n)
+
+
+def _to_int(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 3).astype(object)
+    return a[:, 0] + (a[:, 1] << 64) + (a[:, 2] << 128)
+
+
+def _from_int(v):
+    m = (1 << 64) - 1
+    return np.stack([(v & m), ((v >> 64) & m), (v >> 128)], axis=1).astype(np.uint64)
+
+
+class FpOps:
+    """vector add/sub on the Montgomery representatives (Fp_model::operator+=/-=, fp.tcc:323-532: plain modular add/sub)"""
+    def __init__(self, o): self.o, self.p = o, o.fp_modulus()
+    def mul(self, a, b): return self.o.fp_mul(a, b)
+    def add(self, a, b): return _from_int((_to_int(a) + _to_int(b)) % self.p)
+    def sub(self, a, b): return _from_int((_to_int(a) - _to_int(b)) % self.p)
+    def rand(self, rng, n): return self.o.rand_fp(rng, n)
+
+
+def ops_for(field, oracle):
+    return GfOps(oracle) if field == GF else FpOps(oracle)
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 3), (4097, 4), (70000, 13), (333, 0)])
+def test_vec_lincomb(dev, oracle, fp, field, n, k):
+    """multi_lincheck f_combined_Mz (basic_lincheck_aux.tcc:117-123) / combined_LDT maximal oracles (ldt_reducer_aux.tcc:52-66)."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(n * 31 + k)
+    vecs = [F.rand(rng, n) for _ in range(k)]
+    coeffs = F.rand(rng, max(k, 1))[:k]
+    want = np.zeros((n, 3), dtype=np.uint64)
+    for j in range(k):
+        want = F.add(want, F.mul(bcast(coeffs[j], n), vecs[j]))
+    fpref = C.byref(fp) if field == FP else None
+    if k == 0:                                # empty combination = zero vector; needs the explicit length of the C call
+        o = dev.upload(F.rand(rng, n))
+        dev._chk(dev.lib.b200_vec_lincomb(dev.ctx, C.c_int(field), fpref, C.c_uint64(o), C.c_size_t(n), C.c_size_t(0), None, None))
+        got = dev.download(o, n)
+        dev.free(o)
+    else:
+        got = dev.vec_lincomb(field, fp if field == FP else None, coeffs, vecs)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("form", ["ab", "ab+c", "ab-cd", "a-cd", "a+c"])
+def test_vec_mul_add(dev, oracle, fp, field, form):
+    """fz = fw*Z + f1v (r1cs_rs_iop.tcc:216-221); lincheck combined*p1 - fz*p2 (basic_lincheck_aux.tcc:131-137);
+    Az*Bz - Cz (rowcheck.tcc:61-82)."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(7)
+    n = 50001
+    a, b, c, d = (F.rand(rng, n) for _ in range(4))
+    fpp = fp if field == FP else None
+    if form == "ab":
+        got, want = dev.vec_mul_add(field, fpp, a, b), F.mul(a, b)
+    elif form == "ab+c":
+        got, want = dev.vec_mul_add(field, fpp, a, b, c), F.add(F.mul(a, b), c)
+    elif form == "ab-cd":
+        got, want = dev.vec_mul_add(field, fpp, a, b, c, d, subtract=True), F.sub(F.mul(a, b), F.mul(c, d))
+    elif form == "a-cd":
+        got, want = dev.vec_mul_add(field, fpp, a, None, c, d, subtract=True), F.sub(a, F.mul(c, d))
+    else:
+        got, want = dev.vec_mul_add(field, fpp, a, None, c), F.add(a, c)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("shift,mask", [(10, 7), (0, 7), (3, 0xFFFF)])
+def test_vec_mul_table(dev, oracle, fp, field, shift, mask):
+    """rowcheck's Z_H^-1 per coset of H in L (rowcheck.tcc:36-84): additive index = pos / |H|, multiplicative = pos mod #cosets."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(11)
+    n = 1 << 13
+    a = F.rand(rng, n)
+    table = F.rand(rng, min(mask, (n - 1) >> shift) + 1)
+    idx = (np.arange(n) >> shift) & mask
+    fpp = fp if field == FP else None
+    assert (dev.vec_mul_table(field, fpp, a, table, shift, mask) == F.mul(a, table[idx])).all()
+    assert (dev.vec_mul_table(field, fpp, None, table, shift, mask, n=n) == table[idx]).all()
+
+
+@pytest.mark.parametrize("dim,k", [(1, 1), (8, 1), (13, 1), (13, 3), (10, 20)])
+def test_gf192_subset_sum_products(dev, oracle, dim, k):
+    """all_subset_sums (utils.tcc:8-30) and subspace_element_powers (exponentiation.tcc:22-54)."""
+    rng = np.random.default_rng(dim * 100 + k)
+    tables = rand_elems(rng, k * (dim + 1)).reshape(k, dim + 1, 3)
+    n = 1 << dim
+    idx = np.arange(n)
+    want = None
+    for f in range(k):
+        v = bcast(tables[f, 0], n)
+        for j in range(dim):
+            v[(idx >> j) & 1 == 1] ^= tables[f, 1 + j]
+        want = v if want is None else oracle.gf192_mul(want, v)
+    assert (dev.gf192_subset_sum_products(dim, tables) == want).all()
+
+
+def test_subspace_element_powers_matches_repeated_multiplication(dev, oracle):
+    """x^e over an affine subspace via one factor per set bit of e == e-fold product of the elements."""
+    dim, e = 9, 11
+    basis, shift = standard_basis(dim), el(1 << dim)
+    n = 1 << dim
+    elems_tab = np.concatenate([shift.reshape(1, 3), basis]).reshape(1, dim + 1, 3)
+    xs = dev.gf192_subset_sum_products(dim, elems_tab)
+    want = xs.copy()
+    for _ in range(e - 1):
+        want = oracle.gf192_mul(want, xs)
+
+    def frob(t, times):
+        for _ in range(times):
+            t = oracle.gf192_mul(t, t)
+        return t
+    tabs = np.stack([frob(elems_tab[0].copy(), b) for b in range(4) if (e >> b) & 1])
+    assert (dev.gf192_subset_sum_products(dim, tabs) == want).all()
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 5000, 1 << 15])
+def test_fp_geometric(dev, oracle, fp, n):
+    """coset_element_powers (exponentiation.tcc:56-72); vanishing polynomial over a coset (vanishing_polynomial.tcc:115-165)."""
+    rng = np.random.default_rng(n)
+    a, r, c = oracle.rand_fp(rng, 3)
+    want = np.zeros((n, 3), dtype=np.uint64)
+    cur = a.reshape(1, 3)
+    for i in range(n):                       # sequential like the reference
+        want[i] = cur[0]
+        cur = oracle.fp_mul(cur, r.reshape(1, 3))
+    assert (dev.fp_geometric(fp, n, a, r) == want).all()
+    assert (dev.fp_geometric(fp, n, a, r, add=c) == FpOps(oracle).add(want, bcast(c, n))).all()
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("n", [1, 7, 8, 2047, 2048, 2049, 100000, (1 << 22) + 5])
+def test_poly_eval(dev, oracle, fp, field, n):
+    """polynomial::evaluation_at_point (polynomial.tcc:98-109): Horner."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(n)
+    coeffs = F.rand(rng, n)
+    x = F.rand(rng, 1)
+    got = dev.poly_eval(field, fp if field == FP else None, coeffs, x[0])
+    # checker: blocked Horner with the oracle's vector multiply (log-depth, same value as the scalar recurrence)
+    vals, y = coeffs, x
+    while len(vals) > 1:
+        if len(vals) % 2:
+            vals = np.concatenate([vals, np.zeros((1, 3), dtype=np.uint64)])
+        vals = F.add(vals[0::2], F.mul(vals[1::2], np.repeat(y, len(vals) // 2, axis=0)))
+        y = F.mul(y, y)
+    assert (got == vals[0]).all()
+    if n <= 2049:                            # and the literal scalar recurrence at small sizes
+        acc = np.zeros((1, 3), dtype=np.uint64)
+        for i in range(n - 1, -1, -1):
+            acc = F.add(F.mul(acc, x), coeffs[i:i + 1])
+        assert (got == acc[0]).all()
+
+
+def _inv(F, field, oracle, x):
+    return oracle.gf192_inv(x.reshape(1, 3))[0] if field == GF else oracle.fp_inv(x)
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("log_deg,n_p,linearized", [(3, 20, True), (4, 17, True), (5, 64, True), (6, 200, True), (4, 100, False), (5, 33, False)])
+def test_poly_divide_sparse(dev, oracle, fp, field, log_deg, n_p, linearized):
+    """polynomial_over_linearized_polynomial (linearized_polynomial.tcc:238-291) and
+    polynomial_over_multiplicative_vanishing_polynomial (vanishing_polynomial.tcc:312-358): the checker is the reference's
+    sequential coefficient-clearing loop; P = Q*Z + R is verified by evaluating both sides at a random point as well."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(log_deg * 1000 + n_p)
+    deg = 1 << log_deg
+    P = F.rand(rng, n_p)
+    if linearized:                         # Z = lead*y^deg + sum_j Z[j] y^(2^(j-1)) + Z[0]
+        pows = [0] + [1 << k for k in range(log_deg)]
+    else:                                  # Z = y^deg + Z[0]
+        pows = [0]
+    coefs = F.rand(rng, len(pows))
+    lead = F.rand(rng, 1)[0]
+    lead_inv = _inv(F, field, oracle, lead)
+    # sequential restatement
+    quo = P[deg:].copy(); rem = P[:deg].copy()
+    for i in range(len(quo) - 1, -1, -1):
+        tw = F.mul(quo[i:i + 1], lead_inv.reshape(1, 3))
+        quo[i] = tw[0]
+        for c, pw in zip(coefs, pows):
+            t = F.mul(tw, c.reshape(1, 3))
+            if i + pw < deg:
+                rem[i + pw] = F.sub(rem[i + pw:i + pw + 1], t)[0]
+            else:
+                quo[i + pw - deg] = F.sub(quo[i + pw - deg:i + pw - deg + 1], t)[0]
+    q, r = dev.poly_divide_sparse(field, fp if field == FP else None, P, deg, lead_inv, coefs, pows)
+    assert (q == quo).all() and (r == rem).all()
