@@ -13,23 +13,24 @@
 #include "b200_ref_traits.hpp"
 #include "libiop_b200/host/b200_elementwise.hpp"
 #include "libiop_b200/host/b200_hotpath.hpp"
+#include "libiop_b200/host/b200_residency.hpp"
 
 namespace libiop {
 namespace b200_glue {
 
-/* device copy of a host vector (asynchronous: the vector outlives the next synchronising call in every caller) */
+/* device view of a host vector: its resident copy when the adapter produced the vector, else an asynchronous upload
+   (the vector outlives the next synchronising call in every caller) */
 template<typename FieldT>
-libiop_b200::device_buffer to_device(const std::vector<FieldT> &v)
+libiop_b200::device_view to_device(const std::vector<FieldT> &v)
 {
-    libiop_b200::device_buffer b(v.size());
-    b.upload_async(v);
-    return b;
+    return libiop_b200::device_view(v);
 }
 
+/* result of a device pass as the shared host vector the IOP layer expects; the device copy stays resident */
 template<typename FieldT>
-std::shared_ptr<std::vector<FieldT>> to_host(const libiop_b200::device_buffer &b, std::size_t n)
+std::shared_ptr<std::vector<FieldT>> to_host(libiop_b200::device_buffer &b, std::size_t n)
 {
-    return std::make_shared<std::vector<FieldT>>(b.template download<FieldT>(n));
+    return std::make_shared<std::vector<FieldT>>(libiop_b200::download_and_keep<FieldT>(std::move(b), n));
 }
 
 } // namespace b200_glue

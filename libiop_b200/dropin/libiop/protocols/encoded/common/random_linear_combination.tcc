@@ -13,14 +13,14 @@ template<> inline std::shared_ptr<std::vector<FIELD>> random_linear_combination_
         throw std::invalid_argument("Random Linear Combination Oracle: Expected same number of evaluations as in registration."); \
     using namespace libiop_b200;                                                                                           \
     const std::size_t n = constituent_oracle_evaluations[0]->size();                                                       \
-    std::vector<device_buffer> d_in;                                                                                       \
+    std::vector<device_view> d_in;                                                                                         \
     d_in.reserve(this->num_oracles_);                                                                                      \
     for (auto &v : constituent_oracle_evaluations) {                                                                       \
         if (v->size() != n) throw std::invalid_argument("Vectors of mismatched size.");                                    \
         d_in.emplace_back(b200_glue::to_device(*v));                                                                       \
     }                                                                                                                      \
     std::vector<const device_buffer *> ptrs;                                                                               \
-    for (auto &b : d_in) ptrs.push_back(&b);                                                                               \
+    for (auto &b : d_in) ptrs.push_back(&b.buf());                                                                               \
     device_buffer d_out(n);                                                                                                \
     vec_lincomb<FIELD>(d_out, n, this->random_coefficients_, ptrs);                                                        \
     return b200_glue::to_host<FIELD>(d_out, n);                                                                            \

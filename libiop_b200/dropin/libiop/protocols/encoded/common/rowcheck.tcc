@@ -20,11 +20,11 @@ template<> inline std::shared_ptr<std::vector<FIELD>> rowcheck_ABC_virtual_oracl
     const std::size_t order_H = this->constraint_domain_.num_elements();                                                   \
     const std::size_t num_cosets_of_H = n / order_H;                                                                       \
     if (Z_inv.size() != num_cosets_of_H) throw std::logic_error("rowcheck: unexpected number of distinct Z_H evaluations"); \
-    device_buffer d_A = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                          \
-    device_buffer d_B = b200_glue::to_device(*constituent_oracle_evaluations[1]);                                          \
-    device_buffer d_C = b200_glue::to_device(*constituent_oracle_evaluations[2]);                                          \
+    device_view d_A = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                          \
+    device_view d_B = b200_glue::to_device(*constituent_oracle_evaluations[1]);                                          \
+    device_view d_C = b200_glue::to_device(*constituent_oracle_evaluations[2]);                                          \
     device_buffer d_t(n), d_out(n);                                                                                        \
-    vec_mul_add<FIELD>(d_t, d_A, &d_B, &d_C, nullptr, true, n);                                                            \
+    vec_mul_add<FIELD>(d_t, d_A.buf(), &d_B.buf(), &d_C.buf(), nullptr, true, n);                                                            \
     if (this->codeword_domain_.type() == affine_subspace_type)                                                             \
         vec_mul_table<FIELD>(d_out, &d_t, Z_inv, (unsigned)libff::log2(order_H), ~std::size_t(0), n);                      \
     else                                                                                                                   \

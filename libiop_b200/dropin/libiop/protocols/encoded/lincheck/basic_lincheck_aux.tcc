@@ -38,23 +38,23 @@ template<> inline std::shared_ptr<std::vector<FIELD>> multi_lincheck_virtual_ora
     const std::size_t n = this->codeword_domain_.num_elements();                                                           \
     device_buffer d_p1(n), d_p2(n), d_comb(n), d_out(n);                                                                   \
     {                                                                                                                      \
-        device_buffer c1 = b200_glue::to_device(this->p_alpha_prime_.coefficients());                                      \
-        FFT_over_field_subset_device<FIELD>(c1, this->p_alpha_prime_.coefficients().size(), this->codeword_domain_, d_p1); \
-        device_buffer c2 = b200_glue::to_device(this->p_alpha_ABC_.coefficients());                                        \
-        FFT_over_field_subset_device<FIELD>(c2, this->p_alpha_ABC_.coefficients().size(), this->codeword_domain_, d_p2);   \
+        device_view c1 = b200_glue::to_device(this->p_alpha_prime_.coefficients());                                            \
+        FFT_over_field_subset_device<FIELD>(c1.buf(), this->p_alpha_prime_.coefficients().size(), this->codeword_domain_, d_p1); \
+        device_view c2 = b200_glue::to_device(this->p_alpha_ABC_.coefficients());                                                \
+        FFT_over_field_subset_device<FIELD>(c2.buf(), this->p_alpha_ABC_.coefficients().size(), this->codeword_domain_, d_p2);   \
         throw_status(context(), b200_sync(context()));                                                                     \
     }                                                                                                                      \
-    device_buffer d_fz = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                         \
-    std::vector<device_buffer> d_Mz;                                                                                       \
+    device_view d_fz = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                           \
+    std::vector<device_view> d_Mz;                                                                                         \
     std::vector<const device_buffer *> Mz_ptrs;                                                                            \
     d_Mz.reserve(this->matrices_.size());                                                                                  \
     for (std::size_t m = 0; m < this->matrices_.size(); ++m) {                                                             \
         if (constituent_oracle_evaluations[m + 1]->size() != n) throw std::invalid_argument("Vectors of mismatched size."); \
         d_Mz.emplace_back(b200_glue::to_device(*constituent_oracle_evaluations[m + 1]));                                   \
     }                                                                                                                      \
-    for (auto &b : d_Mz) Mz_ptrs.push_back(&b);                                                                            \
+    for (auto &b : d_Mz) Mz_ptrs.push_back(&b.buf());                                                                            \
     vec_lincomb<FIELD>(d_comb, n, this->r_Mz_, Mz_ptrs);                                                                   \
-    vec_mul_add<FIELD>(d_out, d_comb, &d_p1, &d_fz, &d_p2, true, n);                                                       \
+    vec_mul_add<FIELD>(d_out, d_comb, &d_p1, &d_fz.buf(), &d_p2, true, n);                                                       \
     std::shared_ptr<std::vector<FIELD>> result = b200_glue::to_host<FIELD>(d_out, n);                                      \
     libff::leave_block("multi_lincheck evaluated contents");                                                               \
     return result;                                                                                                         \

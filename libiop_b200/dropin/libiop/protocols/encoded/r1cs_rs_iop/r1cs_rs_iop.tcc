@@ -20,15 +20,15 @@ template<> inline std::shared_ptr<std::vector<FIELD>> fz_virtual_oracle<FIELD>::
     if (fw->size() != n)                                                                                                   \
         throw std::invalid_argument("Provided fw evaluations don't match the declared codeword domain size.");             \
     using namespace libiop_b200;                                                                                           \
-    device_buffer d_fw = b200_glue::to_device(*fw), d_Z(n), d_f1v(n), d_out(n);                                            \
+    device_view d_fw = b200_glue::to_device(*fw); device_buffer d_Z(n), d_f1v(n), d_out(n);                                            \
     const vanishing_polynomial<FIELD> input_vp(this->input_variable_domain_);                                              \
     vanishing_polynomial_over_domain<FIELD>(d_Z, input_vp, this->codeword_domain_);                                        \
     std::vector<FIELD> f_1v_evaluations({ FIELD::one() });                                                                 \
     f_1v_evaluations.insert(f_1v_evaluations.end(), this->primary_input_.begin(), this->primary_input_.end());             \
     const std::vector<FIELD> f_1v_coefficients = IFFT_over_field_subset<FIELD>(f_1v_evaluations, this->input_variable_domain_); \
-    device_buffer d_c = b200_glue::to_device(f_1v_coefficients);                                                           \
-    FFT_over_field_subset_device<FIELD>(d_c, f_1v_coefficients.size(), this->codeword_domain_, d_f1v);                     \
-    vec_mul_add<FIELD>(d_out, d_fw, &d_Z, &d_f1v, nullptr, false, n);                                                      \
+    device_view d_c = b200_glue::to_device(f_1v_coefficients);                                                             \
+    FFT_over_field_subset_device<FIELD>(d_c.buf(), f_1v_coefficients.size(), this->codeword_domain_, d_f1v);                     \
+    vec_mul_add<FIELD>(d_out, d_fw.buf(), &d_Z, &d_f1v, nullptr, false, n);                                                      \
     std::shared_ptr<std::vector<FIELD>> result = b200_glue::to_host<FIELD>(d_out, n);                                      \
     libff::leave_block("fz evaluated contents");                                                                           \
     return result;                                                                                                         \

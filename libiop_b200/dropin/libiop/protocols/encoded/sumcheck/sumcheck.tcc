@@ -19,8 +19,8 @@ template<> inline std::shared_ptr<std::vector<FIELD>> sumcheck_g_oracle<FIELD>::
     libff::enter_block("Sumcheck: g evaluated contents");                                                                  \
     using namespace libiop_b200;                                                                                           \
     const std::size_t n = this->codeword_domain_.num_elements();                                                           \
-    device_buffer d_f = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                          \
-    device_buffer d_h = b200_glue::to_device(*constituent_oracle_evaluations[1]);                                          \
+    device_view d_f = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                          \
+    device_view d_h = b200_glue::to_device(*constituent_oracle_evaluations[1]);                                          \
     device_buffer d_Z(n), d_t(n), d_u(n), d_out(n);                                                                        \
     vanishing_polynomial_over_domain<FIELD>(d_Z, this->Z_, this->codeword_domain_);                                        \
     if (this->field_subset_type_ == affine_subspace_type) {                                                                \
@@ -29,11 +29,11 @@ template<> inline std::shared_ptr<std::vector<FIELD>> sumcheck_g_oracle<FIELD>::
         throw_status(context(), b200_gf192_inv(context(), d_t.get(), d_t.get(), n));                                       \
         domain_element_powers<FIELD>(d_u, this->codeword_domain_, this->summation_domain_.num_elements(),                  \
                                      this->eps_inv_times_claimed_sum_);                                                    \
-        vec_mul_add<FIELD>(d_u, d_u, &d_t, &d_Z, &d_h, false, n);          /* mu' x^(|H|-1) + Z_H h */                     \
-        vec_mul_add<FIELD>(d_out, d_f, nullptr, &d_u, nullptr, true, n);   /* f - (...) */                                 \
+        vec_mul_add<FIELD>(d_u, d_u, &d_t, &d_Z, &d_h.buf(), false, n);          /* mu' x^(|H|-1) + Z_H h */                     \
+        vec_mul_add<FIELD>(d_out, d_f.buf(), nullptr, &d_u, nullptr, true, n);   /* f - (...) */                                 \
     } else {                                                                                                               \
         /* d_t = f - Z_H h; d_u = constant |H|^-1 mu ... folded: (f - Z_H h - c) * x^-1 */                                 \
-        vec_mul_add<FIELD>(d_t, d_f, nullptr, &d_Z, &d_h, true, n);                                                        \
+        vec_mul_add<FIELD>(d_t, d_f.buf(), nullptr, &d_Z, &d_h.buf(), true, n);                                                        \
         geometric_sequence<FIELD>(d_u, n, this->codeword_domain_.shift().inverse(), this->codeword_domain_.generator().inverse(), \
                                   FIELD::zero());                                                                          \
         /* (t - c) * xinv = t*xinv - c*xinv: second term via the same sequence scaled by c */                              \

@@ -17,14 +17,14 @@ template<> inline std::shared_ptr<std::vector<FIELD>> combined_LDT_virtual_oracl
         throw std::invalid_argument("Expected same number of evaluations as in registration.");                            \
     using namespace libiop_b200;                                                                                           \
     const std::size_t n = constituent_oracle_evaluations[0]->size();                                                       \
-    std::vector<device_buffer> d_in;                                                                                       \
+    std::vector<device_view> d_in;                                                                                         \
     d_in.reserve(this->num_input_oracles_);                                                                                \
     for (auto &v : constituent_oracle_evaluations) {                                                                       \
         if (v->size() != n) throw std::invalid_argument("Vectors of mismatched size.");                                    \
         d_in.emplace_back(b200_glue::to_device(*v));                                                                       \
     }                                                                                                                      \
     std::vector<const device_buffer *> ptrs;                                                                               \
-    for (auto &b : d_in) ptrs.push_back(&b);                                                                               \
+    for (auto &b : d_in) ptrs.push_back(&b.buf());                                                                               \
     const std::vector<FIELD> direct(this->coefficients_.begin(), this->coefficients_.begin() + this->num_input_oracles_);  \
     device_buffer d_out(n), d_bump(n);                                                                                     \
     vec_lincomb<FIELD>(d_out, n, direct, ptrs);                                                                            \
@@ -32,7 +32,7 @@ template<> inline std::shared_ptr<std::vector<FIELD>> combined_LDT_virtual_oracl
         const std::size_t idx = this->submaximal_oracle_indices_[i];                                                       \
         domain_element_powers<FIELD>(d_bump, this->codeword_domain_, this->max_degree_ - this->input_oracle_degrees_[idx], \
                                      this->coefficients_[this->num_input_oracles_ + i]);                                   \
-        vec_mul_add<FIELD>(d_out, d_out, nullptr, &d_bump, &d_in[idx], false, n);                                          \
+        vec_mul_add<FIELD>(d_out, d_out, nullptr, &d_bump, &d_in[idx].buf(), false, n);                                          \
     }                                                                                                                      \
     return b200_glue::to_host<FIELD>(d_out, n);                                                                            \
 }

@@ -18,6 +18,7 @@
 
 #include "b200_device.hpp"
 #include "b200_fields.hpp"
+#include "b200_residency.hpp"
 
 namespace libiop_b200 {
 
@@ -75,9 +76,9 @@ std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, Doma
     if (coeffs.size() > domain.num_elements())
         throw std::invalid_argument("FFT_over_field_subset: more coefficients than domain elements");
     device_buffer in(coeffs.size()), out(domain.num_elements());
-    in.upload(coeffs);
+    in.upload_async(coeffs);
     FFT_over_field_subset_device<FieldT>(in, coeffs.size(), domain, out);
-    return out.template download<FieldT>(domain.num_elements());
+    return download_and_keep<FieldT>(std::move(out), domain.num_elements());   /* the codeword stays resident for its consumers */
 }
 
 /* fft.hpp:70-76 */
@@ -88,7 +89,7 @@ std::vector<FieldT> IFFT_over_field_subset(const std::vector<FieldT> evals, Doma
         throw std::invalid_argument("IFFT_over_field_subset: evaluation vector does not match the domain");
     if (evals.size() == 1) return evals;           /* fft.tcc:397-401 */
     device_buffer in(evals.size()), out(evals.size());
-    in.upload(evals);
+    in.upload_async(evals);
     IFFT_over_field_subset_device<FieldT>(in, domain, out);
     return out.template download<FieldT>(evals.size());
 }
@@ -132,10 +133,10 @@ std::shared_ptr<std::vector<FieldT>> evaluate_next_f_i_over_entire_domain(
     const std::shared_ptr<std::vector<FieldT>> &f_i_evals, const DomainT &f_i_domain, const std::size_t coset_size, const FieldT x_i)
 {
     const std::size_t n = f_i_evals->size();
-    device_buffer in(n), out(n / coset_size);
-    in.upload(*f_i_evals);
-    evaluate_next_f_i_over_entire_domain_device<FieldT>(in, f_i_domain, coset_size, x_i, out);
-    return std::make_shared<std::vector<FieldT>>(out.template download<FieldT>(n / coset_size));
+    const device_view in(*f_i_evals);
+    device_buffer out(n / coset_size);
+    evaluate_next_f_i_over_entire_domain_device<FieldT>(in.buf(), f_i_domain, coset_size, x_i, out);
+    return std::make_shared<std::vector<FieldT>>(download_and_keep<FieldT>(std::move(out), n / coset_size));
 }
 
 } // namespace libiop_b200

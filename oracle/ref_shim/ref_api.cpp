@@ -39,6 +39,7 @@
 #ifdef B200_GPU_INTEGRATION
 /* the drop-in build serves the process's large blocks (the prover's oracles) from page-locked memory */
 #include "libiop_b200/host/b200_device.hpp"
+#include "libiop_b200/host/b200_residency.hpp"
 B200_DEFINE_PINNED_OPERATOR_NEW
 extern "C" void refgpu_arena_stats(uint64_t *slabs, uint64_t *reserved_bytes, uint64_t *free_bytes)
 {
@@ -46,6 +47,11 @@ extern "C" void refgpu_arena_stats(uint64_t *slabs, uint64_t *reserved_bytes, ui
     *slabs = a ? a->slab_count() : 0;
     *reserved_bytes = a ? a->reserved_bytes() : 0;
     *free_bytes = a ? a->free_bytes() : 0;
+}
+extern "C" void refgpu_residency_stats(uint64_t *hits, uint64_t *misses, uint64_t *stale)
+{
+    libiop_b200::residency &r = libiop_b200::residency::instance();
+    *hits = r.hits(); *misses = r.misses(); *stale = r.stale();
 }
 #define REFN(name) refgpu_##name
 #else

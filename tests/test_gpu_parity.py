@@ -358,6 +358,55 @@ def test_other_reference_provers_with_b200_dropin_are_bit_exact(golden, which, l
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == want[(which, log_n, zk)]
 
 
+def test_residency_cache_hits_are_true_copies(golden):
+    """The adapter keeps device copies of the codeword vectors it produced and reuses them when the reference hands
+    the same std::vector to the next stage (libiop_b200/host/b200_residency.hpp).  With B200_RESIDENCY_VERIFY=1 every
+    cache hit is compared in full against the host vector; all four provers must still emit the reference transcripts,
+    and the cache must actually be used."""
+    import subprocess, sys, os
+    from oracle_lib import ReferenceGpu
+    if not ReferenceGpu.available():
+        pytest.skip("oracle/_ref/libiopref_gpu.so not built (needs /root/reference at build time)")
+    code = r"""
+import hashlib, sys, ctypes as C
+sys.path.insert(0, 'tests')
+from oracle_lib import ReferenceGpu
+g = ReferenceGpu()
+out = []
+_, d, a = g.aurora_gf192(12, make_zk=False, verify=True); out.append(('aurora', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
+_, d, a = g.aurora_gf192(10, make_zk=True, verify=True); out.append(('aurora', 10, 1, len(d), hashlib.sha256(d).hexdigest(), a))
+_, d, a = g.aurora_edwards(12); out.append(('aurora_edwards', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
+_, d, a, _ = g.fractal_edwards(12); out.append(('fractal_edwards', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
+_, d, a = g.ligero_gf192(12, make_zk=False); out.append(('ligero_gf192', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
+h, m, s = C.c_uint64(), C.c_uint64(), C.c_uint64()
+g._real.refgpu_residency_stats(C.byref(h), C.byref(m), C.byref(s))
+for o in out: print('RES', *o)
+print('STATS', h.value, m.value, s.value)
+"""
+    env = dict(os.environ, B200_RESIDENCY_VERIFY="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    want = {}
+    for line in golden["aurora_fingerprints"]:
+        n, z, ln, h = str(line).split(",")
+        want[("aurora", int(n), int(z))] = (int(ln), h)
+    for line in golden["prover_fingerprints"]:
+        w, n, z, ln, h = str(line).split(",")
+        want[(w, int(n), int(z))] = (int(ln), h)
+    seen = 0
+    for line in r.stdout.splitlines():
+        if line.startswith("RES "):
+            _, w, n, z, ln, h, acc = line.split()
+            assert int(acc) == 1
+            assert (int(ln), h) == want[(w, int(n), int(z))], line
+            seen += 1
+        if line.startswith("STATS "):
+            hits = int(line.split()[1])
+            assert hits > 20, line
+    assert seen == 5
+
+
 # ------------------------------------------------------------------ proof of work (SURVEY §8f N2)
 def test_pow_solve(dev, oracle, golden):
     """b200_pow_solve returns the FIRST accepted candidate in the reference's order (pow.tcc:87-102)."""

@@ -49,3 +49,11 @@ def test_no_cpu_fallback_without_device():
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("B200() succeeded without a CUDA device")
+
+
+def test_pinned_arena_allocator_host_logic():
+    """tests/cpp/arena_test.cpp: free-list allocator behind the pinned operator new (malloc-backed slabs) and
+    make_uninitialized_vector."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "arena_test.bin"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(ROOT, "tests", "cpp", "arena_test.bin")], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failed" in out.stdout, out.stdout + out.stderr
