@@ -14,11 +14,16 @@ The elementwise virtual-oracle passes, proof-of-work and transcript assembly of 
 NOT in the step — this is stated in config.workload.
 
   value : inputs resident in HBM, CUDA-event timed on the context's stream.
-  e2e   : the same calls through the host-buffer C ABI (upload inputs from pinned host memory, download
-          every result), i.e. what the drop-in C++ adapter (libiop_b200/host/) does per call.
-  --impl reference : the unmodified reference's CPU implementation of the same calls (oracle/_ref,
-          built from /root/reference in the build container; falls back to the oracle port), on a bounded
-          sample of the workload, extrapolated by the reference's own operation counts.
+  e2e   : the WHOLE Aurora prover at N = 2^20 through the reference-facing API: the reference's own
+          aurora_snark_prover (unmodified libiop host code: IOP layer, protocols, BCS transformation, hash chain,
+          query phase) over host std::vectors, with this library dropped in under its hot-path headers
+          (libiop_b200/lib/libiop_b200_dropin.so, libiop_b200/dropin/).  Every oracle crosses PCIe inside the timed
+          region (h2d / d2h bytes are counted by the library).  value = 2^20 / prover wall seconds.  The transcript is
+          compared byte for byte with the CPU reference's in the whole_prover_dropin section.
+  hot_path_host_buffers : the star calls alone through the host-buffer C ABI (upload, kernel, download per call).
+  --impl reference : the unmodified reference aurora_snark_prover on the host CPU (oracle/_ref/libiopref.so, built
+          from /root/reference in the build container), single-threaded like the reference is, on a bounded sample
+          (N = 2^17) of the same workload; constraints/s.
 """
 import argparse
 import ctypes as C
@@ -309,8 +314,9 @@ def run_gpu(args):
                              "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
                      "note": "integer-pipe bound, not HBM bound: ~1050 instructions (289 IMAD.WIDE) per GF(2^192) multiplication, "
                              "100 multiplications per 24-byte coefficient; see DESIGN.md 3.1-3.2"},
-        "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
-                "ms_per_step": e2e_ms / e2e_steps},
+        "hot_path_host_buffers": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
+                                  "ms_per_step": e2e_ms / e2e_steps,
+                                  "what": "the star calls alone through the host-buffer C ABI (upload, kernel, download per call)"},
         "gpu_launches": None,
         "transcript_gather": {"ranks": len(all_roots), "bytes_per_rank": len(roots),
                               "distinct_instances": len(set(all_roots)) == len(all_roots)},
@@ -319,8 +325,21 @@ def run_gpu(args):
     # launches per step: counted from the scheduler; measured with ncu in profiles/
     out["gpu_launches"] = int(launches_per_step) * args.steps
     out["gpu_launches_per_step"] = int(launches_per_step)
+    # e2e: the whole reference prover over host vectors with the library dropped in, one proof per rank
+    e2e = whole_prover_e2e(LOG_N, runs=max(1, min(args.steps, 3)), warmup=2)
+    if dist:
+        import torch
+        t = torch.tensor([e2e.get("prover_s", float("inf"))], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if "prover_s" in e2e:
+            e2e["prover_s_max_over_ranks"] = float(t.item())
+    if "prover_s" in e2e:
+        secs = e2e.get("prover_s_max_over_ranks", e2e["prover_s"])
+        e2e = dict({"value": world * N / secs, "unit": "constraints/s"}, **e2e)
+    out["e2e"] = e2e
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
+        out["cpu_baseline_hot_path"] = cpu_baseline_hot_path(sample_log_n=args.cpu_sample_log_n)
     if rank == 0 and args.dropin_log_n:
         out["whole_prover_dropin"] = whole_prover_dropin(args.dropin_log_n)
     if rank == 0:
@@ -370,7 +389,65 @@ def cpu_reference_times(sample_log_n, use_ref=True):
     return kind, secs
 
 
-def cpu_baseline(sample_log_n=14):
+class _quiet_stdout:
+    """the reference printf()s its parameter blocks; keep stdout to the one JSON line"""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.devnull = os.open(os.devnull, os.O_WRONLY); self.saved = os.dup(1); os.dup2(self.devnull, 1)
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
+
+
+def whole_prover_e2e(log_n, runs=3, warmup=2):
+    """The reference's aurora_snark_prover over host vectors with the B200 library dropped in (libiop_b200/prover.py):
+    wall seconds of the prover call (instance generation excluded, get_transcript included — SURVEY.md §8d metric 1)."""
+    try:
+        from libiop_b200 import prover
+        if not prover.available():
+            return {"unavailable": "libiop_b200/lib/libiop_b200_dropin.so was not built (needs /root/reference at build time)"}
+        with _quiet_stdout():
+            p = prover.DropinProver()
+            for _ in range(warmup):
+                p.aurora_gf192(log_n, verify=False)
+            s0 = p.device_stats()
+            times, dump = [], b""
+            for _ in range(runs):
+                secs, dump, _ = p.aurora_gf192(log_n, verify=False)
+                times.append(secs)
+            s1 = p.device_stats()
+        import hashlib
+        return {"prover_s": float(np.median(times)), "prover_s_all": times,
+                "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // runs, "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // runs,
+                "gpu_launches_per_proof": (s1["launches"] - s0["launches"]) // runs,
+                "transcript_bytes": len(dump), "transcript_sha256": hashlib.sha256(dump).hexdigest(),
+                "api": "aurora_snark_prover<gf192, binary_hash_digest>(constraint_system, primary_input, auxiliary_input, params), N=2^%d, "
+                       "rho=3, FRI localization 2, non-zk, host std::vector oracles" % log_n,
+                "residency": p.residency_stats(), "pinned_arena": p.arena_stats()}
+    except Exception as e:
+        return {"unavailable": repr(e)}
+
+
+def cpu_reference_prover(sample_log_n):
+    """The unmodified reference aurora_snark_prover on one host core (the reference is single-threaded)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Reference
+    if not Reference.available():
+        return None
+    with _quiet_stdout():
+        secs, dump, _ = Reference().aurora_gf192(sample_log_n, verify=False)
+    return secs
+
+
+def cpu_baseline(sample_log_n=17):
+    secs = cpu_reference_prover(sample_log_n)
+    if secs is None:
+        return cpu_baseline_hot_path(sample_log_n)
+    return {"value": (1 << sample_log_n) / secs, "unit": "constraints/s", "cores": 1, "kind": "reference",
+            "sample": f"whole unmodified aurora_snark_prover at N=2^{sample_log_n} ({secs:.2f} s on 1 core; the reference has no threading); "
+                      f"same binary measured at N=2^20: 74.6 s = 14.05k constraints/s (profiles/r1_dropin_whole_prover_v2.jsonl)"}
+
+
+def cpu_baseline_hot_path(sample_log_n=14):
     kind, secs = cpu_reference_times(sample_log_n)
     # extrapolate by the reference's own multiplication counts (O(N log N))
     f_s, i_s, fo_s, _ = workload(sample_log_n)
@@ -390,46 +467,52 @@ def whole_prover_dropin(log_n):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     try:
         import hashlib
-        from oracle_lib import Reference, ReferenceGpu
-        if not (Reference.available() and ReferenceGpu.available()):
-            return {"unavailable": "oracle/_ref libraries were not built (need /root/reference at build time)"}
-        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)   # the reference printf()s its parameters
-        try:
-            g, r = ReferenceGpu(), Reference()
-            g.aurora_gf192(10, verify=False)
+        from oracle_lib import Reference
+        from libiop_b200 import prover
+        if not (Reference.available() and prover.available()):
+            return {"unavailable": "oracle/_ref/libiopref.so or libiop_b200/lib/libiop_b200_dropin.so was not built (need /root/reference at build time)"}
+        with _quiet_stdout():
+            g, r = prover.DropinProver(), Reference()
+            g.aurora_gf192(log_n, verify=False)
             gs, gd, acc = g.aurora_gf192(log_n, verify=True)
             cs, cd, _ = r.aurora_gf192(log_n, verify=False)
-        finally:
-            os.dup2(saved, 1); os.close(devnull); os.close(saved)
         return {"log_n": log_n, "cpu_reference_prover_s": cs, "dropin_prover_s": gs, "bit_exact_transcript": cd == gd,
                 "transcript_sha256": hashlib.sha256(gd).hexdigest(), "reference_verifier_accepts": acc == 1,
                 "cpu_constraints_per_s": (1 << log_n) / cs, "dropin_constraints_per_s": (1 << log_n) / gs,
-                "note": "host-side IOP code (virtual oracles, transcript assembly) is the unmodified single-threaded reference"}
+                "note": "same instance, CPU reference vs drop-in, transcripts compared byte for byte; host-side IOP code is the unmodified "
+                        "single-threaded reference in both"}
     except Exception as e:  # never let the optional section break the bench line
         return {"unavailable": repr(e)}
 
 
 def run_reference(args):
+    """Reference arm: the unmodified reference aurora_snark_prover on the host CPU, bounded sample N = 2^cpu_sample_log_n."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, args.warmup and 1)):
-        cpu_reference_times(args.cpu_sample_log_n - 2)
+    n = args.cpu_sample_log_n
+    if args.warmup:
+        cpu_reference_prover(max(10, n - 3))
+    times = []
     for _ in range(max(1, min(args.steps, 3))):
-        b = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
-        vals.append(b)
-    b = vals[-1]
-    v = float(np.mean([x["value"] for x in vals]))
+        secs = cpu_reference_prover(n)
+        if secs is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libiopref.so was not built (needs /root/reference at build time)"}))
+            return
+        times.append(secs)
+    secs = float(np.median(times))
+    v = (1 << n) / secs
     out = {"impl": "reference",
            "metric": "Aurora prover constraints/sec at N=2^20 (hot path: LDE + FRI fold + Merkle); LDE GF-ops/sec vs HBM roofline",
            "value": v, "unit": "constraints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": (1 << LOG_N) / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "gf2^192 (PCLMULQDQ)", "data": "synthetic",
-           "config": {"workload": "aurora_gf192_N2^20_rate1/8_fri_loc2_nonzk hot-path star calls, CPU reference, bounded sample",
-                      "log_n": LOG_N, "codeword_dim": M},
-           "cpu_baseline": dict(b, value=v),
+           "config": {"workload": f"aurora_gf192 rate1/8 fri_loc2 nonzk: whole unmodified aurora_snark_prover on the host CPU, bounded sample N=2^{n} "
+                                  f"(N=2^20 takes 75 s per proof: 14.05k constraints/s, profiles/r1_dropin_whole_prover_v2.jsonl)",
+                      "log_n": n, "codeword_dim": n + RHO},
+           "cpu_baseline": {"value": v, "unit": "constraints/s", "cores": 1, "kind": "reference",
+                            "sample": f"whole aurora_snark_prover at N=2^{n}, median of {len(times)} runs, single thread (the reference has no threading)"},
            "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
     print(json.dumps(out))
@@ -443,7 +526,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dropin-log-n", type=int, default=18, help="also run the reference prover with the B200 drop-in at this size (0 = skip)")
+    ap.add_argument("--dropin-log-n", type=int, default=18, help="side-by-side CPU reference vs drop-in prover with transcript comparison at this size (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

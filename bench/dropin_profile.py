@@ -1,17 +1,22 @@
-"""libff::enter_block profile of the reference prover with the B200 drop-in (B200_REF_PROFILE=1)."""
+"""libff::enter_block profile of the reference prover with the B200 drop-in (B200_REF_PROFILE=1); add B200_TRACE=1 for the
+per-call C-ABI trace.  Usage: python bench/dropin_profile.py [log_n] [gpu|cpu]"""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from oracle_lib import Reference, ReferenceGpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 which = sys.argv[2] if len(sys.argv) > 2 else "gpu"
-r = ReferenceGpu() if which == "gpu" else Reference()
 if which == "gpu":
+    from libiop_b200.prover import DropinProver
+    r = DropinProver()
     os.environ.pop("B200_REF_PROFILE", None)
+    r.aurora_gf192(log_n, verify=False)          # warm-up: plans, pinned slabs, device blocks
     r.aurora_gf192(log_n, verify=False)
     os.environ["B200_REF_PROFILE"] = "1"
-r.aurora_gf192(log_n, verify=False)
-if which == "gpu":
-    import ctypes as C
-    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    r._real.refgpu_arena_stats(C.byref(a), C.byref(b), C.byref(c))
-    print(f"pinned arena: {a.value} slabs, {b.value / 2**30:.2f} GiB reserved, {c.value / 2**30:.2f} GiB free", flush=True)
+    r.aurora_gf192(log_n, verify=False)
+    a = r.arena_stats(); s = r.residency_stats()
+    print(f"pinned arena: {a['slabs']} slabs, {a['reserved_bytes'] / 2**30:.2f} GiB reserved, {a['free_bytes'] / 2**30:.2f} GiB free; "
+          f"residency: {s['hits']} hits, {s['misses']} misses, {s['stale']} stale, {s['resident_bytes'] / 2**30:.2f} GiB resident", flush=True)
+else:
+    from oracle_lib import Reference
+    os.environ["B200_REF_PROFILE"] = "1"
+    Reference().aurora_gf192(log_n, verify=False)

@@ -183,6 +183,7 @@ int b200_pow_solve(b200_ctx *, const uint8_t *challenge, size_t digest_len, uint
 
 /* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the FFT tile passes ---- */
 unsigned long long b200_launch_count(b200_ctx *);
+void b200_transfer_bytes(b200_ctx *, unsigned long long *h2d, unsigned long long *d2h);   /* running totals of upload / download bytes */
 int b200_profile_begin(b200_ctx *);
 int b200_profile_end(b200_ctx *, char *buf, size_t cap);  /* "label\tms\n" per recorded launch; returns #records */
 

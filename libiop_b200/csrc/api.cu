@@ -135,12 +135,14 @@ void b200_host_free(b200_ctx *, void *p) { if (p) cudaFreeHost(p); }
 int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *src, size_t n_elems)
 {
     B200_TRACE_SCOPE(c, "upload", n_elems * 24);
+    c->h2d_bytes += n_elems * 24;
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, src, n_elems * 24, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems)
 {
     B200_TRACE_SCOPE(c, "download", n_elems * 24);
+    c->d2h_bytes += n_elems * 24;
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + src_offset * 24, n_elems * 24, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -148,12 +150,14 @@ int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, s
 int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_bytes)
 {
     B200_TRACE_SCOPE(c, "upload_bytes", n_bytes);
+    c->h2d_bytes += n_bytes;
     B200_CUDA(c, cudaMemcpyAsync((void *)(uintptr_t)dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes)
 {
     B200_TRACE_SCOPE(c, "download_bytes", n_bytes);
+    c->d2h_bytes += n_bytes;
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + offset, n_bytes, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -194,6 +198,11 @@ int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, siz
 
 /* ---- instrumentation ---- */
 unsigned long long b200_launch_count(b200_ctx *c) { return c->n_launches; }
+void b200_transfer_bytes(b200_ctx *c, unsigned long long *h2d, unsigned long long *d2h)
+{
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
+}
 int b200_profile_begin(b200_ctx *c)
 {
     for (auto &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

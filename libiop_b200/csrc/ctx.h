@@ -42,6 +42,7 @@ struct b200_ctx {
     std::map<std::string, std::shared_ptr<b200::NttPlan>> ntt_plans;
     /* instrumentation: every kernel launch is counted; with profiling on, tile passes are bracketed by events */
     unsigned long long n_launches = 0;
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;   /* bytes moved by upload / download / gather calls */
     bool trace = false;   /* B200_TRACE=1: every C-ABI compute/transfer call prints its synchronised wall time to stderr */
     bool profiling = false;
     struct ProfRec { std::string label; cudaEvent_t a, b; };
@@ -124,7 +125,9 @@ struct ApiTrace {
         if (c && c->trace) {
             cudaStreamSynchronize(c->stream);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            fprintf(stderr, "b200 %-28s %12zu %10.3f ms\n", name, detail, ms);
+            static const std::chrono::steady_clock::time_point epoch = std::chrono::steady_clock::now();
+            const double at = std::chrono::duration<double, std::milli>(t0 - epoch).count();
+            fprintf(stderr, "b200 %-28s %12zu %10.3f ms  @%10.3f\n", name, detail, ms, at);
         }
     }
 };

@@ -1,0 +1,91 @@
+/*
+ * sodium_shim.c — stand-ins for the two libsodium symbols libiop links against (INSTALL.md:10,21;
+ * libiop/bcs/hashing/blake2b.cpp:15,37,62, blake2b.tcc:56,146,172,200; libff random_element via randombytes_buf),
+ * for images without libsodium.  A deployment with libsodium installed links that instead and drops this file.
+ *   crypto_generichash_blake2b : RFC 7693 BLAKE2b, sequential mode, optional key, 1..64 byte digests
+ *   randombytes_buf            : seedable xorshift64 stream (deterministic instances / salts for parity runs);
+ *                                b200_shim_randombytes_seed(0) restores the default seed.
+ * Host-side control-plane hashing only (hash chain, query positions, verifier): bulk hashing runs on the device.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+static const uint64_t b2_iv[8] = {
+    0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL };
+
+static inline uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+
+/* message word schedule: sigma[r][i], generated from the RFC's first ten permutations (rounds 10, 11 repeat 0, 1) */
+static const uint8_t b2_sigma[10][16] = {
+    {  0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15 }, { 14, 10,  4,  8,  9, 15, 13,  6,  1, 12,  0,  2, 11,  7,  5,  3 },
+    { 11,  8, 12,  0,  5,  2, 15, 13, 10, 14,  3,  6,  7,  1,  9,  4 }, {  7,  9,  3,  1, 13, 12, 11, 14,  2,  6,  5, 10,  4,  0, 15,  8 },
+    {  9,  0,  5,  7,  2,  4, 10, 15, 14,  1, 11, 12,  6,  8,  3, 13 }, {  2, 12,  6, 10,  0, 11,  8,  3,  4, 13,  7,  5, 15, 14,  1,  9 },
+    { 12,  5,  1, 15, 14, 13,  4, 10,  0,  7,  6,  3,  9,  2,  8, 11 }, { 13, 11,  7, 14, 12,  1,  3,  9,  5,  0, 15,  4,  8,  6,  2, 10 },
+    {  6, 15, 14,  9, 11,  3,  0,  8, 12,  2, 13,  7,  1,  4, 10,  5 }, { 10,  2,  8,  4,  7,  6,  1,  5, 15, 11,  9, 14,  3, 12, 13,  0 } };
+
+typedef struct { uint64_t h[8]; uint64_t t; uint8_t block[128]; size_t fill; } b2_state;
+
+static void b2_compress(b2_state *s, int last)
+{
+    uint64_t m[16], v[16];
+    memcpy(m, s->block, 128);                      /* little-endian host (x86-64) */
+    for (int i = 0; i < 8; ++i) { v[i] = s->h[i]; v[8 + i] = b2_iv[i]; }
+    v[12] ^= s->t;                                 /* message lengths below 2^64 bytes: high counter word is zero */
+    if (last) v[14] = ~v[14];
+    for (int r = 0; r < 12; ++r) {
+        const uint8_t *sg = b2_sigma[r % 10];
+#define B2_MIX(a, b, c, d, x, y)                     \
+        v[a] += v[b] + m[x]; v[d] = rotr64(v[d] ^ v[a], 32); \
+        v[c] += v[d];        v[b] = rotr64(v[b] ^ v[c], 24); \
+        v[a] += v[b] + m[y]; v[d] = rotr64(v[d] ^ v[a], 16); \
+        v[c] += v[d];        v[b] = rotr64(v[b] ^ v[c], 63);
+        B2_MIX(0, 4,  8, 12, sg[0],  sg[1])  B2_MIX(1, 5,  9, 13, sg[2],  sg[3])
+        B2_MIX(2, 6, 10, 14, sg[4],  sg[5])  B2_MIX(3, 7, 11, 15, sg[6],  sg[7])
+        B2_MIX(0, 5, 10, 15, sg[8],  sg[9])  B2_MIX(1, 6, 11, 12, sg[10], sg[11])
+        B2_MIX(2, 7,  8, 13, sg[12], sg[13]) B2_MIX(3, 4,  9, 14, sg[14], sg[15])
+#undef B2_MIX
+    }
+    for (int i = 0; i < 8; ++i) s->h[i] ^= v[i] ^ v[8 + i];
+}
+
+static void b2_absorb(b2_state *s, const uint8_t *in, size_t n)
+{
+    while (n) {
+        if (s->fill == 128) { s->t += 128; b2_compress(s, 0); s->fill = 0; }   /* a full block is only final if no byte follows */
+        const size_t take = (128 - s->fill < n) ? 128 - s->fill : n;
+        memcpy(s->block + s->fill, in, take);
+        s->fill += take; in += take; n -= take;
+    }
+}
+
+int crypto_generichash_blake2b(unsigned char *out, size_t outlen, const unsigned char *in, unsigned long long inlen,
+                               const unsigned char *key, size_t keylen)
+{
+    if (outlen == 0 || outlen > 64 || keylen > 64) return -1;
+    b2_state s;
+    memset(&s, 0, sizeof s);
+    memcpy(s.h, b2_iv, sizeof s.h);
+    s.h[0] ^= 0x01010000ULL ^ ((uint64_t)keylen << 8) ^ (uint64_t)outlen;   /* fanout = depth = 1 */
+    if (keylen) { uint8_t kb[128] = {0}; memcpy(kb, key, keylen); b2_absorb(&s, kb, 128); }
+    b2_absorb(&s, in, (size_t)inlen);
+    s.t += s.fill;
+    memset(s.block + s.fill, 0, 128 - s.fill);
+    b2_compress(&s, 1);
+    memcpy(out, s.h, outlen);
+    return 0;
+}
+
+static uint64_t shim_rng_state = 0x9E3779B97F4A7C15ULL;
+void b200_shim_randombytes_seed(uint64_t seed) { shim_rng_state = seed ? seed : 0x9E3779B97F4A7C15ULL; }
+void randombytes_buf(void *buf, size_t size)
+{
+    unsigned char *p = (unsigned char *)buf;
+    for (size_t i = 0; i < size; ++i) {
+        shim_rng_state ^= shim_rng_state << 13;
+        shim_rng_state ^= shim_rng_state >> 7;
+        shim_rng_state ^= shim_rng_state << 17;
+        p[i] = (unsigned char)(shim_rng_state >> 32);
+    }
+}

@@ -10,6 +10,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -33,7 +34,10 @@ inline b200_ctx *context()
 {
     static b200_ctx *ctx = nullptr;
     if (!ctx) {
-        ctx = b200_ctx_create(0);
+        /* device ordinal: B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun / mpirun), else 0 */
+        const char *d = std::getenv("B200_DEVICE");
+        if (!d) d = std::getenv("LOCAL_RANK");
+        ctx = b200_ctx_create(d ? std::atoi(d) : 0);
         if (!ctx) throw std::runtime_error("libiop_b200: no CUDA device (the hot path has no CPU fallback)");
     }
     return ctx;

@@ -163,6 +163,15 @@ private:
     std::map<uintptr_t, std::size_t> free_, used_;
 };
 
+/* Called with the address of every arena block just before it is released (the residency cache uses it to drop the
+   device copy of a host vector the moment the vector dies).  One hook per process. */
+typedef void (*arena_release_hook_fn)(void *);
+inline arena_release_hook_fn &arena_release_hook()
+{
+    static arena_release_hook_fn hook = nullptr;
+    return hook;
+}
+
 /* std::vector<T> of n elements whose storage is NOT value-initialised (the caller overwrites all of it, e.g. by a
    device->host copy).  std::vector offers no such constructor; with libstdc++ / libc++ (three-pointer layout
    {begin, end, end_of_storage}) the end pointer is advanced over reserved storage.  Any other library takes the
@@ -226,7 +235,11 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
     {                                                                                                                    \
         if (!p) return;                                                                                                  \
         pinned_arena *a = arena();                                                                                       \
-        if (a && a->release(p)) return;                                                                                  \
+        if (a && a->owns((uintptr_t)p)) {                                                                                \
+            if (arena_release_hook()) arena_release_hook()(p);                                                           \
+            a->release(p);                                                                                               \
+            return;                                                                                                      \
+        }                                                                                                                \
         std::free(p);                                                                                                    \
     }                                                                                                                    \
     } }                                                                                                                  \

@@ -10,7 +10,9 @@
  * Safety: a hit requires the same address AND length AND an equal sample of 32 elements (first, last, evenly strided)
  * read from the host vector at lookup time, so an allocation recycled for different contents is never mistaken for
  * the vector that was registered.  Only codeword-domain evaluation vectors are registered (immutable once submitted,
- * iop.tcc:272-307); B200_RESIDENCY_VERIFY=1 additionally compares the complete contents on every hit (debug / tests),
+ * iop.tcc:272-307).  When the process uses the pinned arena (b200_pinned_arena.hpp) the cache is told the moment a
+ * host block is released and drops the entry, so device memory follows the lifetime of the host vectors.
+ * B200_RESIDENCY_VERIFY=1 additionally compares the complete contents on every hit (debug / tests),
  * B200_RESIDENCY=0 disables the cache.  The cache is LRU with a byte budget (B200_RESIDENT_GB, default 24).
  */
 #ifndef LIBIOP_B200_RESIDENCY_HPP_
@@ -47,9 +49,18 @@ class residency {
         verify_ = v && v[0] == '1';
         const char *g = std::getenv("B200_RESIDENT_GB");
         budget_ = (std::size_t)(g ? std::strtoull(g, nullptr, 10) : 24) << 30;
+        arena_release_hook() = &residency::host_block_released;
     }
+    /* the pinned arena is about to recycle this host block: its device copy is dead weight from now on */
+    static void host_block_released(void *p) { instance().drop(p); }
 public:
-    static residency &instance() { static residency r; return r; }
+    static residency &instance() { static residency *r = new residency(); return *r; }   /* never destroyed: outlives every vector */
+    void drop(const void *host)
+    {
+        if (lru_.empty()) return;
+        for (auto it = lru_.begin(); it != lru_.end(); ++it)
+            if (it->host == host) { bytes_ -= it->n * 24; lru_.erase(it); return; }
+    }
     static constexpr std::size_t min_elems = 4096;
 
     /* park `buf` (n elements) as the device copy of the host array at `host` */

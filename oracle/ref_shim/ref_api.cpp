@@ -36,27 +36,7 @@
 #include "libiop/snark/ligero_snark.hpp"
 #include "libiop/relations/examples/r1cs_examples.hpp"
 
-#ifdef B200_GPU_INTEGRATION
-/* the drop-in build serves the process's large blocks (the prover's oracles) from page-locked memory */
-#include "libiop_b200/host/b200_device.hpp"
-#include "libiop_b200/host/b200_residency.hpp"
-B200_DEFINE_PINNED_OPERATOR_NEW
-extern "C" void refgpu_arena_stats(uint64_t *slabs, uint64_t *reserved_bytes, uint64_t *free_bytes)
-{
-    libiop_b200::pinned_arena *a = libiop_b200::pinned_new_detail::arena();
-    *slabs = a ? a->slab_count() : 0;
-    *reserved_bytes = a ? a->reserved_bytes() : 0;
-    *free_bytes = a ? a->free_bytes() : 0;
-}
-extern "C" void refgpu_residency_stats(uint64_t *hits, uint64_t *misses, uint64_t *stale)
-{
-    libiop_b200::residency &r = libiop_b200::residency::instance();
-    *hits = r.hits(); *misses = r.misses(); *stale = r.stale();
-}
-#define REFN(name) refgpu_##name
-#else
 #define REFN(name) ref_##name
-#endif
 
 using namespace libiop;
 typedef libff::gf192 G;

@@ -224,9 +224,8 @@ class Oracle:
 
 
 class Reference:
-    """The unmodified reference (oracle/_ref/libiopref.so), when present.
-    With gpu=True: the same reference prover built with the B200 adapter shadowing its three hot-path
-    headers (oracle/_ref/libiopref_gpu.so, `make -C oracle refgpu`) — the drop-in integration build."""
+    """The unmodified reference on the CPU (oracle/_ref/libiopref.so), when present: the checker for the whole-prover
+    parity tests and the CPU baseline of bench.py."""
     PREFIX = "ref_"
     LIBNAME = "libiopref.so"
 
@@ -396,7 +395,26 @@ class Reference:
                                                      C.c_uint64(seed), C.c_int(int(verify))))
 
 
-class ReferenceGpu(Reference):
-    """Reference prover + B200 drop-in (needs a CUDA device at call time)."""
-    PREFIX = "refgpu_"
-    LIBNAME = "libiopref_gpu.so"
+def _dropin():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from libiop_b200 import prover
+    return prover
+
+
+class ReferenceGpu:
+    """The product under test at whole-prover level: libiop_b200/lib/libiop_b200_dropin.so — the reference's own provers
+    with the B200 library dropped in (libiop_b200/dropin/, bound by libiop_b200/prover.py).  Same call signatures as
+    Reference above so the parity tests run both side by side.  Needs a CUDA device at call time."""
+
+    @classmethod
+    def available(cls):
+        return _dropin().available()
+
+    def __init__(self):
+        self._p = _dropin().DropinProver()
+
+    def __getattr__(self, name):
+        return getattr(self._p, name)

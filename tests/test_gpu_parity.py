@@ -306,15 +306,15 @@ def test_cpp_adapter_reference_style_tests():
 # ------------------------------------------------------------------ whole-prover drop-in parity (T5, T6)
 @pytest.mark.parametrize("log_n,zk", [(10, False), (10, True), (12, False), (14, False)])
 def test_reference_prover_with_b200_dropin_is_bit_exact(golden, log_n, zk):
-    """The UNMODIFIED reference aurora_snark_prover, compiled with the B200 adapter shadowing its three
-    hot-path headers (oracle/ref_shim/gpu_overrides -> oracle/_ref/libiopref_gpu.so), must emit the same
+    """The UNMODIFIED reference aurora_snark_prover, compiled with the B200 adapter shadowing its hot-path
+    headers (libiop_b200/dropin -> libiop_b200/lib/libiop_b200_dropin.so), must emit the same
     transcript bytes as the CPU reference (canonical dump of SURVEY.md §8c), and the reference verifier
     must accept it.  Fingerprints of the CPU run are in the golden fixture (N=2^10, 2^12); where the CPU
     reference library travelled to this box it is also run side by side."""
     import hashlib
     from oracle_lib import Reference, ReferenceGpu
     if not ReferenceGpu.available():
-        pytest.skip("oracle/_ref/libiopref_gpu.so not built (needs /root/reference at build time)")
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
     g = ReferenceGpu()
     secs, dump, accepted = g.aurora_gf192(log_n, make_zk=zk, verify=True)
     assert accepted == 1, "reference verifier rejected the GPU-built proof"
@@ -342,7 +342,7 @@ def test_other_reference_provers_with_b200_dropin_are_bit_exact(golden, which, l
     import hashlib
     from oracle_lib import ReferenceGpu
     if not ReferenceGpu.available():
-        pytest.skip("oracle/_ref/libiopref_gpu.so not built (needs /root/reference at build time)")
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
     g = ReferenceGpu()
     if which == "aurora_edwards":
         _, dump, acc = g.aurora_edwards(log_n)
@@ -366,7 +366,7 @@ def test_residency_cache_hits_are_true_copies(golden):
     import subprocess, sys, os
     from oracle_lib import ReferenceGpu
     if not ReferenceGpu.available():
-        pytest.skip("oracle/_ref/libiopref_gpu.so not built (needs /root/reference at build time)")
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
     code = r"""
 import hashlib, sys, ctypes as C
 sys.path.insert(0, 'tests')
@@ -378,10 +378,9 @@ _, d, a = g.aurora_gf192(10, make_zk=True, verify=True); out.append(('aurora', 1
 _, d, a = g.aurora_edwards(12); out.append(('aurora_edwards', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
 _, d, a, _ = g.fractal_edwards(12); out.append(('fractal_edwards', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
 _, d, a = g.ligero_gf192(12, make_zk=False); out.append(('ligero_gf192', 12, 0, len(d), hashlib.sha256(d).hexdigest(), a))
-h, m, s = C.c_uint64(), C.c_uint64(), C.c_uint64()
-g._real.refgpu_residency_stats(C.byref(h), C.byref(m), C.byref(s))
+st = g.residency_stats()
 for o in out: print('RES', *o)
-print('STATS', h.value, m.value, s.value)
+print('STATS', st['hits'], st['misses'], st['stale'])
 """
     env = dict(os.environ, B200_RESIDENCY_VERIFY="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
