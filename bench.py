@@ -304,7 +304,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                     "traffic": 348.4e6, "traffic_source": "ncu --set full, profiles/r1_tilepass_ncu_summary.md (dram read+write per launch)",
+                     "traffic": 350.5e6, "traffic_source": "ncu --set full, profiles/r1_ncu_summary_v2.md (dram read+write of one butterfly pass)",
                      "algorithmic_bytes_per_launch": pass_bytes, "launch_ms": dom_ms, "launch_label": dom_label,
                      "gf_mul_per_s_in_kernel": 8 * (n_l // 2) / (dom_ms * 1e-3), "gf_mul_peak_measured": 20.2e9,
                      "frac_of_multiplier_peak": 8 * (n_l // 2) / (dom_ms * 1e-3) / 20.2e9,
@@ -312,8 +312,8 @@ def run_gpu(args):
                              "algorithmic_bytes": lde_bytes, "achieved_gbs": lde_gbs, "frac": lde_gbs / peak,
                              "gf_mul_per_s_reference_count": 1.5 * M * n_l / (lde_ms * 1e-3),
                              "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
-                     "note": "integer-pipe bound, not HBM bound: ~1050 instructions (289 IMAD.WIDE) per GF(2^192) multiplication, "
-                             "100 multiplications per 24-byte coefficient; see DESIGN.md 3.1-3.2"},
+                     "note": "integer-pipe bound, not HBM bound: ~950 warp instructions (289 IMAD.WIDE) per GF(2^192) multiplication-butterfly, "
+                             "100 multiplications per 24-byte coefficient; see DESIGN.md 3.1-3.2 and profiles/r1_ncu_summary_v2.md"},
         "hot_path_host_buffers": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
                                   "ms_per_step": e2e_ms / e2e_steps,
                                   "what": "the star calls alone through the host-buffer C ABI (upload, kernel, download per call)"},
@@ -448,7 +448,8 @@ def cpu_baseline(sample_log_n=17):
 
 
 def cpu_baseline_hot_path(sample_log_n=14):
-    kind, secs = cpu_reference_times(sample_log_n)
+    with _quiet_stdout():
+        kind, secs = cpu_reference_times(sample_log_n)
     # extrapolate by the reference's own multiplication counts (O(N log N))
     f_s, i_s, fo_s, _ = workload(sample_log_n)
     f_f, i_f, fo_f, _ = workload(LOG_N)

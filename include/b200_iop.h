@@ -150,6 +150,9 @@ int b200_vec_lincomb(b200_ctx *, int field, const b200_fp_params *fp, b200_buf o
  * f - (c*x^(|H|-1) + Z_H*h) (sumcheck.tcc:95-99). */
 int b200_vec_mul_add(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf b, b200_buf c,
                      b200_buf d, int subtract, size_t n);
+/* out[i] = a[i] * mul + add with host scalars mul / add (NULL = absent): f - claimed_eval (boundary_constraint.tcc:56-60),
+ * x - y_i (lagrange_polynomial.tcc:76-85), k * v (batch_inverse_and_mul, algebra/utils.tcc:38-69). */
+int b200_vec_affine(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, const uint64_t *mul, const uint64_t *add, size_t n);
 /* out[i] = a[i] * table[(i >> shift) & mask] (a == 0: the table value itself): factors that repeat over cosets of H in L,
  * e.g. Z_H^-1 in rowcheck (rowcheck.tcc:36-84: additive shift = log|H|, multiplicative shift = 0, mask = |L|/|H| - 1). */
 int b200_vec_mul_table(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf table,

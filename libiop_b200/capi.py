@@ -352,6 +352,17 @@ class B200:
                 if b_:
                     self.free(b_)
 
+    def vec_affine(self, field, fp, a, mul=None, add=None):
+        n = len(a)
+        da = self.upload(a); o = self.alloc(max(n, 1))
+        mp = np.ascontiguousarray(mul, dtype=np.uint64).ctypes.data_as(_u64p) if mul is not None else None
+        ap = np.ascontiguousarray(add, dtype=np.uint64).ctypes.data_as(_u64p) if add is not None else None
+        try:
+            self._chk(self.lib.b200_vec_affine(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(o), C.c_uint64(da), mp, ap, C.c_size_t(n)))
+            return self.download(o, n)
+        finally:
+            self.free(da); self.free(o)
+
     def vec_mul_table(self, field, fp, a, table, shift, mask, n=None):
         n = len(a) if a is not None else n
         da = self.upload(a) if a is not None else 0

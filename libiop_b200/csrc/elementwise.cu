@@ -112,6 +112,19 @@ mul_add_kernel(typename F::T *out, const typename F::T *a, const typename F::T *
     }
 }
 
+/* ---- 2b. out[i] = a[i] * mul + add with scalar mul / add (either may be absent) -------------------------------- */
+template<typename F> __global__ void __launch_bounds__(256)
+affine_kernel(typename F::T *out, const typename F::T *a, const typename F::T mul, const typename F::T add, int has_mul, int has_add,
+              size_t n, const F f)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        typename F::T r = ld_el(a, i);
+        if (has_mul) r = f.mul(r, mul);
+        if (has_add) r = f.add(r, add);
+        st_el(out, i, r);
+    }
+}
+
 /* ---- 3. out[i] = a[i] * table[(i >> shift) & mask]   (values that repeat over cosets, e.g. Z_H^-1: rowcheck.tcc:36-84) */
 template<typename F> __global__ void __launch_bounds__(256)
 mul_table_kernel(typename F::T *out, const typename F::T *a, const typename F::T *table, uint32_t shift, size_t mask, size_t n, const F f)
@@ -386,6 +399,21 @@ int b200_vec_mul_add(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf 
     else
         mul_add_kernel<FpF><<<ew_grid(c, n, 256), 256, 0, c->stream>>>((fp192 *)out, (const fp192 *)a, (const fp192 *)b, (const fp192 *)cc,
                                                                       (const fp192 *)d, subtract, n, make_fpf(fp));
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int b200_vec_affine(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, const uint64_t *mul, const uint64_t *add, size_t n)
+{
+    B200_TRACE_SCOPE(c, "vec_affine", n);
+    if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
+    if (!n) return 0;
+    if (field == B200_FIELD_GF192)
+        affine_kernel<GfF><<<ew_grid(c, n, 256), 256, 0, c->stream>>>((gf192 *)out, (const gf192 *)a, mul ? host_el<gf192>(mul) : gf_zero(),
+                                                                     add ? host_el<gf192>(add) : gf_zero(), mul != nullptr, add != nullptr, n, GfF());
+    else
+        affine_kernel<FpF><<<ew_grid(c, n, 256), 256, 0, c->stream>>>((fp192 *)out, (const fp192 *)a, mul ? host_el<fp192>(mul) : fp_zero(),
+                                                                     add ? host_el<fp192>(add) : fp_zero(), mul != nullptr, add != nullptr, n, make_fpf(fp));
     B200_LAUNCH_CHECK(c);
     return 0;
 }

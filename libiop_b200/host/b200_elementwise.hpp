@@ -50,6 +50,22 @@ void vec_mul_add(device_buffer &out, const device_buffer &a, const device_buffer
                                              b ? b->get() : 0, c ? c->get() : 0, d ? d->get() : 0, subtract ? 1 : 0, n));
 }
 
+/* out = a * mul + add with scalar mul / add (nullptr = absent) */
+template<typename FieldT>
+void vec_affine(device_buffer &out, const device_buffer &a, const FieldT *mul, const FieldT *add, std::size_t n)
+{
+    throw_status(context(), b200_vec_affine(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), out.get(), a.get(),
+                                            mul ? limbs(*mul) : nullptr, add ? limbs(*add) : nullptr, n));
+}
+
+/* out[i] = a[i]^-1 (zero stays zero, as in the reference's batch_inverse with has_zeroes, algebra/utils.tcc:73-103) */
+template<typename FieldT>
+void vec_inverse(device_buffer &out, const device_buffer &a, std::size_t n)
+{
+    if (field_traits<FieldT>::kind == B200_FIELD_GF192) throw_status(context(), b200_gf192_inv(context(), out.get(), a.get(), n));
+    else throw_status(context(), b200_fp_inv(context(), field_traits<FieldT>::fp(), out.get(), a.get(), n));
+}
+
 /* out[i] = a[i] * table[(i >> shift) & mask] */
 template<typename FieldT>
 void vec_mul_table(device_buffer &out, const device_buffer *a, const std::vector<FieldT> &table, unsigned shift, std::size_t mask, std::size_t n)
@@ -111,6 +127,21 @@ void domain_element_powers(device_buffer &out, const DomainT &domain, std::size_
     } else {
         geometric_sequence<FieldT>(out, domain.num_elements(), scale * field_pow(domain.shift(), exponent),
                                    field_pow(domain.generator(), exponent), FieldT::zero());
+    }
+}
+
+/* sign * x + offset for every element x of the domain, sign = +1 or -1 (all_elements / all_subset_sums with a shifted
+   offset, e.g. x - eval_point in boundary_constraint.tcc:30-50 or x_0 - y in lagrange_polynomial.tcc:72-85) */
+template<typename FieldT, typename DomainT>
+void domain_elements_affine(device_buffer &out, const DomainT &domain, bool negate, const FieldT &offset)
+{
+    const FieldT sign = negate ? -FieldT::one() : FieldT::one();
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        std::vector<FieldT> t = affine_function_table<FieldT>(domain, [](const FieldT &x) { return x; }, sign);
+        t[0] += offset;
+        subspace_function_product<FieldT>(out, domain.dimension(), { t });
+    } else {
+        geometric_sequence<FieldT>(out, domain.num_elements(), sign * domain.shift(), domain.generator(), offset);
     }
 }
 

@@ -229,3 +229,58 @@ def test_poly_divide_sparse(dev, oracle, fp, field, log_deg, n_p, linearized):
                 quo[i + pw - deg] = F.sub(quo[i + pw - deg:i + pw - deg + 1], t)[0]
     q, r = dev.poly_divide_sparse(field, fp if field == FP else None, P, deg, lead_inv, coefs, pows)
     assert (q == quo).all() and (r == rem).all()
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1001, 65537])
+def test_gf192_inv_ragged_and_zeros(dev, oracle, n):
+    """b200_gf192_inv shares one inversion per run of 8 elements (Montgomery's trick, algebra/utils.tcc:38-103): ragged
+    tails and zero elements (inverse taken as zero, like the reference's has_zeroes path) must not disturb neighbours."""
+    rng = np.random.default_rng(n)
+    a = rand_elems(rng, n)
+    zeros = rng.integers(0, n, size=max(1, n // 5))
+    a[zeros] = 0
+    if n > 20:
+        a[8:16] = 0                      # a whole run of zeros
+    got = dev.gf192_inv(a)
+    nz = (a != 0).any(axis=1)
+    want = np.zeros_like(a)
+    if nz.any():
+        want[nz] = oracle.gf192_inv(a[nz])
+    assert (got == want).all()
+    one = np.zeros((int(nz.sum()), 3), dtype=np.uint64); one[:, 0] = 1
+    assert (oracle.gf192_mul(got[nz], a[nz]) == one).all()
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+def test_vec_affine(dev, oracle, fp, field):
+    """out = a*mul + add with scalars: f - claimed_eval (boundary_constraint.tcc:56-60), k * v (utils.tcc:38-69)."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(3)
+    n = 30011
+    a = F.rand(rng, n)
+    m, c = F.rand(rng, 2)
+    fpp = fp if field == FP else None
+    assert (dev.vec_affine(field, fpp, a, m, c) == F.add(F.mul(a, bcast(m, n)), bcast(c, n))).all()
+    assert (dev.vec_affine(field, fpp, a, m, None) == F.mul(a, bcast(m, n))).all()
+    assert (dev.vec_affine(field, fpp, a, None, c) == F.add(a, bcast(c, n))).all()
+    assert (dev.vec_affine(field, fpp, a, None, None) == a).all()
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 1000, 40001])
+def test_fp_inv_ragged_and_zeros(dev, oracle, fp, n):
+    """b200_fp_inv shares one Fermat inversion per run of 16 elements (Montgomery's trick, algebra/utils.tcc:38-103)."""
+    rng = np.random.default_rng(n + 5)
+    a = oracle.rand_fp(rng, n)
+    a[rng.integers(0, n, size=max(1, n // 7))] = 0
+    if n > 40:
+        a[16:32] = 0
+    got = dev.fp_inv(fp, a)
+    nz = (a != 0).any(axis=1)
+    assert (got[~nz] == 0).all()
+    one = bcast(np.array(list(fp.one_mont), dtype=np.uint64), int(nz.sum()))
+    if nz.any():
+        assert (oracle.fp_mul(got[nz], a[nz]) == one).all()
+        k = min(50, int(nz.sum()))
+        idx = np.nonzero(nz)[0][:k]
+        for i in idx:
+            assert (got[i] == oracle.fp_inv(a[i])).all()
