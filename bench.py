@@ -326,7 +326,7 @@ def run_gpu(args):
     out["gpu_launches"] = int(launches_per_step) * args.steps
     out["gpu_launches_per_step"] = int(launches_per_step)
     # e2e: the whole reference prover over host vectors with the library dropped in, one proof per rank
-    e2e = whole_prover_e2e(LOG_N, runs=max(1, min(args.steps, 3)), warmup=2)
+    e2e = whole_prover_e2e(LOG_N, runs=max(1, min(args.steps, 3)), warmup=2, seed_offset=rank)
     if dist:
         import torch
         t = torch.tensor([e2e.get("prover_s", float("inf"))], device="cuda")
@@ -398,7 +398,7 @@ class _quiet_stdout:
         os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
 
 
-def whole_prover_e2e(log_n, runs=3, warmup=2):
+def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0):
     """The reference's aurora_snark_prover over host vectors with the B200 library dropped in (libiop_b200/prover.py):
     wall seconds of the prover call (instance generation excluded, get_transcript included — SURVEY.md §8d metric 1)."""
     try:
@@ -407,19 +407,20 @@ def whole_prover_e2e(log_n, runs=3, warmup=2):
             return {"unavailable": "libiop_b200/lib/libiop_b200_dropin.so was not built (needs /root/reference at build time)"}
         with _quiet_stdout():
             p = prover.DropinProver()
+            seed = prover.DEFAULT_SEED + seed_offset          # one independent instance per rank (BASELINE config 5: seeds s, s+1, ...)
             for _ in range(warmup):
-                p.aurora_gf192(log_n, verify=False)
+                p.aurora_gf192(log_n, seed=seed, verify=False)
             s0 = p.device_stats()
             times, dump = [], b""
             for _ in range(runs):
-                secs, dump, _ = p.aurora_gf192(log_n, verify=False)
+                secs, dump, _ = p.aurora_gf192(log_n, seed=seed, verify=False)
                 times.append(secs)
             s1 = p.device_stats()
         import hashlib
         return {"prover_s": float(np.median(times)), "prover_s_all": times,
                 "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // runs, "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // runs,
                 "gpu_launches_per_proof": (s1["launches"] - s0["launches"]) // runs,
-                "transcript_bytes": len(dump), "transcript_sha256": hashlib.sha256(dump).hexdigest(),
+                "transcript_bytes": len(dump), "transcript_sha256": hashlib.sha256(dump).hexdigest(), "instance_seed": hex(seed),
                 "api": "aurora_snark_prover<gf192, binary_hash_digest>(constraint_system, primary_input, auxiliary_input, params), N=2^%d, "
                        "rho=3, FRI localization 2, non-zk, host std::vector oracles" % log_n,
                 "residency": p.residency_stats(), "pinned_arena": p.arena_stats()}

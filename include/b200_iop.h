@@ -153,6 +153,8 @@ int b200_vec_mul_add(b200_ctx *, int field, const b200_fp_params *fp, b200_buf o
 /* out[i] = a[i] * mul + add with host scalars mul / add (NULL = absent): f - claimed_eval (boundary_constraint.tcc:56-60),
  * x - y_i (lagrange_polynomial.tcc:76-85), k * v (batch_inverse_and_mul, algebra/utils.tcc:38-69). */
 int b200_vec_affine(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, const uint64_t *mul, const uint64_t *add, size_t n);
+/* first index whose element is zero, n if there is none (the y = x position in lagrange_polynomial.tcc:86-104) */
+int b200_vec_find_zero(b200_ctx *, b200_buf a, size_t n, size_t *index_out);
 /* out[i] = a[i] * table[(i >> shift) & mask] (a == 0: the table value itself): factors that repeat over cosets of H in L,
  * e.g. Z_H^-1 in rowcheck (rowcheck.tcc:36-84: additive shift = log|H|, multiplicative shift = 0, mask = |L|/|H| - 1). */
 int b200_vec_mul_table(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf table,

@@ -125,6 +125,13 @@ affine_kernel(typename F::T *out, const typename F::T *a, const typename F::T mu
     }
 }
 
+/* ---- 2c. first index holding the zero element (n if none): the x = y position of a Lagrange denominator vector ---- */
+__global__ void __launch_bounds__(256) find_zero_kernel(const uint64_t *a, size_t n, unsigned long long *first)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if ((__ldg(a + 3 * i) | __ldg(a + 3 * i + 1) | __ldg(a + 3 * i + 2)) == 0) atomicMin(first, (unsigned long long)i);
+}
+
 /* ---- 3. out[i] = a[i] * table[(i >> shift) & mask]   (values that repeat over cosets, e.g. Z_H^-1: rowcheck.tcc:36-84) */
 template<typename F> __global__ void __launch_bounds__(256)
 mul_table_kernel(typename F::T *out, const typename F::T *a, const typename F::T *table, uint32_t shift, size_t mask, size_t n, const F f)
@@ -415,6 +422,23 @@ int b200_vec_affine(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf o
         affine_kernel<FpF><<<ew_grid(c, n, 256), 256, 0, c->stream>>>((fp192 *)out, (const fp192 *)a, mul ? host_el<fp192>(mul) : fp_zero(),
                                                                      add ? host_el<fp192>(add) : fp_zero(), mul != nullptr, add != nullptr, n, make_fpf(fp));
     B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int b200_vec_find_zero(b200_ctx *c, b200_buf a, size_t n, size_t *index_out)
+{
+    B200_TRACE_SCOPE(c, "vec_find_zero", n);
+    unsigned long long *dev = (unsigned long long *)scratch_get(c, 3, 64);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate scratch");
+    unsigned long long first = (unsigned long long)n;
+    B200_CUDA(c, cudaMemcpyAsync(dev, &first, 8, cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        find_zero_kernel<<<ew_grid(c, n, 256), 256, 0, c->stream>>>((const uint64_t *)(uintptr_t)a, n, dev);
+        B200_LAUNCH_CHECK(c);
+    }
+    B200_CUDA(c, cudaMemcpyAsync(&first, dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    *index_out = (size_t)first;
     return 0;
 }
 
