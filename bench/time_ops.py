@@ -36,4 +36,11 @@ e2 = [rnd(1 << m) for _ in range(3)]
 res["merkle 4x2^23 c2"] = t(lambda: dev.merkle_build_dev([e] + e2, 1 << m, 2, 1, nodes))
 res["merkle 1x2^23 c2"] = t(lambda: dev.merkle_build_dev([e], 1 << m, 2, 1, nodes))
 res["merkle 1x2^22 c4"] = t(lambda: dev.merkle_build_dev([e], 1 << 22, 4, 1, nodes))
+# prime-field NTT (BASELINE config 3 shape: 2^20 coefficients onto the 2^23 coset, and the 2^20 inverse)
+fp = L.FpParams.edwards_fr()
+gen = np.array(fp.to_mont(19), dtype=np.uint64)
+cd23, cd20 = L.Domain.coset(fp, 23, gen), L.Domain.coset(fp, 20, gen)
+res["ntt 2^20->2^23"] = t(lambda: dev.fp_ntt_dev(fp, cd23, c, 1 << n, e))
+res["intt 2^20"] = t(lambda: dev.fp_intt_dev(fp, cd20, c, o))
+res["fold fp 2^23 eta1"] = t(lambda: dev.fri_fold_dev(2, fp, cd23, 1, x, e, f))
 print(os.environ.get("B200_LIB", "default"), " | ".join(f"{k}: {v:.3f} ms" for k, v in res.items()))
