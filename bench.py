@@ -337,6 +337,10 @@ def run_gpu(args):
         secs = e2e.get("prover_s_max_over_ranks", e2e["prover_s"])
         e2e = dict({"value": world * N / secs, "unit": "constraints/s"}, **e2e)
     out["e2e"] = e2e
+    if rank == 0 and world == 1 and args.concurrency > 1:
+        # throughput with several prover processes sharing this GPU (the reference's host code is single-threaded and
+        # leaves the device idle 60 % of a proof): P independent instances proving back to back
+        out["e2e_throughput"] = whole_prover_throughput("dropin", LOG_N, runs=3, procs=args.concurrency)
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
         out["cpu_baseline_hot_path"] = cpu_baseline_hot_path(sample_log_n=args.cpu_sample_log_n)
@@ -428,6 +432,20 @@ def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0):
         return {"unavailable": repr(e)}
 
 
+def whole_prover_throughput(impl, log_n, runs, procs):
+    """bench/e2e_throughput.py: `procs` prover processes, each proving its own instance `runs` times back to back."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        import e2e_throughput
+        r = e2e_throughput.measure(impl, log_n, runs, procs)
+        r["unit"] = "constraints/s"
+        r["value"] = r.pop("constraints_per_s")
+        r["host_cores"] = os.cpu_count()
+        return r
+    except Exception as e:
+        return {"unavailable": repr(e)}
+
+
 def cpu_reference_prover(sample_log_n):
     """The unmodified reference aurora_snark_prover on one host core (the reference is single-threaded)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -515,8 +533,11 @@ def run_reference(args):
                       "log_n": n, "codeword_dim": n + RHO},
            "cpu_baseline": {"value": v, "unit": "constraints/s", "cores": 1, "kind": "reference",
                             "sample": f"whole aurora_snark_prover at N=2^{n}, median of {len(times)} runs, single thread (the reference has no threading)"},
-           "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "wall_s": time.perf_counter() - t0}
+           "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.concurrency > 1:
+        # the reference has no threading: one proof uses one core.  For a per-socket figure, one independent prover per core.
+        out["cpu_all_cores"] = whole_prover_throughput("cpu", n, runs=1, procs=os.cpu_count() or 1)
+    out["wall_s"] = time.perf_counter() - t0
     print(json.dumps(out))
 
 
@@ -528,6 +549,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--concurrency", type=int, default=8, help="prover processes sharing the GPU in the e2e_throughput section (1 = skip)")
     ap.add_argument("--dropin-log-n", type=int, default=18, help="side-by-side CPU reference vs drop-in prover with transcript comparison at this size (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

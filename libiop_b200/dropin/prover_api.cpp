@@ -128,6 +128,27 @@ double b200_prover_aurora_gf192(uint32_t log_n, uint32_t k_inputs, int make_zk, 
     return seconds(t0, t1);
 }
 
+/* The same prover call `repeats` times on ONE generated instance (instance generation costs more than the proof at
+   N = 2^20); secs_out[repeats].  Used for throughput measurements with several prover processes per GPU. */
+void b200_prover_aurora_gf192_repeat(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
+                                     uint64_t seed, uint32_t repeats, double *secs_out)
+{
+    init_once();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, n - 1);
+    aurora_snark_parameters<G, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
+        blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    for (uint32_t r = 0; r < repeats; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
+            ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+        secs_out[r] = seconds(t0, std::chrono::steady_clock::now());
+    }
+}
+
 /* Aurora over edwards_Fr, multiplicative cosets (README.md:160-164 `--is_multiplicative 1 --field_size=181`), non-zk */
 double b200_prover_aurora_edwards(uint32_t log_n, uint32_t k_inputs, uint32_t rs_extra, uint32_t fri_loc, uint64_t seed,
                                   int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)

@@ -38,6 +38,13 @@ class DropinProver:
                          (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_int(1 if make_zk else 0), C.c_uint32(rs_extra), C.c_uint32(fri_loc),
                           C.c_uint64(seed), C.c_int(1 if verify else 0)))
 
+    def aurora_gf192_repeat(self, log_n, repeats, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED):
+        """prover seconds of `repeats` proofs of one generated instance (instance generation excluded)"""
+        secs = (C.c_double * repeats)()
+        self.lib.b200_prover_aurora_gf192_repeat(C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_int(1 if make_zk else 0), C.c_uint32(rs_extra),
+                                                 C.c_uint32(fri_loc), C.c_uint64(seed), C.c_uint32(repeats), secs)
+        return list(secs)
+
     def aurora_edwards(self, log_n, k_inputs=31, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED, verify=True):
         return self._run(self.lib.b200_prover_aurora_edwards,
                          (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_uint32(rs_extra), C.c_uint32(fri_loc), C.c_uint64(seed),

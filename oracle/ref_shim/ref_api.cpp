@@ -306,6 +306,26 @@ double REFN(aurora_gf192)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+/* the same prover call `repeats` times on one generated instance (throughput measurements, bench/e2e_throughput.py) */
+void REFN(aurora_gf192_repeat)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
+                               uint64_t seed, uint32_t repeats, double *secs_out)
+{
+    REFN(init)();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, n - 1);
+    aurora_snark_parameters<G, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
+        blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    for (uint32_t r = 0; r < repeats; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
+            ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+        secs_out[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+}
+
 } /* extern "C" */
 
 /* ---- deterministic R1CS instances for both field kinds ----------------------------------------

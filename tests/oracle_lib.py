@@ -372,6 +372,12 @@ class Reference:
                                          C.byref(ln), C.byref(acc))
         return secs, buf[:ln.value].tobytes(), acc.value
 
+    def aurora_gf192_repeat(self, log_n, repeats, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=0x9E3779B97F4A7C15):
+        secs = (C.c_double * repeats)()
+        self.lib.ref_aurora_gf192_repeat(C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_int(int(make_zk)), C.c_uint32(rs_extra),
+                                         C.c_uint32(fri_loc), C.c_uint64(seed), C.c_uint32(repeats), secs)
+        return list(secs)
+
     def _run(self, fn, args, cap=1 << 27):
         buf = np.zeros(cap, dtype=np.uint8)
         ln = C.c_size_t(); acc = C.c_int()
