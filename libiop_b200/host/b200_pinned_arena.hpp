@@ -47,10 +47,8 @@ public:
     {
         bytes = (bytes + kAlign - 1) & ~(kAlign - 1);
         std::lock_guard<std::mutex> lock(mu_);
-        busy_ = true;
         void *p = take(bytes);
         if (!p && grow(bytes)) p = take(bytes);
-        busy_ = false;
         return p;
     }
 
@@ -60,7 +58,6 @@ public:
         const uintptr_t a = (uintptr_t)p;
         if (!owns(a)) return false;
         std::lock_guard<std::mutex> lock(mu_);
-        busy_ = true;
         auto it = used_.find(a);
         if (it != used_.end()) {
             std::size_t len = it->second;
@@ -82,20 +79,18 @@ public:
             }
             free_[start] = len;
         }
-        busy_ = false;
         return true;
     }
 
     bool owns(uintptr_t a) const
     {
         /* slabs_ only grows and is read without the lock: entries are published with their count last */
-        const std::size_t n = n_slabs_;
+        const std::size_t n = __atomic_load_n(&n_slabs_, __ATOMIC_ACQUIRE);
         for (std::size_t i = 0; i < n; ++i)
             if (a >= slabs_[i].base && a < slabs_[i].base + slabs_[i].bytes) return true;
         return false;
     }
 
-    bool busy() const { return busy_; }
     std::size_t slab_count() const { return n_slabs_; }
     std::size_t reserved_bytes() const
     {
@@ -157,7 +152,6 @@ private:
     slab_alloc_fn slab_alloc_;
     std::size_t slab_bytes_;
     std::mutex mu_;
-    volatile bool busy_ = false;
     slab slabs_[kMaxSlabs];
     std::size_t n_slabs_ = 0;
     std::map<uintptr_t, std::size_t> free_, used_;
@@ -203,20 +197,18 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
         try { c = context(); } catch (...) { return nullptr; }                                                          \
         return b200_host_alloc(c, bytes);                                                                                \
     }                                                                                                                    \
+    inline pinned_arena *make_arena()              /* malloc + placement new: must not re-enter operator new */            \
+    {                                                                                                                    \
+        const char *off = std::getenv("B200_PINNED_ARENA");                                                              \
+        if (off && off[0] == '0') return nullptr;                                                                        \
+        const char *mb = std::getenv("B200_PINNED_SLAB_MB");                                                             \
+        const std::size_t slab = (mb ? std::strtoull(mb, nullptr, 10) : 1024) << 20;                                     \
+        void *mem = std::malloc(sizeof(pinned_arena));                                                                   \
+        return mem ? new (mem) pinned_arena(&cuda_slab, slab) : nullptr;                                                 \
+    }                                                                                                                    \
     inline pinned_arena *arena()                                                                                         \
     {                                                                                                                    \
-        static pinned_arena *a = nullptr;                                                                                \
-        static bool init = false;                                                                                        \
-        if (!init) {                                                                                                     \
-            init = true;                                                                                                 \
-            const char *off = std::getenv("B200_PINNED_ARENA");                                                          \
-            if (!(off && off[0] == '0')) {                                                                               \
-                const char *mb = std::getenv("B200_PINNED_SLAB_MB");                                                     \
-                const std::size_t slab = (mb ? std::strtoull(mb, nullptr, 10) : 1024) << 20;                             \
-                void *mem = std::malloc(sizeof(pinned_arena));                                                           \
-                if (mem) a = new (mem) pinned_arena(&cuda_slab, slab);                                                   \
-            }                                                                                                            \
-        }                                                                                                                \
+        static pinned_arena *a = make_arena();     /* thread-safe one-time initialisation, never destroyed */            \
         return a;                                                                                                        \
     }                                                                                                                    \
     inline void *alloc(std::size_t n)                                                                                    \
