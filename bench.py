@@ -482,7 +482,7 @@ def cpu_baseline_hot_path(sample_log_n=14):
 
 def whole_prover_dropin(log_n):
     """The UNMODIFIED reference aurora_snark_prover (host C++ of libiop) with this library dropped in under its three
-    hot-path headers (oracle/_ref/libiopref_gpu.so, built in the build container) next to the plain CPU reference
+    hot-path headers (libiop_b200/lib/libiop_b200_dropin.so, built in the build container) next to the plain CPU reference
     (oracle/_ref/libiopref.so) on the same instance: whole-prover seconds and transcript equality."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     try:

@@ -1,6 +1,6 @@
 """Whole-prover check at BASELINE sizes: the unmodified reference aurora_snark_prover on the host CPU
 (oracle/_ref/libiopref.so) versus the same host code with the B200 hot path dropped in
-(oracle/_ref/libiopref_gpu.so).  Prints prover seconds, transcript fingerprints (must be equal) and
+(libiop_b200/lib/libiop_b200_dropin.so).  Prints prover seconds, transcript fingerprints (must be equal) and
 verifier verdicts.  Usage (under gpurun): python bench/dropin_prover_bench.py 16 18 20"""
 import hashlib
 import json

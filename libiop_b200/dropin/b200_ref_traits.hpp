@@ -1,6 +1,6 @@
 /*
  * b200_ref_traits.hpp — binds the C++ adapter (libiop_b200/host) to the reference's own field types
- * (TEST INFRASTRUCTURE: part of the drop-in integration build, oracle/Makefile target `refgpu`).
+ * (part of the drop-in build, libiop_b200/dropin/Makefile).
  * This is the code a libiop maintainer would add.
  */
 #ifndef B200_REF_TRAITS_HPP_

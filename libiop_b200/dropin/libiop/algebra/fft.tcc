@@ -1,5 +1,5 @@
 /*
- * Shadow of libiop/algebra/fft.tcc for the drop-in integration build (TEST INFRASTRUCTURE).
+ * Shadow of libiop/algebra/fft.tcc for the drop-in build.
  * The reference's own file is included unmodified from where it lies, with its three dispatchers
  * renamed; the dispatchers declared in libiop/algebra/fft.hpp:62-88 are then defined here and forward
  * to the B200 adapter for libff::gf192 / libff::edwards_Fr (everything else keeps the CPU path).

@@ -1,4 +1,4 @@
-/* Shadow of libiop/bcs/pow.tcc for the drop-in integration build (TEST INFRASTRUCTURE): the proof-of-work grind
+/* Shadow of libiop/bcs/pow.tcc for the drop-in build: the proof-of-work grind
    pow<FieldT, binary_hash_digest>::solve_pow (pow.tcc:71-102) runs on the B200 (b200_pow_solve) for the fields
    the adapter serves; the result is re-checked with the tree's own node hasher (verify_pow, pow.tcc:104-112). */
 #include "b200_ref_traits.hpp"

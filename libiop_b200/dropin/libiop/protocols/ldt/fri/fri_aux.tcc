@@ -1,4 +1,4 @@
-/* Shadow of libiop/protocols/ldt/fri/fri_aux.tcc for the drop-in integration build (TEST INFRASTRUCTURE):
+/* Shadow of libiop/protocols/ldt/fri/fri_aux.tcc for the drop-in build:
    evaluate_next_f_i_over_entire_domain (fri_aux.hpp:23-28) forwards to the B200 adapter. */
 #include "b200_ref_traits.hpp"
 #include "libiop_b200/host/b200_hotpath.hpp"
