@@ -63,7 +63,10 @@ struct AdditivePlan {
     std::vector<gf192> basis, beta, betainv;
     std::vector<std::vector<gf192>> gamma; /* gamma[j][b], b < d-1-j : recursed_betas of fft.tcc:85-92 */
     gf192 *tw = nullptr, *itw = nullptr, *sums = nullptr;
-    ~AdditivePlan() { cudaFree(tw); cudaFree(itw); cudaFree(sums); }
+    /* recursed shifts per (shift, extra basis vectors), kept on the device: a prover calls the same few domains thousands
+       of times (Ligero: 2570 row transforms over two domains) and recomputing them costs a stream synchronisation */
+    std::map<std::string, gf192 *> taus_cache;
+    ~AdditivePlan() { cudaFree(tw); cudaFree(itw); cudaFree(sums); for (auto &kv : taus_cache) cudaFree(kv.second); }
 };
 
 __host__ __device__ __forceinline__ size_t tw_offset(uint32_t d, uint32_t j)
@@ -113,8 +116,11 @@ __device__ __forceinline__ uint32_t insert_zero(uint32_t k, uint32_t pos)
     return ((k >> pos) << (pos + 1)) | low;
 }
 
-template <bool INV>
-__global__ void __launch_bounds__(B200_TILE_THREADS, B200_TILE_MINBLOCKS) additive_tile_pass(const PassParams P)
+/* NT threads per CTA, at least MB resident CTAs per SM.  Two instantiations per direction: 256 x 2 for grids that fill the
+   machine (two 96 KiB tiles per SM) and 512 x 1 for small transforms whose whole pass is a handful of CTAs (a 2^11-point
+   Ligero row is ONE tile: the chain of ~70 dependent steps then runs twice as fast on 16 warps). */
+template <bool INV, int NT, int MB>
+__global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
 {
     extern __shared__ uint64_t smem[];
 
@@ -419,19 +425,23 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
     const size_t smem = 3 * (((size_t)1 << tb) + B200_SMEM_PAD) * sizeof(uint64_t) + ((size_t)d << p.cb) * sizeof(gf192);
     static bool attr_set[2] = {false, false};
     if (!attr_set[INV]) {
-        B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t) + 8192)));
+        const int max_smem = (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t) + 8192);
+        B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[INV] = true;
     }
     const uint64_t nblocks = ((uint64_t)1 << (d - tbw)) * (n_cosets >> p.cb);
     if (nblocks > 0x7fffffffull) return set_err(c, B200_ERR_INVALID, "grid too large");
+    const bool few_ctas = nblocks <= (uint64_t)c->sm_count && tb >= 10;   /* less than one CTA per SM: latency-bound, widen the CTA */
     uint32_t n_tw = 0, n_tay = 0, n_bf = 0;
     for (uint32_t o : p.ops) { const uint32_t k = o >> 8; n_tw += k == OP_TW; n_tay += k == OP_TAY; n_bf += k == OP_BF; }
     char label[160];
     snprintf(label, sizeof label, "additive_tile_pass<%d> d=%u cosets=%u grid=%llu tile=2^%u tw=%u tay=%u bf=%u", (int)INV, d, n_cosets,
              (unsigned long long)nblocks, tb, n_tw, n_tay, n_bf);
     ProfScope prof(c, label);
-    additive_tile_pass<INV><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
+    if (few_ctas) additive_tile_pass<INV, 512, 1><<<(unsigned)nblocks, 512, smem, c->stream>>>(P);
+    else additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
     return 0;
 }
@@ -446,15 +456,27 @@ static int upload_taus(b200_ctx *c, const AdditivePlan &pl, const b200_domain *L
 {
     const uint32_t rows = 1 + (m - d);
     const size_t bytes = (size_t)rows * std::max(d, 1u) * sizeof(gf192);
+    const gf192 *basis = (const gf192 *)L->basis;
+    std::string key((const char *)L->shift, sizeof(gf192));
+    if (m > d) key.append((const char *)(basis + d), (size_t)(m - d) * sizeof(gf192));
+    AdditivePlan &plan = const_cast<AdditivePlan &>(pl);
+    auto hit = plan.taus_cache.find(key);
+    if (hit != plan.taus_cache.end()) { *dev = hit->second; return 0; }
     gf192 *h = (gf192 *)staging_get(c, std::max(bytes, (size_t)4096));
-    gf192 *dv = (gf192 *)scratch_get(c, 1, std::max(bytes, (size_t)4096));
-    if (!h || !dv) return set_err(c, B200_ERR_NOMEM, "cannot allocate tau staging");
+    if (!h) return set_err(c, B200_ERR_NOMEM, "cannot allocate tau staging");
     B200_CUDA(c, cudaStreamSynchronize(c->stream)); /* staging buffer may still be in flight */
+    if (plan.taus_cache.size() >= 256) {             /* bounded: drop everything (the stream is idle here) */
+        for (auto &kv : plan.taus_cache) cudaFree(kv.second);
+        plan.taus_cache.clear();
+    }
+    gf192 *dv = nullptr;
+    if (cudaMalloc(&dv, std::max(bytes, (size_t)256)) != cudaSuccess) { cudaGetLastError(); return set_err(c, B200_ERR_NOMEM, "cannot allocate tau table"); }
     gf192 s; memcpy(&s, L->shift, sizeof s);
     compute_taus(pl, s, h);
-    const gf192 *basis = (const gf192 *)L->basis;
     for (uint32_t k = 0; k < m - d; ++k) compute_taus(pl, basis[d + k], h + (size_t)(1 + k) * d);
     B200_CUDA(c, cudaMemcpyAsync(dv, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));  /* the staging buffer is reused by the next miss */
+    plan.taus_cache[key] = dv;
     *dev = dv;
     return 0;
 }

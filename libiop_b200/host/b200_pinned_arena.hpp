@@ -8,7 +8,7 @@
  * slabs makes every such vector DMA-able in place at PCIe line rate and removes the page faults.
  *
  * How: B200_DEFINE_PINNED_OPERATOR_NEW (below) replaces the global allocation functions of the
- * binary that includes it (C++ [replacement.functions]); blocks >= B200_PINNED_MIN_BYTES come from
+ * binary that includes it (C++ [replacement.functions]); blocks >= B200_PINNED_MIN_BYTES (32 KiB) come from
  * the arena, everything else from malloc.  operator delete recognises arena blocks by address, so
  * memory allocated by either path can be released by the other translation units of the process.
  * If page-locking fails (no device, ulimit) the arena declines and malloc serves the request:
@@ -32,7 +32,7 @@
 namespace libiop_b200 {
 
 #ifndef B200_PINNED_MIN_BYTES
-#define B200_PINNED_MIN_BYTES (std::size_t(256) << 10)
+#define B200_PINNED_MIN_BYTES (std::size_t(32) << 10)   /* Ligero's 2^11-element rows (48 KiB) included */
 #endif
 
 /* First-fit free-list allocator over slabs obtained from `slab_alloc` (cudaHostAlloc in production, malloc in the

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,7 @@ namespace libiop_b200 {
 class residency {
     struct entry { const void *host; std::size_t n; unsigned char sample[32 * 24]; std::size_t sample_bytes; device_buffer buf; };
     std::list<entry> lru_;                       /* front = most recent */
+    std::unordered_map<const void *, std::list<entry>::iterator> by_host_;   /* one entry per host address */
     std::size_t bytes_ = 0, budget_, hits_ = 0, misses_ = 0, stale_ = 0;
     bool enabled_, verify_;
 
@@ -57,9 +59,11 @@ public:
     static residency &instance() { static residency *r = new residency(); return *r; }   /* never destroyed: outlives every vector */
     void drop(const void *host)
     {
-        if (lru_.empty()) return;
-        for (auto it = lru_.begin(); it != lru_.end(); ++it)
-            if (it->host == host) { bytes_ -= it->n * 24; lru_.erase(it); return; }
+        auto found = by_host_.find(host);
+        if (found == by_host_.end()) return;
+        bytes_ -= found->second->n * 24;
+        lru_.erase(found->second);
+        by_host_.erase(found);
     }
     static constexpr std::size_t min_elems = 4096;
 
@@ -67,26 +71,27 @@ public:
     void put(const void *host, std::size_t n, device_buffer &&buf)
     {
         if (!enabled_ || n < min_elems) return;
-        for (auto it = lru_.begin(); it != lru_.end();)           /* one entry per address */
-            if (it->host == host) { bytes_ -= it->n * 24; it = lru_.erase(it); } else ++it;
+        drop(host);                                               /* one entry per address */
         lru_.emplace_front();
         entry &e = lru_.front();
         e.host = host; e.n = n; e.buf = std::move(buf);
         e.sample_bytes = take_sample(host, n, e.sample);
+        by_host_[host] = lru_.begin();
         bytes_ += n * 24;
-        while (bytes_ > budget_ && lru_.size() > 1) { bytes_ -= lru_.back().n * 24; lru_.pop_back(); }
+        while (bytes_ > budget_ && lru_.size() > 1) drop(lru_.back().host);
     }
 
     /* device copy of the n-element host array at `host`, or nullptr */
     const device_buffer *find(const void *host, std::size_t n)
     {
         if (!enabled_ || n < min_elems) return nullptr;
-        for (auto it = lru_.begin(); it != lru_.end(); ++it) {
-            if (it->host != host) continue;
+        auto found = by_host_.find(host);
+        if (found != by_host_.end()) {
+            auto it = found->second;
             unsigned char now[32 * 24];
             const std::size_t nb = take_sample(host, n, now);
             if (it->n != n || nb != it->sample_bytes || std::memcmp(now, it->sample, nb) != 0) {
-                bytes_ -= it->n * 24; lru_.erase(it); ++stale_; ++misses_;
+                drop(host); ++stale_; ++misses_;
                 return nullptr;
             }
             if (verify_) {
@@ -102,7 +107,7 @@ public:
         ++misses_;
         return nullptr;
     }
-    void clear() { lru_.clear(); bytes_ = 0; }
+    void clear() { lru_.clear(); by_host_.clear(); bytes_ = 0; }
     std::size_t hits() const { return hits_; }
     std::size_t misses() const { return misses_; }
     std::size_t stale() const { return stale_; }
