@@ -25,6 +25,9 @@
 #include <cstring>
 
 #include "ctx.h"
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "gf192.cuh"
 
 namespace b200 {
@@ -55,6 +58,7 @@ struct PassParams {
     uint32_t n_extra;
     uint32_t src_coset_stride_log; /* src advances by coset << this (use 32 for "shared source") */
     uint32_t n_ops;
+    uint32_t cl_log;    /* log2(CTAs per tile) for additive_cluster_pass (thread-block cluster, tile spread over DSMEM) */
     uint32_t ops[B200_MAX_OPS];
 };
 
@@ -259,6 +263,160 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* Small transforms: one tile spread over a thread-block cluster.
+   A transform of <= 2^12 points is a single tile, and additive_tile_pass runs its chain of dependent steps (11 twists, 55
+   radix-conversion strides and 11 butterfly stages for a 2^11-point Ligero row) on ONE SM: ~0.3 ms during which the other
+   147 SMs idle, and Ligero makes 2570 such calls per proof.  Here the tile is split over the shared memories of a cluster
+   of up to 8 CTAs (distributed shared memory): element L lives in CTA L >> lb at offset L & (2^lb - 1); twists touch only
+   the CTA's own slice, radix-conversion and butterfly steps whose stride crosses slices read and write the partner CTA's
+   shared memory directly.  Steps that stay inside a slice are separated by __syncthreads, steps that cross (or follow a
+   crossing step) by a cluster barrier.  Same step semantics as additive_tile_pass. */
+struct ClusterTile {
+    uint64_t *base[8];   /* plane 0 of every CTA of the cluster (generic addresses into distributed shared memory) */
+    uint32_t lb, S1;     /* log2(elements per CTA), plane stride in u64 */
+    __device__ __forceinline__ uint64_t *at(uint32_t L) const { return base[L >> lb] + (L & ((1u << lb) - 1u)); }
+    __device__ __forceinline__ gf192 ld(uint32_t L) const
+    {
+        const uint64_t *q = at(L);
+        const uint64_t a = q[0], b = q[S1], c = q[2 * S1];
+        gf192 r;
+        r.w[0] = (uint32_t)a; r.w[1] = (uint32_t)(a >> 32);
+        r.w[2] = (uint32_t)b; r.w[3] = (uint32_t)(b >> 32);
+        r.w[4] = (uint32_t)c; r.w[5] = (uint32_t)(c >> 32);
+        return r;
+    }
+    __device__ __forceinline__ void st(uint32_t L, const gf192 &x) const
+    {
+        uint64_t *q = at(L);
+        q[0] = (uint64_t)x.w[0] | ((uint64_t)x.w[1] << 32);
+        q[S1] = (uint64_t)x.w[2] | ((uint64_t)x.w[3] << 32);
+        q[2 * S1] = (uint64_t)x.w[4] | ((uint64_t)x.w[5] << 32);
+    }
+    __device__ __forceinline__ void xor_into(uint32_t Ldst, uint32_t Lsrc) const
+    {
+        uint64_t *qd = at(Ldst);
+        const uint64_t *qs = at(Lsrc);
+        qd[0] ^= qs[0]; qd[S1] ^= qs[S1]; qd[2 * S1] ^= qs[2 * S1];
+    }
+};
+
+template <bool INV>
+__global__ void __launch_bounds__(256, 1) additive_cluster_pass(const PassParams P)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ uint64_t smem[];
+
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t C = 1u << P.cl_log;
+    const uint32_t mainb = P.hi - P.lo;
+    const uint32_t tbw = mainb + P.c + P.ctop;
+    const uint32_t tb = tbw + P.cb;
+    const uint32_t T = 1u << tb;
+    const uint32_t lb = tb - P.cl_log, slice = 1u << lb;
+    const uint32_t wmask = (1u << tbw) - 1u;
+    ClusterTile t;
+    t.lb = lb; t.S1 = slice + B200_SMEM_PAD;
+    for (uint32_t r = 0; r < 8; ++r) t.base[r] = (r < C) ? cluster.map_shared_rank(smem, r) : smem;
+    gf192 *tau_s = reinterpret_cast<gf192 *>(smem + 3 * (slice + B200_SMEM_PAD));   /* [2^cb][d], one copy per CTA */
+
+    const uint32_t d = P.d;
+    const uint32_t tilebits = d - tbw;
+    const uint32_t tile_id = blockIdx.x >> P.cl_log;
+    const uint32_t coset_base = (tile_id >> tilebits) << P.cb;
+    const uint32_t tile = tile_id & ((1u << tilebits) - 1u);
+    const uint32_t midbits = P.lo - P.c;
+    const uint32_t mid = tile & ((1u << midbits) - 1u);
+    const uint32_t top = tile >> midbits;
+
+    for (uint32_t e = threadIdx.x; e < (d << P.cb); e += blockDim.x) {
+        const uint32_t cl = e / d, dep = e - cl * d;
+        const uint32_t coset = coset_base + cl;
+        gf192 v = ldg_elem(P.taus + dep);
+        for (uint32_t k = 0; k < P.n_extra; ++k)
+            if ((coset >> k) & 1u) gf_addto(v, ldg_elem(P.taus + (size_t)(1 + k) * d + dep));
+        tau_s[e] = v;
+    }
+
+    const bool shared_src = P.src_coset_stride_log >= 32;
+    auto global_index = [&](uint32_t L) -> uint32_t {
+        const uint32_t Lw = L & wmask;
+        const uint32_t w = Lw & ((1u << P.c) - 1u);
+        const uint32_t u = (Lw >> P.c) & ((1u << mainb) - 1u);
+        const uint32_t tbv = Lw >> (P.c + mainb);
+        return w | (mid << P.c) | (u << P.lo) | (top << P.hi) | (P.ctop ? (tbv << (d - P.ctop)) : 0u);
+    };
+
+    /* every CTA fills its own slice */
+    for (uint32_t o = threadIdx.x; o < slice; o += blockDim.x) {
+        const uint32_t L = rank * slice + o;
+        const uint32_t i = global_index(L);
+        const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
+        const size_t cofs = shared_src ? 0 : ((size_t)(coset_base + (L >> tbw)) << P.src_coset_stride_log);
+        t.st(L, ldg_elem(P.src + cofs + a));
+    }
+
+    bool prev_crosses = true;                      /* the first barrier must be cluster-wide: remote slices are being filled */
+    for (uint32_t o = 0; o < P.n_ops; ++o) {
+        const uint32_t kind = P.ops[o] >> 8, bit = P.ops[o] & 0xffu;
+        const uint32_t pos = bit - P.lo + P.c;
+        const bool crosses = (kind == OP_TAY) ? (pos + 2 > lb) : (kind == OP_BF) ? (pos + 1 > lb) : false;
+        if (prev_crosses || crosses) cluster.sync(); else __syncthreads();
+        prev_crosses = crosses;
+        if (kind == OP_TW) {
+            const gf192 *tab = P.tw + tw_offset(d, bit);
+            for (uint32_t q = threadIdx.x; q < slice; q += blockDim.x) {
+                const uint32_t L = rank * slice + q;
+                const uint32_t e = global_index(L) >> bit;
+                if (e != 0) t.st(L, gf_mul(t.ld(L), ldg_elem(tab + e)));
+            }
+        } else if (kind == OP_TAY) {
+            const uint32_t per = (T >> 2) >> P.cl_log;               /* quads per CTA; contiguous k blocks stay in the slice when the stride does */
+            for (uint32_t kl = threadIdx.x; kl < per; kl += blockDim.x) {
+                const uint32_t k = rank * per + kl;
+                const uint32_t low = k & ((1u << pos) - 1u);
+                const uint32_t base = ((k >> pos) << (pos + 2)) | low;
+                const uint32_t B = base | (1u << pos), Cq = base | (2u << pos), D = base | (3u << pos);
+                if (!INV) { t.xor_into(Cq, D); t.xor_into(B, Cq); }
+                else      { t.xor_into(B, Cq); t.xor_into(Cq, D); }
+            }
+        } else {
+            const uint32_t jj = bit;
+            const uint32_t depth = d - 1 - jj;
+            const gf192 *stab = P.sums + (size_t)jj * B200_SUM_CHUNKS * 256;
+            const uint32_t per = (T >> 1) >> P.cl_log;
+            for (uint32_t kl = threadIdx.x; kl < per; kl += blockDim.x) {
+                const uint32_t k = rank * per + kl;
+                const uint32_t L0 = insert_zero(k, pos), L1 = L0 | (1u << pos);
+                const uint32_t tix = global_index(L0) & ((1u << jj) - 1u);
+                gf192 tw = tau_s[(L0 >> tbw) * d + depth];
+                if (jj > 0) gf_addto(tw, ldg_elem(stab + (tix & 255u)));
+                if (jj > 8) gf_addto(tw, ldg_elem(stab + 256 + ((tix >> 8) & 255u)));
+                if (jj > 16) gf_addto(tw, ldg_elem(stab + 512 + ((tix >> 16) & 255u)));
+                if (jj > 24) gf_addto(tw, ldg_elem(stab + 768 + (tix >> 24)));
+                gf192 a = t.ld(L0), b = t.ld(L1);
+                if (INV) gf_addto(b, a);
+                gf_addto(a, gf_mul(b, tw));
+                if (!INV) gf_addto(b, a);
+                t.st(L0, a); t.st(L1, b);
+            }
+        }
+    }
+    cluster.sync();                                /* remote writes of the last step have landed; nobody touches a peer afterwards */
+
+    uint64_t *out = reinterpret_cast<uint64_t *>(P.dst);
+    const uint64_t *mine = smem;
+    const uint32_t S1 = slice + B200_SMEM_PAD;
+    for (uint32_t o = threadIdx.x; o < slice; o += blockDim.x) {
+        const uint32_t L = rank * slice + o;
+        const uint32_t i = global_index(L);
+        const uint32_t a = (P.bitrev == 2) ? (__brev(i) >> (32 - d)) : i;
+        uint64_t *q = out + (((size_t)(coset_base + (L >> tbw)) << d) + a) * 3;
+        q[0] = mine[o]; q[1] = mine[o + S1]; q[2] = mine[o + 2 * S1];
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 /* plan construction                                                                              */
 
 /* powers by doubling: tab[2^b + e] = tab[e] * base^(2^b) */
@@ -414,6 +572,12 @@ static std::vector<Pass> schedule(const std::vector<uint32_t> &steps, uint32_t d
     return passes;
 }
 
+static bool cluster_disabled()
+{
+    static const bool off = getenv("B200_NO_CLUSTER") != nullptr;     /* ablation switch */
+    return off;
+}
+
 template <bool INV>
 static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uint32_t n_cosets)
 {
@@ -434,12 +598,34 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
     const uint64_t nblocks = ((uint64_t)1 << (d - tbw)) * (n_cosets >> p.cb);
     if (nblocks > 0x7fffffffull) return set_err(c, B200_ERR_INVALID, "grid too large");
     const bool few_ctas = nblocks <= (uint64_t)c->sm_count && tb >= 10;   /* less than one CTA per SM: latency-bound, widen the CTA */
+    /* a handful of tiles: spread each over a cluster of CTAs (distributed shared memory), see additive_cluster_pass */
+    const bool cluster_off = cluster_disabled();
+    uint32_t cl_log = 0;
+    if (!cluster_off && tb >= 9 && nblocks * 8 <= (uint64_t)c->sm_count) cl_log = 3;
+    else if (!cluster_off && tb >= 9 && nblocks * 4 <= (uint64_t)c->sm_count) cl_log = 2;
     uint32_t n_tw = 0, n_tay = 0, n_bf = 0;
     for (uint32_t o : p.ops) { const uint32_t k = o >> 8; n_tw += k == OP_TW; n_tay += k == OP_TAY; n_bf += k == OP_BF; }
     char label[160];
     snprintf(label, sizeof label, "additive_tile_pass<%d> d=%u cosets=%u grid=%llu tile=2^%u tw=%u tay=%u bf=%u", (int)INV, d, n_cosets,
              (unsigned long long)nblocks, tb, n_tw, n_tay, n_bf);
     ProfScope prof(c, label);
+    if (cl_log) {
+        P.cl_log = cl_log;
+        const size_t slice = (size_t)1 << (tb - cl_log);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)(nblocks << cl_log), 1, 1);
+        cfg.blockDim = dim3(256, 1, 1);
+        cfg.dynamicSmemBytes = 3 * (slice + B200_SMEM_PAD) * sizeof(uint64_t) + ((size_t)d << p.cb) * sizeof(gf192);
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1u << cl_log; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        B200_CUDA(c, cudaLaunchKernelEx(&cfg, additive_cluster_pass<INV>, P));
+        B200_LAUNCH_CHECK(c);
+        return 0;
+    }
     if (few_ctas) additive_tile_pass<INV, 512, 1><<<(unsigned)nblocks, 512, smem, c->stream>>>(P);
     else additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
@@ -530,8 +716,9 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
     uint32_t first_hi = d <= tb ? d : tb - kCoalesceBits;
     {
         Pass p; p.lo = 0; p.hi = first_hi; p.c = 0; p.ctop = d <= tb ? 0 : kCoalesceBits; p.bitrev = 1;
-        if (d < kTileBits) {                      /* small transform: several cosets per CTA, tau table <= 8 KiB */
-            p.cb = std::min(kTileBits - d, m - d);
+        const bool spread = !cluster_disabled() && d >= 9 && (uint64_t)n_cosets * 8 <= (uint64_t)c->sm_count;
+        if (d < kTileBits && !spread) {           /* small transform: several cosets per CTA, tau table <= 8 KiB */
+            p.cb = std::min(kTileBits - d, m - d);    /* (with few cosets each one is spread over a cluster instead) */
             while (p.cb > 0 && ((size_t)d << p.cb) * sizeof(gf192) > 8192) --p.cb;
         }
         for (uint32_t jj = 0; jj < first_hi; ++jj) p.ops.push_back((OP_BF << 8) | jj);
