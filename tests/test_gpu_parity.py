@@ -358,6 +358,34 @@ def test_other_reference_provers_with_b200_dropin_are_bit_exact(golden, which, l
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == want[(which, log_n, zk)]
 
 
+def _extra_fingerprints():
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prover_fingerprints_extra.json")
+    return json.load(open(path))
+
+
+@pytest.mark.parametrize("case", _extra_fingerprints(), ids=lambda c: f"{c['prover']}-2^{c['log_n']}{'-zk' if c['zk'] else ''}")
+def test_dropin_provers_match_cpu_reference_fingerprints(case):
+    """More sizes and the zero-knowledge variants: the transcript bytes of the drop-in provers must hash to the fingerprints
+    of the CPU reference runs recorded by tests/golden/make_prover_fingerprints.py, and the reference verifier must accept."""
+    import hashlib
+    from oracle_lib import ReferenceGpu
+    if not ReferenceGpu.available():
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
+    g = ReferenceGpu()
+    which, log_n, zk = case["prover"], case["log_n"], case["zk"]
+    if which == "aurora_gf192":
+        _, dump, acc = g.aurora_gf192(log_n, make_zk=zk)
+    elif which == "aurora_edwards":
+        _, dump, acc = g.aurora_edwards(log_n)
+    elif which == "fractal_edwards":
+        _, dump, acc, _ = g.fractal_edwards(log_n)
+    else:
+        _, dump, acc = g.ligero_gf192(log_n, make_zk=zk)
+    assert acc == 1, "reference verifier rejected the GPU-built proof"
+    assert (len(dump), hashlib.sha256(dump).hexdigest()) == (case["bytes"], case["sha256"])
+
+
 def test_residency_cache_hits_are_true_copies(golden):
     """The adapter keeps device copies of the codeword vectors it produced and reuses them when the reference hands
     the same std::vector to the next stage (libiop_b200/host/b200_residency.hpp).  With B200_RESIDENCY_VERIFY=1 every
