@@ -171,6 +171,12 @@ int b200_fp_geometric(b200_ctx *, const b200_fp_params *fp, b200_buf out, size_t
 /* polynomial<FieldT>::evaluation_at_point (algebra/polynomials/polynomial.tcc:98-109): out = sum_i coeffs[i] * x^i (host result) */
 int b200_poly_eval(b200_ctx *, int field, const b200_fp_params *fp, b200_buf coeffs, size_t n, const uint64_t x[3], uint64_t out[3]);
 
+/* Sparse matrix-vector product over CSR rows: y[i] = sum_{k in [row_ptr[i], row_ptr[i+1])} coeff[k] * x[col[k]].
+ * r1cs_constraint_system::create_Az_Bz_Cz_from_variable_assignment (relations/r1cs.tcc:236-266), one call per matrix.
+ * row_ptr (n_rows+1), col (nnz), coeff (nnz*3 limbs) are host arrays; x (n_x elements) and y_out (n_rows) device buffers. */
+int b200_spmv_csr(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows, const uint64_t *row_ptr, const uint32_t *col,
+                  const uint64_t *coeff, b200_buf x, size_t n_x, b200_buf y_out);
+
 /* polynomial_over_vanishing_polynomial (algebra/polynomials/vanishing_polynomial.tcc:312-371,
  * linearized_polynomial.tcc:238-291): P = Q*Z + R for the sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j]
  * (pows[j] < deg; additive: the linearized vanishing polynomial of a subspace, multiplicative: y^deg - c).

@@ -426,6 +426,19 @@ class B200:
             for b_ in (dp, dq, dr):
                 self.free(b_)
 
+    def spmv_csr(self, field, fp, row_ptr, col, coeff, x):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64); col = np.ascontiguousarray(col, dtype=np.uint32)
+        coeff = np.ascontiguousarray(coeff, dtype=np.uint64).reshape(-1, 3)
+        n = len(row_ptr) - 1
+        dx = self.upload(x); dy = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_spmv_csr(self.ctx, C.c_int(field), self._fpref(fp), C.c_size_t(n), row_ptr.ctypes.data_as(_u64p),
+                                             col.ctypes.data_as(C.POINTER(C.c_uint32)), coeff.ctypes.data_as(_u64p), C.c_uint64(dx),
+                                             C.c_size_t(len(x)), C.c_uint64(dy)))
+            return self.download(dy, n)
+        finally:
+            self.free(dx); self.free(dy)
+
     def pow_solve(self, challenge, pow_bitlen, pow_upperbound=0):
         out = (C.c_uint8 * 32)()
         self._chk(self.lib.b200_pow_solve(self.ctx, bytes(challenge), C.c_size_t(32), C.c_uint32(pow_bitlen), C.c_uint64(pow_upperbound), out))

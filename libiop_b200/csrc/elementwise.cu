@@ -364,6 +364,20 @@ static int divide_run(b200_ctx *c, const F &f, b200_buf p, size_t n_p, size_t de
     return 0;
 }
 
+/* ---- 8. sparse matrix-vector product, CSR rows: y[i] = sum_k coeff[k] * x[col[k]] --------------
+   r1cs_constraint_system::create_Az_Bz_Cz_from_variable_assignment (relations/r1cs.tcc:236-266): R1CS rows hold a handful of
+   terms each, so one thread per row; the gather from x is the only irregular access and x (24 MiB at N = 2^20) sits in L2. */
+template<typename F> __global__ void __launch_bounds__(256)
+spmv_csr_kernel(typename F::T *y, const uint64_t *row_ptr, const uint32_t *col, const typename F::T *coeff, const typename F::T *x,
+                size_t n_rows, const F f)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_rows; i += (size_t)gridDim.x * blockDim.x) {
+        typename F::T acc = f.zero();
+        for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) acc = f.add(acc, f.mul(ld_el(coeff, k), ld_el(x, col[k])));
+        st_el(y, i, acc);
+    }
+}
+
 static bool field_ok(b200_ctx *c, int field, const b200_fp_params *fp)
 {
     if (field == B200_FIELD_GF192) return true;
@@ -502,6 +516,36 @@ int b200_poly_eval(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf co
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (field == B200_FIELD_GF192) return poly_eval_run(c, GfF(), coeffs, n, x, out);
     return poly_eval_run(c, make_fpf(fp), coeffs, n, x, out);
+}
+
+int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_rows, const uint64_t *row_ptr, const uint32_t *col,
+                  const uint64_t *coeff, b200_buf x, size_t n_x, b200_buf y_out)
+{
+    B200_TRACE_SCOPE(c, "spmv_csr", n_rows);
+    if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
+    if (!n_rows) return 0;
+    const size_t nnz = (size_t)row_ptr[n_rows];
+    for (size_t k = 0; k < nnz; ++k)
+        if (col[k] >= n_x) return set_err(c, B200_ERR_INVALID, "spmv: column index %u outside the vector (%zu)", col[k], n_x);
+    /* matrix goes up with the call (the prover builds a fresh constraint system per proof): row_ptr | coeff | col */
+    const size_t b_rp = (n_rows + 1) * sizeof(uint64_t), b_cf = nnz * 24, b_cl = nnz * sizeof(uint32_t);
+    char *dev = (char *)scratch_get(c, 2, b_rp + b_cf + b_cl + 64);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate %zu bytes for the sparse matrix", b_rp + b_cf + b_cl);
+    B200_CUDA(c, cudaMemcpyAsync(dev, row_ptr, b_rp, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaMemcpyAsync(dev + b_rp, coeff, b_cf, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaMemcpyAsync(dev + b_rp + b_cf, col, b_cl, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += b_rp + b_cf + b_cl;
+    const uint64_t *d_rp = (const uint64_t *)dev;
+    const uint32_t *d_cl = (const uint32_t *)(dev + b_rp + b_cf);
+    if (field == B200_FIELD_GF192)
+        spmv_csr_kernel<GfF><<<ew_grid(c, n_rows, 256), 256, 0, c->stream>>>((gf192 *)y_out, d_rp, d_cl, (const gf192 *)(dev + b_rp),
+                                                                            (const gf192 *)x, n_rows, GfF());
+    else
+        spmv_csr_kernel<FpF><<<ew_grid(c, n_rows, 256), 256, 0, c->stream>>>((fp192 *)y_out, d_rp, d_cl, (const fp192 *)(dev + b_rp),
+                                                                            (const fp192 *)x, n_rows, make_fpf(fp));
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));      /* the host arrays may be released by the caller */
+    return 0;
 }
 
 int b200_poly_divide_sparse(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf p, size_t n_p, size_t deg,

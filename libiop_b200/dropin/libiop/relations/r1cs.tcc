@@ -1,0 +1,64 @@
+/* Shadow of libiop/relations/r1cs.tcc for the drop-in build.
+   r1cs_constraint_system::create_Az_Bz_Cz_from_variable_assignment (r1cs.tcc:236-266): the three sparse matrix-vector
+   products A z, B z, C z.  The constraints are flattened once into CSR arrays (one pass over the terms, no arithmetic) and
+   each product is one b200_spmv_csr call; z goes up once, Az / Bz / Cz come down.
+   Crossover (measured, Aurora N = 2^20 on the B200 box): flattening costs about as much as the reference's own pass over
+   the terms, so with the one-term rows of generate_r1cs_example the device route is slower (whole prover 0.74 -> 0.78 s);
+   it is taken from three terms per row on average, where the multiplications dominate.  Small systems keep the host loop. */
+#include "b200_dropin_common.hpp"
+#include B200_REF_FILE(libiop/relations/r1cs.tcc)
+
+namespace libiop {
+namespace b200_glue {
+template<typename FieldT, typename SelectLC>
+void spmv_rows(const std::vector<r1cs_constraint<FieldT>> &constraints, SelectLC lc_of, const libiop_b200::device_buffer &d_z, std::size_t n_z,
+               std::vector<FieldT> &out)
+{
+    using namespace libiop_b200;
+    const std::size_t n = constraints.size();
+    std::vector<uint64_t> row_ptr(n + 1, 0);
+    std::size_t nnz = 0;
+    for (std::size_t i = 0; i < n; ++i) { nnz += lc_of(constraints[i]).terms.size(); row_ptr[i + 1] = nnz; }
+    std::vector<uint32_t> col(nnz);
+    std::vector<FieldT> coeff = make_uninitialized_vector<FieldT>(nnz);
+    std::size_t k = 0;
+    for (std::size_t i = 0; i < n; ++i)
+        for (auto &lt : lc_of(constraints[i]).terms) { col[k] = (uint32_t)lt.index_; coeff[k] = lt.coeff_; ++k; }
+    device_buffer d_y(n);
+    throw_status(context(), b200_spmv_csr(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), n, row_ptr.data(), col.data(),
+                                          reinterpret_cast<const uint64_t *>(coeff.data()), d_z.get(), n_z, d_y.get()));
+    const std::vector<FieldT> y = d_y.template download<FieldT>(n);
+    out.insert(out.end(), y.begin(), y.end());
+}
+}
+
+#define B200_ABCZ_SPECIALISE(FIELD)                                                                                        \
+template<> inline void r1cs_constraint_system<FIELD>::create_Az_Bz_Cz_from_variable_assignment(                            \
+    const r1cs_variable_assignment<FIELD> &variable_assignment,                                                            \
+    std::vector<FIELD> &Az_out, std::vector<FIELD> &Bz_out, std::vector<FIELD> &Cz_out) const                              \
+{                                                                                                                          \
+    std::size_t n_terms = 0;                                                                                               \
+    for (auto &cons : this->constraints_) n_terms += cons.a_.terms.size() + cons.b_.terms.size() + cons.c_.terms.size();   \
+    if (this->constraints_.size() < 16384 || n_terms < 9 * this->constraints_.size()) {   /* same loop as r1cs.tcc:243-265 */                                 \
+        for (auto &cons : this->constraints_) {                                                                            \
+            FIELD a = FIELD::zero(), b = FIELD::zero(), c = FIELD::zero();                                                 \
+            for (auto &lt : cons.a_.terms) a += variable_assignment[lt.index_] * lt.coeff_;                                \
+            for (auto &lt : cons.b_.terms) b += variable_assignment[lt.index_] * lt.coeff_;                                \
+            for (auto &lt : cons.c_.terms) c += variable_assignment[lt.index_] * lt.coeff_;                                \
+            Az_out.emplace_back(a); Bz_out.emplace_back(b); Cz_out.emplace_back(c);                                        \
+        }                                                                                                                  \
+        return;                                                                                                            \
+    }                                                                                                                      \
+    using namespace libiop_b200;                                                                                           \
+    device_buffer d_z(variable_assignment.size());                                                                         \
+    d_z.upload(variable_assignment);                                                                                       \
+    b200_glue::spmv_rows<FIELD>(this->constraints_, [](const r1cs_constraint<FIELD> &c) -> const linear_combination<FIELD> & { return c.a_; }, \
+                                d_z, variable_assignment.size(), Az_out);                                                  \
+    b200_glue::spmv_rows<FIELD>(this->constraints_, [](const r1cs_constraint<FIELD> &c) -> const linear_combination<FIELD> & { return c.b_; }, \
+                                d_z, variable_assignment.size(), Bz_out);                                                  \
+    b200_glue::spmv_rows<FIELD>(this->constraints_, [](const r1cs_constraint<FIELD> &c) -> const linear_combination<FIELD> & { return c.c_; }, \
+                                d_z, variable_assignment.size(), Cz_out);                                                  \
+}
+B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
+#undef B200_ABCZ_SPECIALISE
+} // namespace libiop

@@ -284,3 +284,29 @@ def test_fp_inv_ragged_and_zeros(dev, oracle, fp, n):
         idx = np.nonzero(nz)[0][:k]
         for i in idx:
             assert (got[i] == oracle.fp_inv(a[i])).all()
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+def test_spmv_csr(dev, oracle, fp, field):
+    """create_Az_Bz_Cz_from_variable_assignment (relations/r1cs.tcc:236-266): rows with 0..4 terms, repeated columns."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(99)
+    n_rows, n_x = 5000, 777
+    lens = rng.integers(0, 5, size=n_rows)
+    lens[:3] = [0, 4, 0]
+    row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    nnz = int(row_ptr[-1])
+    col = rng.integers(0, n_x, size=nnz).astype(np.uint32)
+    coeff = F.rand(rng, nnz)
+    x = F.rand(rng, n_x)
+    prod = F.mul(coeff, x[col])
+    want = np.zeros((n_rows, 3), dtype=np.uint64)
+    for j in range(4):                                     # j-th term of every row that has one
+        rows = np.nonzero(lens > j)[0]
+        idx = (row_ptr[rows] + j).astype(np.int64)
+        want[rows] = F.add(want[rows], prod[idx])
+    got = dev.spmv_csr(field, fp if field == FP else None, row_ptr, col, coeff, x)
+    assert (got == want).all()
+    with pytest.raises(Exception):
+        bad = col.copy(); bad[5] = n_x
+        dev.spmv_csr(field, fp if field == FP else None, row_ptr, bad, coeff, x)
