@@ -10,6 +10,11 @@
 
 namespace libiop {
 namespace b200_glue {
+inline std::size_t spmv_min_terms_per_row()          /* B200_SPMV_MIN_TERMS_PER_ROW overrides the measured crossover (tests: 0) */
+{
+    static const std::size_t v = std::getenv("B200_SPMV_MIN_TERMS_PER_ROW") ? std::strtoull(std::getenv("B200_SPMV_MIN_TERMS_PER_ROW"), nullptr, 10) : 3;
+    return v;
+}
 template<typename FieldT, typename SelectLC>
 void spmv_rows(const std::vector<r1cs_constraint<FieldT>> &constraints, SelectLC lc_of, const libiop_b200::device_buffer &d_z, std::size_t n_z,
                std::vector<FieldT> &out)
@@ -39,7 +44,7 @@ template<> inline void r1cs_constraint_system<FIELD>::create_Az_Bz_Cz_from_varia
 {                                                                                                                          \
     std::size_t n_terms = 0;                                                                                               \
     for (auto &cons : this->constraints_) n_terms += cons.a_.terms.size() + cons.b_.terms.size() + cons.c_.terms.size();   \
-    if (this->constraints_.size() < 16384 || n_terms < 9 * this->constraints_.size()) {   /* same loop as r1cs.tcc:243-265 */                                 \
+    if (this->constraints_.size() < 16384 || n_terms < 3 * b200_glue::spmv_min_terms_per_row() * this->constraints_.size()) { /* r1cs.tcc:243-265 */                                 \
         for (auto &cons : this->constraints_) {                                                                            \
             FIELD a = FIELD::zero(), b = FIELD::zero(), c = FIELD::zero();                                                 \
             for (auto &lt : cons.a_.terms) a += variable_assignment[lt.index_] * lt.coeff_;                                \

@@ -386,6 +386,38 @@ def test_dropin_provers_match_cpu_reference_fingerprints(case):
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == (case["bytes"], case["sha256"])
 
 
+def test_device_spmv_route_of_the_dropin_is_bit_exact():
+    """create_Az_Bz_Cz_from_variable_assignment goes to b200_spmv_csr only from three terms per row (measured crossover);
+    B200_SPMV_MIN_TERMS_PER_ROW=0 forces that route for the one-term rows of generate_r1cs_example — same transcripts."""
+    import subprocess, sys, os
+    from oracle_lib import ReferenceGpu
+    if not ReferenceGpu.available():
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
+    code = r"""
+import hashlib, sys
+sys.path.insert(0, 'tests')
+from oracle_lib import ReferenceGpu
+g = ReferenceGpu()
+for which, n in (('aurora_gf192', 14), ('aurora_edwards', 14)):
+    _, d, a = getattr(g, which)(n)
+    print('RES', which, n, len(d), hashlib.sha256(d).hexdigest(), a)
+print('LAUNCHED', g.device_stats()['launches'])
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, B200_SPMV_MIN_TERMS_PER_ROW="0", B200_TRACE="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "spmv_csr" in r.stderr, "the device SpMV route was not taken"
+    want = {(c["prover"], c["log_n"]): (c["bytes"], c["sha256"]) for c in _extra_fingerprints() if not c["zk"]}
+    seen = 0
+    for line in r.stdout.splitlines():
+        if line.startswith("RES "):
+            _, w, n, ln, h, acc = line.split()
+            assert int(acc) == 1 and (int(ln), h) == want[(w, int(n))], line
+            seen += 1
+    assert seen == 2
+
+
 def test_residency_cache_hits_are_true_copies(golden):
     """The adapter keeps device copies of the codeword vectors it produced and reuses them when the reference hands
     the same std::vector to the next stage (libiop_b200/host/b200_residency.hpp).  With B200_RESIDENCY_VERIFY=1 every
