@@ -418,6 +418,20 @@ print('LAUNCHED', g.device_stats()['launches'])
     assert seen == 2
 
 
+def test_standalone_cpp_program_on_the_reference_api():
+    """libiop_b200/dropin/examples/aurora_prove.cpp: a plain C++ executable calling aurora_snark_prover / aurora_snark_verifier with
+    the library dropped in (replacement operator new in the executable itself): runs, verifies, and is deterministic."""
+    import subprocess, os, re
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libiop_b200", "lib", "aurora_prove")
+    if not os.path.exists(exe):
+        pytest.skip("libiop_b200/lib/aurora_prove not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "14", "0", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sums = re.findall(r"\(accept\), transcript (\d+) bytes, fnv1a ([0-9a-f]{16})", r.stderr)
+    assert len(sums) == 2 and sums[0] == sums[1], r.stderr[-1000:]
+    assert int(sums[0][0]) == 149800            # same length as the CPU reference's transcript at N = 2^14 (prover_fingerprints_extra.json)
+
+
 def test_residency_cache_hits_are_true_copies(golden):
     """The adapter keeps device copies of the codeword vectors it produced and reuses them when the reference hands
     the same std::vector to the next stage (libiop_b200/host/b200_residency.hpp).  With B200_RESIDENCY_VERIFY=1 every
