@@ -35,7 +35,7 @@ namespace b200 {
 enum : uint32_t { OP_TW = 1, OP_TAY = 2, OP_BF = 3 };
 #define B200_MAX_OPS 160
 #ifndef B200_ILP
-#define B200_ILP 2
+#define B200_ILP 1   /* independent butterflies in flight per thread; with the 4-class multiplier 1 is 1-1.5 % faster than 2 (bench/build_variants.sh) */
 #endif
 #ifndef B200_TILE_THREADS
 #define B200_TILE_THREADS 256
