@@ -18,15 +18,15 @@
 namespace libiop {
 namespace b200_glue {
 template<typename FieldT> std::vector<FieldT> fft(const std::vector<FieldT> &c, const field_subset<FieldT> &d, std::true_type)
-{ return libiop_b200::FFT_over_field_subset<FieldT>(c, d); }
+{ return libiop_b200::FFT_over_field_subset_cref<FieldT>(c, d); }
 template<typename FieldT> std::vector<FieldT> fft(const std::vector<FieldT> &c, const field_subset<FieldT> &d, std::false_type)
 { return ref_cpu_FFT_over_field_subset<FieldT>(c, d); }
 template<typename FieldT> std::vector<FieldT> ifft(const std::vector<FieldT> &e, const field_subset<FieldT> &d, std::true_type)
-{ return libiop_b200::IFFT_over_field_subset<FieldT>(e, d); }
+{ return libiop_b200::IFFT_over_field_subset_cref<FieldT>(e, d); }
 template<typename FieldT> std::vector<FieldT> ifft(const std::vector<FieldT> &e, const field_subset<FieldT> &d, std::false_type)
 { return ref_cpu_IFFT_over_field_subset<FieldT>(e, d); }
 template<typename FieldT> std::vector<FieldT> ifft_kd(const std::vector<FieldT> &e, size_t deg, const field_subset<FieldT> &d, std::true_type)
-{ return libiop_b200::IFFT_of_known_degree_over_field_subset<FieldT>(e, deg, d); }
+{ return libiop_b200::IFFT_of_known_degree_over_field_subset_cref<FieldT>(e, deg, d); }
 template<typename FieldT> std::vector<FieldT> ifft_kd(const std::vector<FieldT> &e, size_t deg, const field_subset<FieldT> &d, std::false_type)
 { return ref_cpu_IFFT_of_known_degree_over_field_subset<FieldT>(e, deg, d); }
 }

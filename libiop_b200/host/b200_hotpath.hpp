@@ -70,8 +70,11 @@ void IFFT_over_field_subset_device(const device_buffer &evals, const DomainT &do
     throw_status(context(), rc);
 }
 
+/* The reference's signatures take the vectors BY VALUE (fft.hpp:62-88); the implementations below take references so that a
+   caller that already holds the vector (the drop-in dispatchers, which received the reference's by-value copy) does not
+   pay a second copy of up to 192 MiB.  The by-value overloads with the reference's names forward to them. */
 template<typename FieldT, typename DomainT>
-std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, DomainT domain)
+std::vector<FieldT> FFT_over_field_subset_cref(const std::vector<FieldT> &coeffs, const DomainT &domain)
 {
     if (coeffs.size() > domain.num_elements())
         throw std::invalid_argument("FFT_over_field_subset: more coefficients than domain elements");
@@ -80,38 +83,46 @@ std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, Doma
     FFT_over_field_subset_device<FieldT>(in, coeffs.size(), domain, out);
     return download_and_keep<FieldT>(std::move(out), domain.num_elements());   /* the codeword stays resident for its consumers */
 }
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, DomainT domain)
+{ return FFT_over_field_subset_cref<FieldT>(coeffs, domain); }
 
-/* fft.hpp:70-76 */
+/* fft.hpp:70-76; `n_evals` leading evaluations of `evals` are transformed (the whole vector by default) */
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> IFFT_over_field_subset_cref(const std::vector<FieldT> &evals, const DomainT &domain, std::size_t n_evals = ~std::size_t(0))
+{
+    if (n_evals == ~std::size_t(0)) n_evals = evals.size();
+    if (n_evals != domain.num_elements() || n_evals > evals.size())
+        throw std::invalid_argument("IFFT_over_field_subset: evaluation vector does not match the domain");
+    if (n_evals == 1) return std::vector<FieldT>(evals.begin(), evals.begin() + 1);           /* fft.tcc:397-401 */
+    device_buffer in(n_evals), out(n_evals);
+    throw_status(context(), b200_upload(context(), in.get(), 0, reinterpret_cast<const uint64_t *>(evals.data()), n_evals));
+    IFFT_over_field_subset_device<FieldT>(in, domain, out);
+    return out.template download<FieldT>(n_evals);
+}
 template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_over_field_subset(const std::vector<FieldT> evals, DomainT domain)
-{
-    if (evals.size() != domain.num_elements())
-        throw std::invalid_argument("IFFT_over_field_subset: evaluation vector does not match the domain");
-    if (evals.size() == 1) return evals;           /* fft.tcc:397-401 */
-    device_buffer in(evals.size()), out(evals.size());
-    in.upload_async(evals);
-    IFFT_over_field_subset_device<FieldT>(in, domain, out);
-    return out.template download<FieldT>(evals.size());
-}
+{ return IFFT_over_field_subset_cref<FieldT>(evals, domain); }
 
-/* fft.hpp:78-88 (fft.tcc:435-475): additive -> first 2^k evaluations over the first k basis vectors,
-   multiplicative -> every (n/2^k)-th evaluation over the order-2^k sub-coset */
+/* fft.hpp:78-88 (fft.tcc:435-475): additive -> first 2^k evaluations over the first k basis vectors (uploaded straight from
+   the caller's vector), multiplicative -> every (n/2^k)-th evaluation over the order-2^k sub-coset */
 template<typename FieldT, typename DomainT>
-std::vector<FieldT> IFFT_of_known_degree_over_field_subset(const std::vector<FieldT> evals, std::size_t degree, DomainT domain)
+std::vector<FieldT> IFFT_of_known_degree_over_field_subset_cref(const std::vector<FieldT> &evals, std::size_t degree, const DomainT &domain)
 {
     std::size_t closest_power_of_two = 1;
     while (closest_power_of_two < degree) closest_power_of_two <<= 1;
     const DomainT minimal = domain.get_subset_of_order(closest_power_of_two);
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE)
+        return IFFT_over_field_subset_cref<FieldT>(evals, minimal, closest_power_of_two);
     std::vector<FieldT> sub;
     sub.reserve(closest_power_of_two);
-    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
-        sub.insert(sub.end(), evals.begin(), evals.begin() + closest_power_of_two);
-    } else {
-        const std::size_t freq = domain.num_elements() / closest_power_of_two;
-        for (std::size_t i = 0; i < domain.num_elements(); i += freq) sub.emplace_back(evals[i]);
-    }
-    return IFFT_over_field_subset<FieldT>(sub, minimal);
+    const std::size_t freq = domain.num_elements() / closest_power_of_two;
+    for (std::size_t i = 0; i < domain.num_elements(); i += freq) sub.emplace_back(evals[i]);
+    return IFFT_over_field_subset_cref<FieldT>(sub, minimal);
 }
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> IFFT_of_known_degree_over_field_subset(const std::vector<FieldT> evals, std::size_t degree, DomainT domain)
+{ return IFFT_of_known_degree_over_field_subset_cref<FieldT>(evals, degree, domain); }
 
 /* fri_aux.hpp:23-28 */
 template<typename FieldT, typename DomainT>
