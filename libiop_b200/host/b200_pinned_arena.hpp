@@ -84,6 +84,8 @@ public:
 
     bool owns(uintptr_t a) const
     {
+        /* called for every operator delete of the process: one range test rejects malloc'd pointers */
+        if (a < __atomic_load_n(&lo_, __ATOMIC_RELAXED) || a >= __atomic_load_n(&hi_, __ATOMIC_RELAXED)) return false;
         /* slabs_ only grows and is read without the lock: entries are published with their count last */
         const std::size_t n = __atomic_load_n(&n_slabs_, __ATOMIC_ACQUIRE);
         for (std::size_t i = 0; i < n; ++i)
@@ -145,6 +147,8 @@ private:
         slabs_[n_slabs_].base = (uintptr_t)p;
         slabs_[n_slabs_].bytes = want;
         __atomic_store_n(&n_slabs_, n_slabs_ + 1, __ATOMIC_RELEASE);
+        if ((uintptr_t)p < lo_) __atomic_store_n(&lo_, (uintptr_t)p, __ATOMIC_RELAXED);
+        if ((uintptr_t)p + want > hi_) __atomic_store_n(&hi_, (uintptr_t)p + want, __ATOMIC_RELAXED);
         free_[(uintptr_t)p] = want;
         return true;
     }
@@ -154,6 +158,7 @@ private:
     std::mutex mu_;
     slab slabs_[kMaxSlabs];
     std::size_t n_slabs_ = 0;
+    uintptr_t lo_ = ~uintptr_t(0), hi_ = 0;          /* address range spanned by all slabs */
     std::map<uintptr_t, std::size_t> free_, used_;
 };
 
