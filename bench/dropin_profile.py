@@ -10,7 +10,8 @@ if which == "gpu":
     from libiop_b200.prover import DropinProver
     r = DropinProver()
     os.environ.pop("B200_REF_PROFILE", None)
-    run = getattr(r, prover_name)
+    zk = len(sys.argv) > 4 and sys.argv[4] == "zk"
+    run = (lambda n, verify: r.aurora_gf192(n, make_zk=True, verify=verify)) if zk else getattr(r, prover_name)
     run(log_n, verify=False)          # warm-up: plans, pinned slabs, device blocks
     run(log_n, verify=False)
     os.environ["B200_REF_PROFILE"] = "1"

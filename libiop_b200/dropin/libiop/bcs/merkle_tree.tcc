@@ -1,7 +1,7 @@
 /* Shadow of libiop/bcs/merkle_tree.tcc for the drop-in integration build.
    merkle_tree<F, binary_hash_digest>::construct_with_leaves_serialized_by_cosets (merkle_tree.hpp:88-90) is explicitly
    specialised for libff::gf192 and libff::edwards_Fr to build the tree on the B200.  The reference's own bookkeeping
-   (zk salt sampling in stream order, merkle_tree.tcc:37-72,110-114) is kept.
+   (zk salts drawn from randombytes_buf with the call pattern of merkle_tree.tcc:37-72,110-114) is kept.
 
    Node storage: the reference keeps one std::string per node (merkle_tree.hpp:49), i.e. 2^23 heap allocations for the
    first Aurora tree at N = 2^20 — 0.4 s of host time for a tree the device hashes in 3 ms — and of those 256 MiB the
@@ -30,6 +30,36 @@ public:
     binary_hash_digest zk_hash(const std::vector<FieldT> &leaf, const zk_salt_type &zk_salt) { return inner->zk_hash(leaf, zk_salt); }
 };
 
+/* The zk salts of all leaves as ONE byte string, drawn from randombytes_buf with exactly the call sizes and order of
+   merkle_tree::sample_leaf_randomness (merkle_tree.tcc:36-72: 1 MiB batches of which the first leafs_per_batch salts are
+   used, then one call per remaining leaf), so the random stream is consumed identically — without the reference's one
+   std::string per leaf (2^22 heap allocations for the first Aurora tree at N = 2^18 zk: 0.36 s). */
+inline std::string sample_salts_flat(std::size_t num_leaves, std::size_t num_zk_bytes)
+{
+    libff::enter_block("BCS: Sample randomness");
+    std::string salts(num_leaves * num_zk_bytes, '\0');
+    const std::size_t batch_bytes = std::size_t(1) << 20;
+    const std::size_t num_batches = (num_leaves * num_zk_bytes) / batch_bytes;
+    const std::size_t leafs_per_batch = (num_batches == 0) ? 0 : num_leaves / num_batches;
+    std::vector<uint8_t> batch(batch_bytes);
+    std::size_t leaf = 0;
+    for (std::size_t b = 0; b < num_batches; ++b) {
+        randombytes_buf(batch.data(), batch_bytes);
+        std::memcpy(&salts[leaf * num_zk_bytes], batch.data(), leafs_per_batch * num_zk_bytes);
+        leaf += leafs_per_batch;
+    }
+    for (; leaf < num_leaves; ++leaf) randombytes_buf(&salts[leaf * num_zk_bytes], num_zk_bytes);
+    libff::leave_block("BCS: Sample randomness");
+    return salts;
+}
+/* salt of leaf `pos`: flat layout (one string for all leaves, trees built by the B200 path) or the reference's per-leaf strings */
+inline zk_salt_type salt_at(const std::vector<zk_salt_type> &salts, std::size_t num_leaves, std::size_t pos)
+{
+    if (salts.size() == num_leaves) return salts[pos];
+    const std::size_t len = salts[0].size() / num_leaves;
+    return salts[0].substr(pos * len, len);
+}
+
 template<typename FieldT>
 std::shared_ptr<resident_nodes_leafhash<FieldT>> gpu_merkle(const std::vector<std::shared_ptr<std::vector<FieldT>>> &leaf_contents, size_t coset,
                                                             size_t num_leaves, size_t digest_len, const std::vector<zk_salt_type> *salts,
@@ -40,16 +70,16 @@ std::shared_ptr<resident_nodes_leafhash<FieldT>> gpu_merkle(const std::vector<st
     std::vector<b200_buf> handles;
     views.reserve(leaf_contents.size());
     for (auto &v : leaf_contents) { views.emplace_back(*v); handles.push_back(views.back().get()); }
-    std::vector<uint8_t> flat;
-    size_t salt_len = 0;
-    if (salts) { salt_len = (*salts)[0].size(); flat.reserve(salt_len * salts->size()); for (auto &s : *salts) flat.insert(flat.end(), s.begin(), s.end()); }
+    /* salts: one flat string (sample_salts_flat) */
+    const size_t salt_len = salts ? (*salts)[0].size() / num_leaves : 0;
     const size_t n_nodes = 2 * num_leaves - 1;
     /* a tree rebuilt over an already decorated hasher keeps the original underneath */
     auto prev = std::dynamic_pointer_cast<resident_nodes_leafhash<FieldT>>(leaf_hasher);
     auto holder = std::make_shared<resident_nodes_leafhash<FieldT>>(prev ? prev->inner : leaf_hasher, n_nodes * digest_len);
     const int kind = field_traits<FieldT>::kind == B200_FIELD_GF192 ? B200_DOMAIN_AFFINE_SUBSPACE : B200_DOMAIN_MULTIPLICATIVE_COSET;
     throw_status(context(), b200_merkle_build(context(), handles.data(), handles.size(), leaf_contents[0]->size(), coset, kind,
-                                              salts ? flat.data() : nullptr, salt_len, digest_len, holder->nodes.get()));
+                                              salts ? reinterpret_cast<const uint8_t *>((*salts)[0].data()) : nullptr, salt_len, digest_len,
+                                              holder->nodes.get()));
     throw_status(context(), b200_sync(context()));       /* uploads of non-resident oracles and the salts are done */
     return holder;
 }
@@ -109,7 +139,8 @@ template<> inline void merkle_tree<FIELD, binary_hash_digest>::construct_with_le
     for (auto &v : leaf_contents)                                                                                                  \
         if ((v->size() / coset_serialization_size) != this->num_leaves_)                                                           \
             throw std::logic_error("Attempting to construct a Merkle tree with a constituent vector of wrong size");              \
-    if (this->make_zk_) this->sample_leaf_randomness();                                                                            \
+    if (this->make_zk_)                                                                                                            \
+        this->zk_leaf_randomness_elements_.assign(1, b200_glue::sample_salts_flat(this->num_leaves_, this->num_zk_bytes_));        \
     this->inner_nodes_.clear();                                                                                                    \
     this->leaf_hasher_ = b200_glue::gpu_merkle<FIELD>(leaf_contents, coset_serialization_size, this->num_leaves_,                  \
         this->digest_len_bytes_, this->make_zk_ ? &this->zk_leaf_randomness_elements_ : nullptr, this->leaf_hasher_);              \
@@ -139,7 +170,9 @@ merkle_tree<FIELD, binary_hash_digest>::get_set_membership_proof(const std::vect
     std::sort(S.begin(), S.end());                                                                                                 \
     S.erase(std::unique(S.begin(), S.end()), S.end());                                                                             \
     if (S.back() >= this->num_leaves_) throw std::invalid_argument("All positions must be between 0 and num_leaves-1.");           \
-    if (this->make_zk_) for (std::size_t pos : S) proof.randomness_hashes.emplace_back(this->zk_leaf_randomness_elements_[pos]);   \
+    if (this->make_zk_)                                                                                                            \
+        for (std::size_t pos : S)                                                                                                  \
+            proof.randomness_hashes.emplace_back(b200_glue::salt_at(this->zk_leaf_randomness_elements_, this->num_leaves_, pos));  \
     proof.auxiliary_hashes = b200_glue::nodes_at<FIELD>(this->inner_nodes_, this->leaf_hasher_, this->digest_len_bytes_,           \
                                                        b200_glue::membership_proof_nodes(this->num_leaves_, S));                   \
     return proof;                                                                                                                  \
