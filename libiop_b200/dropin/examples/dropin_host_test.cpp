@@ -1,0 +1,81 @@
+/*
+ * dropin_host_test.cpp — CPU-only checks of the host logic inside the drop-in shadows (no device call is made):
+ *   1. sample_salts_flat draws the zk salts with the same randombytes_buf call pattern as the reference's
+ *      merkle_tree::sample_leaf_randomness (merkle_tree.tcc:36-72): same bytes, leaf by leaf, for batch-sized and small leaf counts;
+ *   2. membership_proof_nodes lists exactly the sibling nodes, in the order, that the reference's
+ *      get_set_membership_proof (merkle_tree.tcc:242-336) emits, checked against the reference on a CPU-built tree.
+ */
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include <libff/algebra/fields/binary/gf64.hpp>
+#include <libff/algebra/fields/binary/gf192.hpp>
+
+#include "libiop/bcs/merkle_tree.hpp"
+#include "libiop/bcs/hashing/blake2b.hpp"
+
+extern "C" void b200_shim_randombytes_seed(uint64_t seed);
+
+using namespace libiop;
+
+static int failures = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); ++failures; } } while (0)
+
+/* gf64 is not a field the drop-in serves, so this tree runs the reference's own code paths throughout */
+typedef libff::gf64 RefField;
+class exposed_tree : public merkle_tree<RefField, binary_hash_digest> {
+public:
+    using merkle_tree<RefField, binary_hash_digest>::merkle_tree;
+    void sample() { this->sample_leaf_randomness(); }
+    const std::vector<zk_salt_type> &salts() const { return this->zk_leaf_randomness_elements_; }
+    const std::vector<binary_hash_digest> &nodes() const { return this->inner_nodes_; }
+};
+
+int main()
+{
+    libff::inhibit_profiling_info = true;
+    libff::inhibit_profiling_counters = true;
+    /* 1. salts */
+    for (std::size_t leaves : {std::size_t(2), std::size_t(8), std::size_t(1024), std::size_t(1) << 15, std::size_t(1) << 16, std::size_t(1) << 18}) {   /* tree sizes are powers of two >= 2 */
+        exposed_tree t(leaves, std::make_shared<blake2b_leafhash<RefField>>(128), blake2b_two_to_one_hash, 32, true, 128);
+        b200_shim_randombytes_seed(1234 + leaves);
+        t.sample();
+        b200_shim_randombytes_seed(1234 + leaves);
+        const std::size_t zk_bytes = t.salts()[0].size();
+        const std::string flat = b200_glue::sample_salts_flat(leaves, zk_bytes);
+        CHECK(t.salts().size() == leaves && flat.size() == leaves * zk_bytes);
+        bool same = true;
+        for (std::size_t i = 0; i < leaves && same; ++i) same = (flat.compare(i * zk_bytes, zk_bytes, t.salts()[i]) == 0);
+        CHECK(same);
+        CHECK(b200_glue::salt_at(t.salts(), leaves, leaves / 2) == t.salts()[leaves / 2]);
+        CHECK(b200_glue::salt_at({flat}, leaves, leaves / 2) == t.salts()[leaves / 2]);
+    }
+    /* 2. pruned authentication paths: node list vs the reference's proof on a CPU-built tree */
+    std::mt19937_64 rng(7);
+    for (std::size_t log_leaves : {1, 2, 5, 10}) {
+        const std::size_t leaves = std::size_t(1) << log_leaves;
+        exposed_tree t(leaves, std::make_shared<blake2b_leafhash<RefField>>(128), blake2b_two_to_one_hash, 32, false, 128);
+        std::vector<RefField> column(leaves);
+        for (auto &e : column) e = RefField(rng());
+        t.construct({column});
+        for (int trial = 0; trial < 20; ++trial) {
+            std::vector<std::size_t> positions;
+            const std::size_t k = 1 + rng() % (leaves < 12 ? leaves : 12);
+            for (std::size_t i = 0; i < k; ++i) positions.push_back(rng() % leaves);
+            const merkle_tree_set_membership_proof<binary_hash_digest> ref = t.get_set_membership_proof(positions);
+            std::vector<std::size_t> S(positions);
+            std::sort(S.begin(), S.end());
+            S.erase(std::unique(S.begin(), S.end()), S.end());
+            const std::vector<std::size_t> wanted = b200_glue::membership_proof_nodes(leaves, S);
+            CHECK(wanted.size() == ref.auxiliary_hashes.size());
+            bool same = wanted.size() == ref.auxiliary_hashes.size();
+            for (std::size_t i = 0; i < wanted.size() && same; ++i) same = (t.nodes()[wanted[i]] == ref.auxiliary_hashes[i]);
+            CHECK(same);
+        }
+    }
+    std::printf("%d failed\n", failures);
+    return failures ? 1 : 0;
+}

@@ -74,3 +74,14 @@ def test_every_shadow_file_includes_the_reference_file_it_shadows():
                 assert f"#include B200_REF_FILE({rel})" in text, rel
                 n += 1
     assert n >= 15
+
+
+def test_dropin_host_logic_against_the_reference_on_cpu():
+    """libiop_b200/dropin/examples/dropin_host_test.cpp (built by `make -C libiop_b200/dropin` where the reference checkout is):
+    the flat zk-salt sampler consumes randombytes exactly like merkle_tree::sample_leaf_randomness, and the pruned
+    authentication-path node list equals what the reference's get_set_membership_proof emits — no device involved."""
+    exe = os.path.join(ROOT, "libiop_b200", "lib", "dropin_host_test")
+    if not os.path.exists(exe):
+        pytest.skip("libiop_b200/lib/dropin_host_test not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "0 failed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
