@@ -100,6 +100,33 @@ def test_additive_ifft_vs_oracle(dev, oracle, m):
     assert (dev.gf192_ifft(dom_affine(basis, shift), e) == oracle.additive_ifft(e, m, basis, shift)).all()
 
 
+def test_additive_small_transforms_without_the_cluster_kernel():
+    """Small transforms normally run on additive_cluster_pass (tile spread over a thread-block cluster); B200_NO_CLUSTER=1
+    keeps them on additive_tile_pass (one CTA per tile).  Both must agree with the oracle."""
+    import subprocess, sys, os
+    code = r"""
+import sys
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np
+import libiop_b200 as L
+from oracle_lib import Oracle, el, rand_elems, standard_basis
+o, dev = Oracle(), L.B200(0)
+rng = np.random.default_rng(5)
+for m, nc in ((9, 512), (11, 2048), (13, 2048), (13, 5000), (15, 1 << 12)):
+    basis, shift = standard_basis(m), el(1 << m)
+    c = rand_elems(rng, nc)
+    ev = dev.gf192_fft(L.Domain.standard(m), c)
+    assert (ev == o.additive_fft(c, m, basis, shift)).all(), (m, nc)
+    d = max(1, int(np.ceil(np.log2(nc))))
+    assert (dev.gf192_ifft(L.Domain.standard(m), ev)[:nc] == c).all(), (m, nc)
+print('OK')
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({"B200_NO_CLUSTER": "1"}, {}):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
 def test_additive_fft_empty_and_errors(dev):
     import libiop_b200 as L
     d = L.Domain.standard(6)
