@@ -39,35 +39,29 @@ template<> inline std::vector<std::vector<FIELD>> matrix_indexer<FIELD>::compute
 {                                                                                                                          \
     this->bivariate_lagrange_poly_ = bivariate_lagrange_polynomial<FIELD>(this->matrix_domain_);                           \
     const std::size_t K = this->index_domain_.num_elements();                                                              \
-    const std::vector<FIELD> H_elems = this->matrix_domain_.all_elements();                                                \
-    const std::vector<FIELD> inv_derivative = b200_glue::inverse_vanishing_derivative_over<FIELD>(this->matrix_domain_);   \
-    std::vector<FIELD> row_evals, col_evals, val_evals, row_times_col_evals;                                               \
-    row_evals.reserve(K); col_evals.reserve(K); val_evals.reserve(K); row_times_col_evals.reserve(K);                      \
-    std::size_t num_nonzero_cnt = 0;                                                                                       \
-    for (std::size_t i = 0; i < this->matrix_->num_rows(); i++) {                                                          \
-        const linear_combination<FIELD> row = this->matrix_->get_row(i);                                                   \
-        const FIELD &row_index_elem = H_elems[i];                                                                          \
-        for (auto &term : row.terms) {                                                                                     \
-            num_nonzero_cnt++;                                                                                             \
-            const std::size_t col_index = this->matrix_domain_.reindex_by_subset(this->input_variable_dim_, term.index_);  \
-            row_evals.emplace_back(row_index_elem);                                                                        \
-            col_evals.emplace_back(H_elems[col_index]);                                                                    \
-            row_times_col_evals.emplace_back(row_index_elem * H_elems[col_index]);                                         \
-            val_evals.emplace_back(term.coeff_ * inv_derivative[col_index]);                                               \
+    const std::vector<FIELD> H = this->matrix_domain_.all_elements();                         /* H[i] = i-th element of H */ \
+    const std::vector<FIELD> inv_dZ = b200_glue::inverse_vanishing_derivative_over<FIELD>(this->matrix_domain_);           \
+    /* one entry per non-zero M[i][j]: (H[i], H[j'], M[i][j] / DZ_H(H[j']), H[i] * H[j']) with j' the position of variable j in H */ \
+    std::vector<FIELD> at_row, at_col, scaled_val, product;                                                                \
+    at_row.reserve(K); at_col.reserve(K); scaled_val.reserve(K); product.reserve(K);                                       \
+    for (std::size_t i = 0; i < this->matrix_->num_rows(); ++i) {                                                          \
+        const linear_combination<FIELD> entries = this->matrix_->get_row(i);                                               \
+        for (const auto &entry : entries.terms) {                                                                          \
+            const std::size_t j = this->matrix_domain_.reindex_by_subset(this->input_variable_dim_, entry.index_);         \
+            at_row.push_back(H[i]);                                                                                        \
+            at_col.push_back(H[j]);                                                                                        \
+            product.push_back(H[i] * H[j]);                                                                                \
+            scaled_val.push_back(entry.coeff_ * inv_dZ[j]);                                                                \
         }                                                                                                                  \
     }                                                                                                                      \
-    for (std::size_t i = num_nonzero_cnt; i < K; i++) {     /* padding entries: val = 0 at an arbitrary element of H */     \
-        row_evals.emplace_back(H_elems[0]);                                                                                \
-        col_evals.emplace_back(H_elems[0]);                                                                                \
-        val_evals.emplace_back(FIELD::zero());                                                                             \
-    }                                                                                                                      \
-    row_evals.swap(col_evals);                              /* the index is for the transpose (fractal_indexer.tcc:110-111) */ \
+    /* padding up to |K| (fractal_indexer.tcc:104-121): row / col at H[0] with value 0; the product column is padded with the  \
+       square of the first element of K; and the index is for the transpose, so row and col trade places */               \
     const FIELD k0 = this->index_domain_.element_by_index(0);                                                              \
-    row_evals.resize(K, k0);                                                                                               \
-    col_evals.resize(K, k0);                                                                                               \
-    val_evals.resize(K, FIELD::zero());                                                                                    \
-    row_times_col_evals.resize(K, k0.squared());                                                                           \
-    return {row_evals, col_evals, val_evals, row_times_col_evals};                                                         \
+    at_row.resize(K, H[0]);                                                                                                \
+    at_col.resize(K, H[0]);                                                                                                \
+    scaled_val.resize(K, FIELD::zero());                                                                                   \
+    product.resize(K, k0.squared());                                                                                       \
+    return {std::move(at_col), std::move(at_row), std::move(scaled_val), std::move(product)};                              \
 }
 B200_FOR_EACH_FIELD(B200_MATRIX_INDEXER_SPECIALISE)
 #undef B200_MATRIX_INDEXER_SPECIALISE
