@@ -192,6 +192,15 @@ int b200_poly_divide_sparse(b200_ctx *, int field, const b200_fp_params *fp, b20
 int b200_pow_solve(b200_ctx *, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound,
                    uint8_t *pow_out);
 
+/* ---- verifier random messages of the BCS hash chain ------------------------------------------------ */
+/* blake2b_FieldT_randomness_extractor (libiop/bcs/hashing/blake2b.tcc:231-256), reached from blake2b_hashchain::squeeze
+ * (blake2b.tcc:76-85) in bcs_protocol::squeeze_verifier_random_messages (bcs_common.tcc:599-615): out[i] = keyed
+ * BLAKE2b(digest 24 bytes, key = u64 i, message = root_plus_index) read as a field element; for B200_FIELD_FP with the
+ * bits above the modulus' top bit cleared and values >= modulus re-drawn with key += n (blake2b.tcc:185-229).
+ * root_plus_index: msg_len host bytes (root || u64 squeeze index; 8..128, multiple of 8). */
+int b200_squeeze_field_elements(b200_ctx *, int field, const b200_fp_params *fp, const uint8_t *root_plus_index,
+                                size_t msg_len, size_t n, b200_buf out);
+
 /* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the FFT tile passes ---- */
 unsigned long long b200_launch_count(b200_ctx *);
 void b200_transfer_bytes(b200_ctx *, unsigned long long *h2d, unsigned long long *d2h);   /* running totals of upload / download bytes */

@@ -444,6 +444,17 @@ class B200:
         self._chk(self.lib.b200_pow_solve(self.ctx, bytes(challenge), C.c_size_t(32), C.c_uint32(pow_bitlen), C.c_uint64(pow_upperbound), out))
         return bytes(out)
 
+    def squeeze_field_elements(self, field, fp, root_plus_index, n):
+        """blake2b_FieldT_randomness_extractor (bcs/hashing/blake2b.tcc:231-256): n elements from root || u64 index."""
+        msg = bytes(root_plus_index)
+        out = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_squeeze_field_elements(self.ctx, C.c_int(field), self._fpref(fp), msg, C.c_size_t(len(msg)),
+                                                           C.c_size_t(n), C.c_uint64(out)))
+            return self.download(out, n)
+        finally:
+            self.free(out)
+
     def blake2b_batch(self, msgs, msg_len, digest_len=32):
         n = len(msgs) // msg_len
         i = self.upload_bytes(msgs); o = self.alloc_bytes(n * digest_len)

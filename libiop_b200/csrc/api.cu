@@ -316,6 +316,13 @@ int b200_pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uin
     return pow_solve(c, challenge, digest_len, pow_bitlen, pow_upperbound, pow_out);
 }
 
+int b200_squeeze_field_elements(b200_ctx *c, int field, const b200_fp_params *fp, const uint8_t *root_plus_index, size_t msg_len,
+                                size_t n, b200_buf out)
+{
+    B200_TRACE_SCOPE(c, "squeeze_field_elements", n);
+    return squeeze_field_elements(c, field, fp, root_plus_index, msg_len, n, out);
+}
+
 int b200_blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out)
 {
     return blake2b_batch(c, in, msg_len, n_msgs, digest_len, out);

@@ -153,6 +153,8 @@ int fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_domain
 int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset,
                  int kind, const uint8_t *salts, size_t salt_len, size_t digest_len, b200_bytes nodes);
 int blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out);
+int squeeze_field_elements(b200_ctx *c, int field, const b200_fp_params *fp, const uint8_t *root_plus_index, size_t msg_len,
+                           size_t n, b200_buf out);
 int pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound, uint8_t *pow_out);
 void plans_clear(b200_ctx *c);
 

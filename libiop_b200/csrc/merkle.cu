@@ -485,6 +485,71 @@ int pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/* verifier random messages: blake2b_FieldT_randomness_extractor (libiop/bcs/hashing/blake2b.tcc:231-256).  Element i is
+   the keyed hash BLAKE2b(outlen = 24, key = u64 i, message = root || u64 squeeze index) (blake2b.tcc:162-183); for a
+   prime field the bits above the modulus' top bit are cleared and a value >= modulus is re-drawn with key += n
+   (rejection sampling, blake2b.tcc:185-229).  Ligero squeezes 4 * N elements after its first round.        */
+struct SqueezeParams {
+    uint64_t msg[16];        /* root || index, zero padded */
+    uint32_t msg_len;        /* bytes, <= 128, multiple of 8 */
+    uint64_t n;
+    uint64_t *out;           /* n elements of 3 x u64 */
+    int prime_field;
+    uint64_t modulus[3], top_mask;   /* prime field only: limb 2 keeps (top_mask) */
+};
+
+__global__ void __launch_bounds__(256) squeeze_kernel(const SqueezeParams P)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint64_t key = i;
+    uint64_t h[8], m[16];
+    for (;;) {
+        h[0] = BLAKE_IV0 ^ 0x01010000ULL ^ (8ull << 8) ^ 24ull;      /* digest 24 bytes, key 8 bytes */
+        h[1] = BLAKE_IV1; h[2] = BLAKE_IV2; h[3] = BLAKE_IV3; h[4] = BLAKE_IV4; h[5] = BLAKE_IV5; h[6] = BLAKE_IV6; h[7] = BLAKE_IV7;
+        m[0] = key;
+#pragma unroll
+        for (int t = 1; t < 16; ++t) m[t] = 0;
+        blake2b_compress(h, m, 128, false);                          /* the key block */
+#pragma unroll
+        for (int t = 0; t < 16; ++t) m[t] = P.msg[t];
+        blake2b_compress(h, m, 128 + (uint64_t)P.msg_len, true);
+        if (!P.prime_field) break;
+        h[2] &= P.top_mask;
+        const bool below = h[2] != P.modulus[2] ? h[2] < P.modulus[2]
+                         : h[1] != P.modulus[1] ? h[1] < P.modulus[1] : h[0] < P.modulus[0];
+        if (below) break;
+        key += P.n;
+    }
+    uint64_t *o = P.out + 3 * i;
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2];
+}
+
+int squeeze_field_elements(b200_ctx *c, int field, const b200_fp_params *fp, const uint8_t *root_plus_index, size_t msg_len,
+                           size_t n, b200_buf out)
+{
+    if (msg_len == 0 || msg_len > 128 || msg_len % 8)
+        return set_err(c, B200_ERR_INVALID, "squeeze: root || index must be 8..128 bytes, a multiple of 8");
+    if (field == B200_FIELD_FP && !fp) return set_err(c, B200_ERR_INVALID, "squeeze: prime field without parameters");
+    if (!n) return 0;
+    SqueezeParams P;
+    memset(&P, 0, sizeof P);
+    memcpy(P.msg, root_plus_index, msg_len);
+    P.msg_len = (uint32_t)msg_len; P.n = n; P.out = (uint64_t *)out;
+    P.prime_field = field == B200_FIELD_FP;
+    if (P.prime_field) {
+        for (int k = 0; k < 3; ++k) P.modulus[k] = fp->modulus[k];
+        if (!P.modulus[2]) return set_err(c, B200_ERR_INVALID, "squeeze: the modulus must use its top limb (3-limb Fp_model)");
+        uint64_t mask = ~0ull;
+        while ((mask >> 1) >= P.modulus[2]) mask >>= 1;              /* smallest 2^k - 1 >= the top limb */
+        P.top_mask = mask;
+    }
+    squeeze_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(P);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
 struct BatchParams { const uint64_t *in; uint64_t *out; size_t msg_words, n; uint32_t digest_len, dw; };
 __global__ void blake2b_batch_kernel(const BatchParams P)
 {

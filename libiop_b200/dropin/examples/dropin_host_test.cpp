@@ -76,6 +76,22 @@ int main()
             CHECK(same);
         }
     }
+    /* 3. short verifier messages stay on the host in the gf192 override of blake2b_FieldT_randomness_extractor:
+          element i is the keyed hash of root || index (blake2b.tcc:162-183) */
+    {
+        const binary_hash_digest root(32, 'r');
+        const std::size_t index = 5, n = 9;
+        const std::vector<libff::gf192> got = blake2b_FieldT_randomness_extractor<libff::gf192>(root, index, n);
+        CHECK(got.size() == n);
+        unsigned char msg[40];
+        std::memcpy(msg, root.data(), 32);
+        std::memcpy(msg + 32, &index, 8);
+        for (std::size_t i = 0; i < n && i < got.size(); ++i) {
+            libff::gf192 want;
+            crypto_generichash_blake2b((unsigned char *)&want, sizeof(want), msg, sizeof(msg), (const unsigned char *)&i, sizeof(i));
+            CHECK(got[i] == want);
+        }
+    }
     std::printf("%d failed\n", failures);
     return failures ? 1 : 0;
 }

@@ -225,5 +225,16 @@ public:
     void clear() { entries_.clear(); }
 };
 
+/* verifier random message of the BCS hash chain (blake2b_FieldT_randomness_extractor, bcs/hashing/blake2b.tcc:231-256):
+   n elements drawn by keyed BLAKE2b from `root || squeeze index` */
+template<typename FieldT>
+std::vector<FieldT> squeeze_field_elements(const unsigned char *root_plus_index, std::size_t len, std::size_t n)
+{
+    device_buffer out(n);
+    throw_status(context(), b200_squeeze_field_elements(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(),
+                                                        root_plus_index, len, n, out.get()));
+    return out.download<FieldT>(n);
+}
+
 } // namespace libiop_b200
 #endif

@@ -234,6 +234,20 @@ void REFN(pow_solve)(uint8_t *pow_out, const uint8_t *challenge, size_t work_par
     if (upper_out) *upper_out = params.pow_upperbound();
 }
 
+/* ---- verifier random messages: blake2b_FieldT_randomness_extractor (bcs/hashing/blake2b.tcc:231-256) ---- */
+void REFN(squeeze_gf192)(uint64_t *out, const uint8_t *root, size_t digest_len, size_t index, size_t n)
+{
+    const std::vector<G> v = blake2b_FieldT_randomness_extractor<G>(binary_hash_digest((const char *)root, digest_len), index, n);
+    if (n) std::memcpy(out, v.data(), n * 24);
+}
+void REFN(squeeze_edwards)(uint64_t *out, const uint8_t *root, size_t digest_len, size_t index, size_t n)
+{
+    REFN(init)();
+    const std::vector<libff::edwards_Fr> v =
+        blake2b_FieldT_randomness_extractor<libff::edwards_Fr>(binary_hash_digest((const char *)root, digest_len), index, n);
+    for (size_t i = 0; i < n; ++i) std::memcpy(out + 3 * i, v[i].mont_repr.data, 24);
+}
+
 /* ---- hashchain ---- */
 void REFN(hashchain_demo)(uint64_t *squeezed /*2 elems*/, uint64_t *positions /*3*/, const uint8_t *absorbed32)
 {

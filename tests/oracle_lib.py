@@ -357,6 +357,13 @@ class Reference:
         self.lib.ref_pow_solve(out, bytes(challenge), C.c_size_t(work_parameter), C.c_size_t(cost_per_hash), C.byref(bl), C.byref(ub))
         return bytes(out), bl.value, ub.value
 
+    def squeeze(self, field_kind, root, index, n):
+        """blake2b_FieldT_randomness_extractor<gf192 | edwards_Fr>(root, index, n) of the unmodified reference."""
+        out = elems(max(n, 1))
+        fn = self.lib.ref_squeeze_gf192 if field_kind == 1 else self.lib.ref_squeeze_edwards
+        fn(_p(out), bytes(root), C.c_size_t(len(root)), C.c_size_t(index), C.c_size_t(n))
+        return out[:n]
+
     def hashchain_demo(self, absorbed=b"\x00" * 32):
         sq = elems(2); pos = np.zeros(3, dtype=np.uint64)
         self.lib.ref_hashchain_demo(_p(sq), _p(pos), absorbed)
@@ -424,3 +431,25 @@ class ReferenceGpu:
 
     def __getattr__(self, name):
         return getattr(self._p, name)
+
+
+def squeeze_model(root, index, n, modulus=None):
+    """hashlib restatement of blake2b_FieldT_randomness_extractor (bcs/hashing/blake2b.tcc:162-256): element i =
+    BLAKE2b(digest 24, key = u64 LE i, root || u64 LE index); prime fields clear the bits above the modulus' top bit
+    and re-draw with key += n while the value is >= modulus."""
+    import hashlib
+    msg = bytes(root) + int(index).to_bytes(8, "little")
+    out = np.zeros((n, 3), dtype=np.uint64)
+    mask = (1 << modulus.bit_length()) - 1 if modulus else None
+    for i in range(n):
+        key = i
+        while True:
+            v = int.from_bytes(hashlib.blake2b(msg, digest_size=24, key=key.to_bytes(8, "little")).digest(), "little")
+            if modulus is None:
+                break
+            v &= mask
+            if v < modulus:
+                break
+            key += n
+        out[i] = [v & (2**64 - 1), (v >> 64) & (2**64 - 1), v >> 128]
+    return out

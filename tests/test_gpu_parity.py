@@ -521,3 +521,58 @@ def test_pow_solve(dev, oracle, golden):
         assert got == want, (bitlen, tries)
         h = hashlib.blake2b(ch + got, digest_size=32).digest()
         assert int.from_bytes(h[24:], "little") & ((1 << bitlen) - 1) == 0
+
+
+# ------------------------------------------------------------------ verifier random messages of the BCS hash chain
+@pytest.mark.parametrize("field", [1, 2])
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 5000])
+def test_squeeze_field_elements(dev, oracle, fp, field, n):
+    """b200_squeeze_field_elements == blake2b_FieldT_randomness_extractor (bcs/hashing/blake2b.tcc:231-256): keyed
+    BLAKE2b per element; for edwards_Fr about half of the draws are rejected and re-drawn with key += n."""
+    from oracle_lib import squeeze_model, Reference
+    root = np.random.default_rng(100 + n).bytes(32)
+    index = 3 + n
+    modulus = oracle.fp_modulus() if field == 2 else None
+    got = dev.squeeze_field_elements(field, fp if field == 2 else None, root + index.to_bytes(8, "little"), n)
+    assert (got == squeeze_model(root, index, n, modulus)).all()
+    if Reference.available():
+        assert (got == Reference().squeeze(field, root, index, n)).all()
+
+
+def test_squeeze_field_elements_at_ligero_size(dev, oracle, fp):
+    """One Ligero lincheck challenge at BASELINE config 4 is 2^18 elements (interleaved_lincheck_ot.tcc:79)."""
+    from oracle_lib import squeeze_model
+    root, index, n = bytes(range(32)), 7, 1 << 18
+    got = dev.squeeze_field_elements(1, None, root + index.to_bytes(8, "little"), n)
+    assert (got == squeeze_model(root, index, n)).all()
+    got = dev.squeeze_field_elements(2, fp, root + index.to_bytes(8, "little"), n)
+    p = oracle.fp_modulus()
+    v = got.astype(object); v = v[:, 0] + (v[:, 1] << 64) + (v[:, 2] << 128)
+    assert (v < p).all()
+    pick = np.arange(0, n, 997)
+    want = squeeze_model_at(root, index, n, pick, p)
+    assert (got[pick] == want).all()
+
+
+def squeeze_model_at(root, index, n, positions, modulus):
+    """squeeze_model restricted to some positions (the draws are independent per position)"""
+    msg = root + int(index).to_bytes(8, "little")
+    mask = (1 << modulus.bit_length()) - 1
+    out = np.zeros((len(positions), 3), dtype=np.uint64)
+    for r, i in enumerate(positions):
+        key = int(i)
+        while True:
+            v = int.from_bytes(hashlib.blake2b(msg, digest_size=24, key=key.to_bytes(8, "little")).digest(), "little") & mask
+            if v < modulus:
+                break
+            key += n
+        out[r] = [v & (2**64 - 1), (v >> 64) & (2**64 - 1), v >> 128]
+    return out
+
+
+def test_squeeze_rejects_bad_arguments(dev, fp):
+    with pytest.raises(Exception):
+        dev.squeeze_field_elements(1, None, b"\x00" * 36, 4)          # not a multiple of 8
+    with pytest.raises(Exception):
+        dev.squeeze_field_elements(1, None, b"\x00" * 136, 4)         # longer than one block
+    assert len(dev.squeeze_field_elements(1, None, b"\x00" * 40, 0)) == 0

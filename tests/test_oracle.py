@@ -229,3 +229,14 @@ def test_pow_golden(oracle, golden):
         assert got.hex() == sol
     ch = hashlib.sha256(b"zero-bits").digest()
     assert oracle.pow_solve(ch, 0, 0)[0] == ch          # the challenge itself is the first candidate
+
+
+@pytest.mark.parametrize("field", [1, 2])
+def test_squeeze_model_matches_the_reference(reference, oracle, field):
+    """The hashlib model the GPU squeeze test checks against == the unmodified reference's
+    blake2b_FieldT_randomness_extractor (bcs/hashing/blake2b.tcc:231-256), rejection sampling included."""
+    from oracle_lib import squeeze_model
+    modulus = oracle.fp_modulus() if field == 2 else None
+    for n, index in ((1, 1), (5, 2), (300, 9)):
+        root = bytes((7 * n + k) & 255 for k in range(32))
+        assert (reference.squeeze(field, root, index, n) == squeeze_model(root, index, n, modulus)).all()
