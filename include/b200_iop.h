@@ -100,6 +100,12 @@ int b200_timer_stop(b200_ctx *, float *ms);          /* synchronises */
 int b200_gf192_fft(b200_ctx *, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out);
 /* IFFT_over_field_subset<gf192>(evals, H) -> additive_IFFT     libiop/algebra/fft.tcc:126-204, 428-433 */
 int b200_gf192_ifft(b200_ctx *, const b200_domain *H, b200_buf evals, b200_buf coeffs_out);
+/* `batch` polynomials over one domain in one call — the row loops of Ligero's interleaved protocols, which run
+ * IFFT_over_field_subset(row, systematic_domain) then FFT_over_field_subset(coefficients, codeword_domain) once per row
+ * (protocols/encoded/ligero/ligero.tcc:293-331, interleaved_lincheck_ot.tcc:283-330, interleaved_rowcheck.tcc).
+ * Row r reads coeffs + r * n_coeffs (evals + r * 2^dim) and writes evals_out + r * 2^dim (coeffs_out + r * 2^dim). */
+int b200_gf192_fft_batch(b200_ctx *, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, size_t batch, b200_buf evals_out);
+int b200_gf192_ifft_batch(b200_ctx *, const b200_domain *H, b200_buf evals, size_t batch, b200_buf coeffs_out);
 /* element-wise helpers (gf192::operator*=, inverse: gf192.cpp:72-184, 245-288) */
 int b200_gf192_mul(b200_ctx *, b200_buf out, b200_buf a, b200_buf b, size_t n);
 int b200_gf192_inv(b200_ctx *, b200_buf out, b200_buf a, size_t n);
@@ -150,6 +156,11 @@ int b200_vec_lincomb(b200_ctx *, int field, const b200_fp_params *fp, b200_buf o
  * f - (c*x^(|H|-1) + Z_H*h) (sumcheck.tcc:95-99). */
 int b200_vec_mul_add(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf b, b200_buf c,
                      b200_buf d, int subtract, size_t n);
+/* out[a] = sum_{r < split} x_r[a]*y_r[a] - sum_{split <= r < rows} x_r[a]*y_r[a]; x, y: rows*n elements, row-major.  The
+ * evaluations of the response polynomial of Ligero's interleaved lincheck: sum over target rows of r_i * f_i minus sum over
+ * input rows of s_i * f_i (protocols/encoded/ligero/interleaved_lincheck_ot.tcc:283-330). */
+int b200_vec_rows_dot(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf x, b200_buf y, size_t n, size_t rows,
+                      size_t split);
 /* out[i] = a[i] * mul + add with host scalars mul / add (NULL = absent): f - claimed_eval (boundary_constraint.tcc:56-60),
  * x - y_i (lagrange_polynomial.tcc:76-85), k * v (batch_inverse_and_mul, algebra/utils.tcc:38-69). */
 int b200_vec_affine(b200_ctx *, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, const uint64_t *mul, const uint64_t *add, size_t n);

@@ -244,6 +244,29 @@ class B200:
         finally:
             self.free(a); self.free(o)
 
+    def gf192_fft_batch(self, dom, rows):
+        """rows: (batch, n_coeffs, 3) -> (batch, 2^dim, 3); one b200_gf192_fft_batch call"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        batch, n_coeffs = rows.shape[0], rows.shape[1]
+        n = 1 << dom.dim
+        a = self.upload(rows.reshape(-1, 3)) if batch * n_coeffs else self.alloc(1); o = self.alloc(max(batch * n, 1))
+        try:
+            self._chk(self.lib.b200_gf192_fft_batch(self.ctx, C.byref(dom.c), C.c_uint64(a), C.c_size_t(n_coeffs), C.c_size_t(batch), C.c_uint64(o)))
+            return self.download(o, batch * n).reshape(batch, n, 3)
+        finally:
+            self.free(a); self.free(o)
+
+    def gf192_ifft_batch(self, dom, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        batch, n = rows.shape[0], 1 << dom.dim
+        assert rows.shape[1] == n
+        a = self.upload(rows.reshape(-1, 3)) if batch else self.alloc(1); o = self.alloc(max(batch * n, 1))
+        try:
+            self._chk(self.lib.b200_gf192_ifft_batch(self.ctx, C.byref(dom.c), C.c_uint64(a), C.c_size_t(batch), C.c_uint64(o)))
+            return self.download(o, batch * n).reshape(batch, n, 3)
+        finally:
+            self.free(a); self.free(o)
+
     def _binop(self, fn, a, b, fp=None):
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 3)
         da = self.upload(a); o = self.alloc(len(a)); db = None
@@ -438,6 +461,20 @@ class B200:
             return self.download(dy, n)
         finally:
             self.free(dx); self.free(dy)
+
+    def vec_rows_dot(self, field, fp, x, y, split):
+        """x, y: (rows, n, 3) -> out[a] = sum_{r<split} x[r,a]*y[r,a] - sum_{r>=split} x[r,a]*y[r,a]"""
+        x = np.ascontiguousarray(x, dtype=np.uint64); y = np.ascontiguousarray(y, dtype=np.uint64)
+        rows, n = x.shape[0], x.shape[1]
+        dx = self.upload(x.reshape(-1, 3)) if rows * n else self.alloc(1)
+        dy = self.upload(y.reshape(-1, 3)) if rows * n else self.alloc(1)
+        o = self.alloc(max(n, 1))
+        try:
+            self._chk(self.lib.b200_vec_rows_dot(self.ctx, C.c_int(field), self._fpref(fp), C.c_uint64(o), C.c_uint64(dx), C.c_uint64(dy),
+                                                 C.c_size_t(n), C.c_size_t(rows), C.c_size_t(split)))
+            return self.download(o, n)
+        finally:
+            self.free(dx); self.free(dy); self.free(o)
 
     def pow_solve(self, challenge, pow_bitlen, pow_upperbound=0):
         out = (C.c_uint8 * 32)()

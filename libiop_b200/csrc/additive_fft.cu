@@ -56,7 +56,8 @@ struct PassParams {
     uint32_t cb;        /* log2(cosets per tile): small transforms pack several cosets into one CTA */
     uint32_t bitrev;    /* load src at bitrev_d(i) (out-of-place first butterfly pass) */
     uint32_t n_extra;
-    uint32_t src_coset_stride_log; /* src advances by coset << this (use 32 for "shared source") */
+    uint32_t src_coset_stride_log; /* src advances by (coset >> src_coset_shr) << this (use 32 for "shared source") */
+    uint32_t src_coset_shr;        /* batched transforms: the 2^shr cosets of one batch row read the same source row */
     uint32_t n_ops;
     uint32_t cl_log;    /* log2(CTAs per tile) for additive_cluster_pass (thread-block cluster, tile spread over DSMEM) */
     uint32_t ops[B200_MAX_OPS];
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
     for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
-        const size_t cofs = shared_src ? 0 : ((size_t)(coset_base + (L >> tbw)) << P.src_coset_stride_log);
+        const size_t cofs = shared_src ? 0 : ((size_t)((coset_base + (L >> tbw)) >> P.src_coset_shr) << P.src_coset_stride_log);
         t.st(L, ldg_elem(P.src + cofs + a));
     }
 
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256, 1) additive_cluster_pass(const PassParams
         const uint32_t L = rank * slice + o;
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
-        const size_t cofs = shared_src ? 0 : ((size_t)(coset_base + (L >> tbw)) << P.src_coset_stride_log);
+        const size_t cofs = shared_src ? 0 : ((size_t)((coset_base + (L >> tbw)) >> P.src_coset_shr) << P.src_coset_stride_log);
         t.st(L, ldg_elem(P.src + cofs + a));
     }
 
@@ -667,7 +668,10 @@ static int upload_taus(b200_ctx *c, const AdditivePlan &pl, const b200_domain *L
     return 0;
 }
 
-int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out)
+/* `batch` independent polynomials over the same domain (Ligero's interleaved rows): row r reads coeffs + r * n_coeffs and
+   writes out + r * 2^m.  Every pass treats the rows as further cosets of the tile grid, so a batch of small transforms
+   fills the machine in the same handful of launches one transform needs. */
+int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out, size_t batch)
 {
     if (!L || L->kind != B200_DOMAIN_AFFINE_SUBSPACE)
         return set_err(c, B200_ERR_INVALID, "additive FFT needs an affine subspace domain");
@@ -676,9 +680,14 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
     const size_t n = (size_t)1 << m;
     if (n_coeffs > n) return set_err(c, B200_ERR_INVALID, "more coefficients (%zu) than domain elements (%zu)", n_coeffs, n);
     gf192 *o = (gf192 *)out;
-    if (n_coeffs <= 1) { /* constant polynomial */
-        fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(o, n_coeffs ? (const gf192 *)coeffs : nullptr, n);
-        B200_LAUNCH_CHECK(c);
+    if (batch == 0) return 0;
+    if (batch > ((size_t)1 << 20) || (batch << m) > ((size_t)1 << 34))
+        return set_err(c, B200_ERR_INVALID, "batch of %zu transforms of 2^%u points is too large", batch, m);
+    if (n_coeffs <= 1) { /* constant polynomials */
+        for (size_t r = 0; r < batch; ++r) {
+            fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(o + r * n, n_coeffs ? (const gf192 *)coeffs + r : nullptr, n);
+            B200_LAUNCH_CHECK(c);
+        }
         return 0;
     }
     const uint32_t d = ceil_log2(n_coeffs);
@@ -690,10 +699,17 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
     if (rc) return rc;
 
     const size_t nd = (size_t)1 << d;
-    gf192 *X = (gf192 *)scratch_get(c, 0, nd * sizeof(gf192));
+    const uint32_t B = (uint32_t)batch;
+    gf192 *X = (gf192 *)scratch_get(c, 0, batch * nd * sizeof(gf192));
     if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate FFT work array");
-    B200_CUDA(c, cudaMemcpyAsync(X, (const void *)coeffs, n_coeffs * sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
-    if (n_coeffs < nd) B200_CUDA(c, cudaMemsetAsync(X + n_coeffs, 0, (nd - n_coeffs) * sizeof(gf192), c->stream));
+    if (n_coeffs == nd || batch == 1) {
+        B200_CUDA(c, cudaMemcpyAsync(X, (const void *)coeffs, batch * n_coeffs * sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
+        if (n_coeffs < nd) B200_CUDA(c, cudaMemsetAsync(X + n_coeffs, 0, (nd - n_coeffs) * sizeof(gf192), c->stream));
+    } else {                                         /* zero-pad every row to 2^d coefficients */
+        B200_CUDA(c, cudaMemsetAsync(X, 0, batch * nd * sizeof(gf192), c->stream));
+        B200_CUDA(c, cudaMemcpy2DAsync(X, nd * sizeof(gf192), (const void *)coeffs, n_coeffs * sizeof(gf192), n_coeffs * sizeof(gf192),
+                                       batch, cudaMemcpyDeviceToDevice, c->stream));
+    }
 
     PassParams P; memset(&P, 0, sizeof P);
     P.tw = pl->tw; P.sums = pl->sums; P.taus = taus; P.n_extra = m - d;
@@ -705,13 +721,13 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
         for (int s = (int)d - 2; s >= (int)j; --s) steps.push_back((OP_TAY << 8) | (uint32_t)s);
     }
     for (const Pass &p : schedule(steps, d)) {
-        P.src = X; P.dst = X; P.src_coset_stride_log = 32; P.n_extra = 0;
-        rc = launch_pass<false>(c, p, P, d, 1);
+        P.src = X; P.dst = X; P.src_coset_stride_log = (B > 1) ? d : 32; P.src_coset_shr = 0; P.n_extra = 0;
+        rc = launch_pass<false>(c, p, P, d, B);
         if (rc) return rc;
     }
     /* butterfly half per coset: bit-reversed load from X (fft.tcc:99), stages 0..d-1 (fft.tcc:101-120) */
     P.n_extra = m - d;
-    const uint32_t n_cosets = 1u << (m - d);
+    const uint32_t n_cosets = B << (m - d);          /* coset index = row * 2^(m-d) + coset of the row */
     const uint32_t tb = std::min(kTileBits, d);
     uint32_t first_hi = d <= tb ? d : tb - kCoalesceBits;
     {
@@ -722,31 +738,37 @@ int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_co
             while (p.cb > 0 && ((size_t)d << p.cb) * sizeof(gf192) > 8192) --p.cb;
         }
         for (uint32_t jj = 0; jj < first_hi; ++jj) p.ops.push_back((OP_BF << 8) | jj);
-        P.src = X; P.dst = o; P.src_coset_stride_log = 32;
+        P.src = X; P.dst = o;
+        if (B > 1) { P.src_coset_stride_log = d; P.src_coset_shr = m - d; }   /* the cosets of a row share the row's X */
+        else { P.src_coset_stride_log = 32; P.src_coset_shr = 0; }
         rc = launch_pass<false>(c, p, P, d, n_cosets);
         if (rc) return rc;
     }
     steps.clear();
     for (uint32_t jj = first_hi; jj < d; ++jj) steps.push_back((OP_BF << 8) | jj);
     for (const Pass &p : schedule(steps, d)) {
-        P.src = o; P.dst = o; P.src_coset_stride_log = d;
+        P.src = o; P.dst = o; P.src_coset_stride_log = d; P.src_coset_shr = 0;
         rc = launch_pass<false>(c, p, P, d, n_cosets);
         if (rc) return rc;
     }
     return 0;
 }
 
-int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out)
+int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out, size_t batch)
 {
     if (!H || H->kind != B200_DOMAIN_AFFINE_SUBSPACE)
         return set_err(c, B200_ERR_INVALID, "additive IFFT needs an affine subspace domain");
     const uint32_t m = H->dim;
     if (m > 31) return set_err(c, B200_ERR_INVALID, "domain dimension %u too large", m);
     const size_t n = (size_t)1 << m;
+    if (batch == 0) return 0;
+    if (batch > ((size_t)1 << 20) || (batch << m) > ((size_t)1 << 34))
+        return set_err(c, B200_ERR_INVALID, "batch of %zu transforms of 2^%u points is too large", batch, m);
     if (m == 0) {
-        B200_CUDA(c, cudaMemcpyAsync((void *)out, (const void *)evals, sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
+        B200_CUDA(c, cudaMemcpyAsync((void *)out, (const void *)evals, batch * sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream));
         return 0;
     }
+    const uint32_t B = (uint32_t)batch;
     std::shared_ptr<AdditivePlan> pl;
     int rc = get_plan(c, (const gf192 *)H->basis, m, true, &pl);
     if (rc) return rc;
@@ -754,11 +776,12 @@ int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf ou
     rc = upload_taus(c, *pl, H, m, m, &taus);
     if (rc) return rc;
 
-    gf192 *X = (gf192 *)scratch_get(c, 0, n * sizeof(gf192));
+    gf192 *X = (gf192 *)scratch_get(c, 0, batch * n * sizeof(gf192));
     if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate IFFT work array");
     gf192 *o = (gf192 *)out;
     PassParams P; memset(&P, 0, sizeof P);
-    P.tw = pl->itw; P.sums = pl->sums; P.taus = taus; P.n_extra = 0; P.src_coset_stride_log = 32;
+    P.tw = pl->itw; P.sums = pl->sums; P.taus = taus; P.n_extra = 0;
+    P.src_coset_stride_log = (B > 1) ? m : 32;       /* batch rows are the "cosets" of the tile grid */
 
     /* inverse butterflies, large stride first (fft.tcc:139-168): evals -> X */
     const uint32_t tb = std::min(kTileBits, m);
@@ -768,7 +791,7 @@ int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf ou
     const gf192 *cur = (const gf192 *)evals;
     for (const Pass &p : schedule(steps, m)) {
         P.src = cur; P.dst = X;
-        rc = launch_pass<true>(c, p, P, m, 1);
+        rc = launch_pass<true>(c, p, P, m, B);
         if (rc) return rc;
         cur = X;
     }
@@ -776,7 +799,7 @@ int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf ou
         Pass p; p.lo = 0; p.hi = last_hi; p.c = 0; p.ctop = m <= tb ? 0 : kCoalesceBits; p.bitrev = 2;
         for (int jj = (int)last_hi - 1; jj >= 0; --jj) p.ops.push_back((OP_BF << 8) | (uint32_t)jj);
         P.src = cur; P.dst = o;
-        rc = launch_pass<true>(c, p, P, m, 1);
+        rc = launch_pass<true>(c, p, P, m, B);
         if (rc) return rc;
     }
     /* radix combinations + inverse twists, deepest level first (fft.tcc:172-201) */
@@ -787,7 +810,7 @@ int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf ou
     }
     for (const Pass &p : schedule(steps, m)) {
         P.src = o; P.dst = o;
-        rc = launch_pass<true>(c, p, P, m, 1);
+        rc = launch_pass<true>(c, p, P, m, B);
         if (rc) return rc;
     }
     return 0;

@@ -240,12 +240,22 @@ int b200_timer_stop(b200_ctx *c, float *ms)
 int b200_gf192_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
 {
     B200_TRACE_SCOPE(c, "gf192_fft", (size_t)1 << L->dim);
-    return additive_fft(c, L, coeffs, n_coeffs, evals_out);
+    return additive_fft(c, L, coeffs, n_coeffs, evals_out, 1);
 }
 int b200_gf192_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
 {
     B200_TRACE_SCOPE(c, "gf192_ifft", (size_t)1 << H->dim);
-    return additive_ifft(c, H, evals, coeffs_out);
+    return additive_ifft(c, H, evals, coeffs_out, 1);
+}
+int b200_gf192_fft_batch(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, size_t batch, b200_buf evals_out)
+{
+    B200_TRACE_SCOPE(c, "gf192_fft_batch", batch << L->dim);
+    return additive_fft(c, L, coeffs, n_coeffs, evals_out, batch);
+}
+int b200_gf192_ifft_batch(b200_ctx *c, const b200_domain *H, b200_buf evals, size_t batch, b200_buf coeffs_out)
+{
+    B200_TRACE_SCOPE(c, "gf192_ifft_batch", batch << H->dim);
+    return additive_ifft(c, H, evals, coeffs_out, batch);
 }
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { return gf192_mul_vec(c, out, a, b, n); }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)

@@ -396,6 +396,19 @@ static FpF make_fpf(const b200_fp_params *fp)
 
 using namespace b200;
 
+/* ---- row-wise inner product of two interleaved codes: out[a] = sum_{r < split} x_r[a] y_r[a] - sum_{r >= split} x_r[a] y_r[a]
+   (x, y: rows x n, row-major).  The response polynomial of Ligero's interleaved lincheck, interleaved_lincheck_ot.tcc:283-330. */
+template<typename F> __global__ void __launch_bounds__(128)
+rows_dot_kernel(typename F::T *out, const typename F::T *x, const typename F::T *y, size_t n, size_t rows, size_t split, const F f)
+{
+    const size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    typename F::T plus = f.zero(), minus = f.zero();
+    for (size_t r = 0; r < split; ++r) plus = f.add(plus, f.mul(ld_el(x, r * n + a), ld_el(y, r * n + a)));
+    for (size_t r = split; r < rows; ++r) minus = f.add(minus, f.mul(ld_el(x, r * n + a), ld_el(y, r * n + a)));
+    st_el(out, a, f.sub(plus, minus));
+}
+
 extern "C" {
 
 int b200_vec_lincomb(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, size_t n, size_t k,
@@ -420,6 +433,22 @@ int b200_vec_mul_add(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf 
     else
         mul_add_kernel<FpF><<<ew_grid(c, n, 256), 256, 0, c->stream>>>((fp192 *)out, (const fp192 *)a, (const fp192 *)b, (const fp192 *)cc,
                                                                       (const fp192 *)d, subtract, n, make_fpf(fp));
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int b200_vec_rows_dot(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf x, b200_buf y, size_t n, size_t rows,
+                      size_t split)
+{
+    B200_TRACE_SCOPE(c, "vec_rows_dot", n * rows);
+    if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
+    if (split > rows) return set_err(c, B200_ERR_INVALID, "b200_vec_rows_dot: split beyond the number of rows");
+    if (!n) return 0;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (field == B200_FIELD_GF192)
+        rows_dot_kernel<GfF><<<grid, 128, 0, c->stream>>>((gf192 *)out, (const gf192 *)x, (const gf192 *)y, n, rows, split, GfF());
+    else
+        rows_dot_kernel<FpF><<<grid, 128, 0, c->stream>>>((fp192 *)out, (const fp192 *)x, (const fp192 *)y, n, rows, split, make_fpf(fp));
     B200_LAUNCH_CHECK(c);
     return 0;
 }

@@ -124,6 +124,43 @@ template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_of_known_degree_over_field_subset(const std::vector<FieldT> evals, std::size_t degree, DomainT domain)
 { return IFFT_of_known_degree_over_field_subset_cref<FieldT>(evals, degree, domain); }
 
+/* Interleaved Reed-Solomon encoding (Ligero): `n_rows` rows, row r holding the |H| evaluations at rows + r * |H|, are
+   interpolated over the systematic domain H and evaluated over the codeword domain L — the reference does this one row at
+   a time with IFFT_over_field_subset + FFT_over_field_subset (ligero.tcc:293-331, interleaved_lincheck_ot.tcc:283-330);
+   here all rows go through b200_gf192_ifft_batch / b200_gf192_fft_batch.  Returns n_rows * |L| elements, row-major.
+   `rows` must stay alive and unmodified until the next synchronising call on the context. */
+template<typename FieldT, typename DomainT>
+device_buffer encode_rows_device(const FieldT *rows, std::size_t n_rows, const DomainT &H, const DomainT &L)
+{
+    static_assert(field_traits<FieldT>::kind == B200_FIELD_GF192, "batched row encoding is implemented for additive domains");
+    const std::size_t nH = H.num_elements(), nL = L.num_elements();
+    device_buffer in(n_rows * nH), coeffs(n_rows * nH), out(n_rows * nL);
+    if (n_rows == 0) return out;
+    throw_status(context(), b200_upload(context(), in.get(), 0, reinterpret_cast<const uint64_t *>(rows), n_rows * nH));
+    std::vector<uint64_t> store_h, store_l;
+    const b200_domain dh = make_domain<FieldT>(H, store_h), dl = make_domain<FieldT>(L, store_l);
+    throw_status(context(), b200_gf192_ifft_batch(context(), &dh, in.get(), n_rows, coeffs.get()));
+    throw_status(context(), b200_gf192_fft_batch(context(), &dl, coeffs.get(), nH, n_rows, out.get()));
+    return out;
+}
+
+/* the same, handed back as one host vector per row (what oracle<FieldT> wants); every row keeps a device copy in the
+   residency cache for the Merkle tree and the linchecks that read it next */
+template<typename FieldT, typename DomainT>
+std::vector<std::vector<FieldT>> encode_rows(const FieldT *rows, std::size_t n_rows, const DomainT &H, const DomainT &L)
+{
+    const std::size_t nL = L.num_elements();
+    const device_buffer all = encode_rows_device<FieldT>(rows, n_rows, H, L);
+    std::vector<std::vector<FieldT>> result;
+    result.reserve(n_rows);
+    for (std::size_t r = 0; r < n_rows; ++r) {
+        device_buffer row(nL);
+        throw_status(context(), b200_copy(context(), row.get(), 0, all.get(), r * nL, nL));
+        result.emplace_back(download_and_keep<FieldT>(std::move(row), nL));
+    }
+    return result;
+}
+
 /* fri_aux.hpp:23-28 */
 template<typename FieldT, typename DomainT>
 void evaluate_next_f_i_over_entire_domain_device(const device_buffer &f_i, const DomainT &f_i_domain, std::size_t coset_size,

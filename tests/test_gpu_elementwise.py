@@ -310,3 +310,21 @@ def test_spmv_csr(dev, oracle, fp, field):
     with pytest.raises(Exception):
         bad = col.copy(); bad[5] = n_x
         dev.spmv_csr(field, fp if field == FP else None, row_ptr, bad, coeff, x)
+
+
+@pytest.mark.parametrize("field", [GF, FP])
+@pytest.mark.parametrize("rows,split,n", [(1, 1, 5), (7, 3, 1000), (6, 0, 129), (5, 5, 128), (0, 0, 9)])
+def test_vec_rows_dot(dev, oracle, fp, field, rows, split, n):
+    """sum over the first `split` rows of x_r * y_r minus the sum over the others: the response evaluations of Ligero's
+    interleaved lincheck (interleaved_lincheck_ot.tcc:283-330), restated with the oracle's field arithmetic."""
+    F = ops_for(field, oracle)
+    rng = np.random.default_rng(31 * rows + n)
+    x = F.rand(rng, rows * n).reshape(rows, n, 3); y = F.rand(rng, rows * n).reshape(rows, n, 3)
+    want = np.zeros((n, 3), dtype=np.uint64)
+    for r in range(rows):
+        prod = F.mul(x[r], y[r])
+        want = F.add(want, prod) if r < split else F.sub(want, prod)
+    got = dev.vec_rows_dot(field, fp if field == FP else None, x, y, split)
+    assert (got == want).all()
+    with pytest.raises(Exception):
+        dev.vec_rows_dot(field, fp if field == FP else None, x, y, rows + 1)

@@ -127,6 +127,46 @@ print('OK')
         assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("m,n_coeffs,batch", [(13, 2048, 5), (13, 2048, 1), (12, 1000, 3), (15, 1 << 13, 2), (11, 2048, 37),
+                                              (8, 64, 300), (13, 1, 4), (14, 1 << 14, 3), (16, 1 << 13, 3)])
+def test_additive_fft_batch_equals_the_oracle_row_by_row(dev, oracle, m, n_coeffs, batch):
+    """b200_gf192_fft_batch: the rows of Ligero's interleaved codes (ligero.tcc:293-331) in one call; every row must be
+    the reference's additive_FFT of that row (non-power-of-two coefficient counts are zero-padded per row)."""
+    import libiop_b200 as L
+    rng = np.random.default_rng(1000 * m + batch)
+    basis, shift = standard_basis(m), el(1 << m)
+    rows = rand_elems(rng, batch * n_coeffs).reshape(batch, n_coeffs, 3)
+    got = dev.gf192_fft_batch(L.Domain.standard(m), rows)
+    assert got.shape == (batch, 1 << m, 3)
+    for r in range(batch):
+        assert (got[r] == oracle.additive_fft(rows[r], m, basis, shift)).all(), r
+
+
+@pytest.mark.parametrize("m,batch", [(11, 7), (11, 1), (13, 3), (5, 300), (14, 2), (1, 5), (0, 4)])
+def test_additive_ifft_batch_equals_the_oracle_row_by_row(dev, oracle, m, batch):
+    import libiop_b200 as L
+    rng = np.random.default_rng(77 * m + batch)
+    basis, shift = standard_basis(m), el(1 << m)
+    rows = rand_elems(rng, batch << m).reshape(batch, 1 << m, 3)
+    got = dev.gf192_ifft_batch(L.Domain.standard(m), rows)
+    for r in range(batch):
+        assert (got[r] == oracle.additive_ifft(rows[r], m, basis, shift)).all(), r
+
+
+def test_additive_batch_lde_at_ligero_size_round_trips(dev):
+    """512 rows 2^11 -> 2^13 (BASELINE config 4): IFFT over the systematic domain, FFT over the codeword domain, and the
+    first 2^11 coefficients of the IFFT over the codeword domain are the row's coefficients again."""
+    import libiop_b200 as L
+    rng = np.random.default_rng(4)
+    rows = rand_elems(rng, 512 << 11).reshape(512, 1 << 11, 3)
+    coeffs = dev.gf192_ifft_batch(L.Domain.standard(11), rows)
+    code = dev.gf192_fft_batch(L.Domain.standard(13), coeffs)
+    back = dev.gf192_ifft_batch(L.Domain.standard(13), code)
+    assert (back[:, :1 << 11] == coeffs).all() and not back[:, 1 << 11:].any()
+    for r in (0, 255, 511):
+        assert (code[r] == dev.gf192_fft(L.Domain.standard(13), coeffs[r])).all()
+
+
 def test_additive_fft_empty_and_errors(dev):
     import libiop_b200 as L
     d = L.Domain.standard(6)
