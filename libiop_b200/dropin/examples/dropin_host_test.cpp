@@ -18,6 +18,7 @@
 #include "libiop/bcs/hashing/blake2b.hpp"
 
 extern "C" void b200_shim_randombytes_seed(uint64_t seed);
+extern "C" void b200_shim_randombytes_secure(void);
 
 using namespace libiop;
 
@@ -52,6 +53,26 @@ int main()
         CHECK(same);
         CHECK(b200_glue::salt_at(t.salts(), leaves, leaves / 2) == t.salts()[leaves / 2]);
         CHECK(b200_glue::salt_at({flat}, leaves, leaves / 2) == t.salts()[leaves / 2]);
+    }
+    /* 1b. a salt length that does not divide the 1 MiB batch (security 100 -> 25 bytes): leafs_per_batch * 25 exceeds the batch;
+           every salt byte must still come from randombytes_buf (no read past the batch buffer) */
+    {
+        b200_shim_randombytes_seed(99);
+        const std::size_t leaves = std::size_t(1) << 17, zk_bytes = 25;
+        const std::string flat = b200_glue::sample_salts_flat(leaves, zk_bytes);
+        CHECK(flat.size() == leaves * zk_bytes);
+        std::size_t zeros = 0;
+        for (std::size_t i = flat.size() - 65536; i < flat.size(); ++i) zeros += flat[i] == 0;
+        CHECK(zeros < 1024);                      /* ~256 expected from a uniform stream */
+    }
+    /* 1c. without the parity switch randombytes_buf is the unpredictable generator: two draws differ, and differ from the seeded stream */
+    {
+        unsigned char a[32], b[32], c[32];
+        b200_shim_randombytes_secure();
+        randombytes_buf(a, 32); randombytes_buf(b, 32);
+        b200_shim_randombytes_seed(0);
+        randombytes_buf(c, 32);
+        CHECK(std::memcmp(a, b, 32) != 0 && std::memcmp(a, c, 32) != 0 && std::memcmp(b, c, 32) != 0);
     }
     /* 2. pruned authentication paths: node list vs the reference's proof on a CPU-built tree */
     std::mt19937_64 rng(7);

@@ -45,7 +45,11 @@ inline std::string sample_salts_flat(std::size_t num_leaves, std::size_t num_zk_
     std::size_t leaf = 0;
     for (std::size_t b = 0; b < num_batches; ++b) {
         randombytes_buf(batch.data(), batch_bytes);
-        std::memcpy(&salts[leaf * num_zk_bytes], batch.data(), leafs_per_batch * num_zk_bytes);
+        /* salt lengths that do not divide 2^20 make leafs_per_batch * num_zk_bytes exceed the batch (the reference reads past
+           its buffer there, merkle_tree.tcc:52-58): the tail of such a batch is drawn with a further call instead */
+        const std::size_t want = leafs_per_batch * num_zk_bytes, have = std::min(want, batch_bytes);
+        std::memcpy(&salts[leaf * num_zk_bytes], batch.data(), have);
+        if (want > have) randombytes_buf(&salts[leaf * num_zk_bytes + have], want - have);
         leaf += leafs_per_batch;
     }
     for (; leaf < num_leaves; ++leaf) randombytes_buf(&salts[leaf * num_zk_bytes], num_zk_bytes);

@@ -39,8 +39,19 @@ typedef libff::gf192 G;
 typedef libff::edwards_Fr Fr;
 
 extern "C" void b200_shim_randombytes_seed(uint64_t seed);
+extern "C" void b200_shim_randombytes_secure(void);
 
 namespace {
+
+/* The instance is always generated from the seeded stream (reproducible benchmarks and parity runs).  The PROOF's own
+   randomness — zero-knowledge masks and Merkle salts, all drawn through randombytes_buf — comes from the unpredictable
+   generator unless the parity harness asks for the seeded stream with B200_DETERMINISTIC_RNG=1 (tests/conftest.py sets it
+   so that zk transcripts can be compared bit for bit with the CPU reference's). */
+void arm_proof_randomness(bool make_zk)
+{
+    const char *e = std::getenv("B200_DETERMINISTIC_RNG");
+    if (make_zk && !(e && e[0] == '1')) b200_shim_randombytes_secure();
+}
 
 void init_once()
 {
@@ -118,6 +129,7 @@ double b200_prover_aurora_gf192(uint32_t log_n, uint32_t k_inputs, int make_zk, 
         128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
         blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
         ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    arm_proof_randomness(make_zk != 0);
     const auto t0 = std::chrono::steady_clock::now();
     const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
         ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
@@ -141,6 +153,7 @@ void b200_prover_aurora_gf192_repeat(uint32_t log_n, uint32_t k_inputs, int make
         128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
         blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
         ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    arm_proof_randomness(make_zk != 0);
     for (uint32_t r = 0; r < repeats; ++r) {
         const auto t0 = std::chrono::steady_clock::now();
         const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
@@ -215,6 +228,7 @@ double b200_prover_ligero_gf192(uint32_t log_n, double height_width_ratio, uint3
     params.make_zk_ = make_zk != 0;
     params.domain_type_ = affine_subspace_type;
     params.bcs_params_ = default_bcs_params<G, binary_hash_digest>(blake2b_type, 128, log_n);
+    arm_proof_randomness(make_zk != 0);
     const auto t0 = std::chrono::steady_clock::now();
     const auto proof = ligero_snark_prover<G, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
     const auto t1 = std::chrono::steady_clock::now();

@@ -3,10 +3,11 @@
  * libiop/bcs/hashing/blake2b.cpp:15,37,62, blake2b.tcc:56,146,172,200; libff random_element via randombytes_buf),
  * for images without libsodium.  A deployment with libsodium installed links that instead and drops this file.
  *   crypto_generichash_blake2b : RFC 7693 BLAKE2b, sequential mode, optional key, 1..64 byte digests
- *   randombytes_buf            : seedable xorshift64 stream (deterministic instances / salts for parity runs);
- *                                b200_shim_randombytes_seed(0) restores the default seed.
+ *   randombytes_buf            : ChaCha20 keystream keyed from getrandom(2) by default; the seeded xorshift64 stream of the
+ *                                parity harness only after b200_shim_randombytes_deterministic() (see below).
  * Host-side control-plane hashing only (hash chain, query positions, verifier): bulk hashing runs on the device.
  */
+#define _GNU_SOURCE
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -77,11 +78,94 @@ int crypto_generichash_blake2b(unsigned char *out, size_t outlen, const unsigned
     return 0;
 }
 
+/* ---- randombytes_buf ---------------------------------------------------------------------------------------------
+ * All of the reference's prover randomness comes through this symbol: the zero-knowledge masking polynomials
+ * (gf192::random_element), Ligero's blinding rows and the Merkle leaf salts (merkle_tree.tcc:37-72).
+ *   default        : a ChaCha20 keystream keyed with 32 bytes from getrandom(2) (re-keyed after fork) — unpredictable.
+ *   deterministic  : the seeded xorshift64 stream of the parity harness (same stream as oracle/ref_shim/sodium_impl.c, so
+ *                    the CPU reference and the drop-in draw identical instances and salts).  NOT zero-knowledge: only
+ *                    b200_shim_randombytes_deterministic() switches it on, and the prover harness (prover_api.cpp) leaves
+ *                    it on across a make_zk proof only when B200_DETERMINISTIC_RNG=1 is set (tests/conftest.py). */
+#include <errno.h>
+#include <stdlib.h>
+#include <sys/random.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+static int shim_deterministic = 0;
 static uint64_t shim_rng_state = 0x9E3779B97F4A7C15ULL;
-void b200_shim_randombytes_seed(uint64_t seed) { shim_rng_state = seed ? seed : 0x9E3779B97F4A7C15ULL; }
+
+void b200_shim_randombytes_deterministic(uint64_t seed)
+{
+    shim_deterministic = 1;
+    shim_rng_state = seed ? seed : 0x9E3779B97F4A7C15ULL;
+}
+void b200_shim_randombytes_secure(void) { shim_deterministic = 0; }
+int b200_shim_randombytes_is_deterministic(void) { return shim_deterministic; }
+/* historical name used by the harnesses: same as ..._deterministic */
+void b200_shim_randombytes_seed(uint64_t seed) { b200_shim_randombytes_deterministic(seed); }
+
+/* ChaCha20 block function (RFC 8439 2.3) */
+#define CC_ROTL(v, n) (((v) << (n)) | ((v) >> (32 - (n))))
+#define CC_QR(a, b, c, d) a += b; d ^= a; d = CC_ROTL(d, 16); c += d; b ^= c; b = CC_ROTL(b, 12); \
+                          a += b; d ^= a; d = CC_ROTL(d, 8);  c += d; b ^= c; b = CC_ROTL(b, 7)
+static void chacha20_block(const uint32_t in[16], uint8_t out[64])
+{
+    uint32_t x[16];
+    for (int i = 0; i < 16; ++i) x[i] = in[i];
+    for (int r = 0; r < 10; ++r) {
+        CC_QR(x[0], x[4], x[8], x[12]); CC_QR(x[1], x[5], x[9], x[13]); CC_QR(x[2], x[6], x[10], x[14]); CC_QR(x[3], x[7], x[11], x[15]);
+        CC_QR(x[0], x[5], x[10], x[15]); CC_QR(x[1], x[6], x[11], x[12]); CC_QR(x[2], x[7], x[8], x[13]); CC_QR(x[3], x[4], x[9], x[14]);
+    }
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t v = x[i] + in[i];
+        out[4 * i] = (uint8_t)v; out[4 * i + 1] = (uint8_t)(v >> 8); out[4 * i + 2] = (uint8_t)(v >> 16); out[4 * i + 3] = (uint8_t)(v >> 24);
+    }
+}
+
+static uint32_t cc_state[16];
+static pid_t cc_pid = 0;
+static int cc_keyed = 0;
+
+static void secure_key(void)
+{
+    uint8_t key[48];
+    size_t got = 0;
+    while (got < sizeof key) {
+        const ssize_t r = getrandom(key + got, sizeof key - got, 0);
+        if (r < 0) { if (errno == EINTR) continue; abort(); }   /* no entropy source: never fall back to something guessable */
+        got += (size_t)r;
+    }
+    cc_state[0] = 0x61707865u; cc_state[1] = 0x3320646eu; cc_state[2] = 0x79622d32u; cc_state[3] = 0x6b206574u;
+    memcpy(&cc_state[4], key, 32);
+    cc_state[12] = 0; memcpy(&cc_state[13], key + 32, 12);
+    memset(key, 0, sizeof key);
+    cc_pid = getpid();
+    cc_keyed = 1;
+}
+
+static void secure_bytes(unsigned char *p, size_t size)
+{
+    if (!cc_keyed || cc_pid != getpid()) secure_key();
+    uint8_t block[64];
+    while (size) {
+        chacha20_block(cc_state, block);
+        if (++cc_state[12] == 0) secure_key();                  /* 256 GiB per key */
+        const size_t k = size < 64 ? size : 64;
+        memcpy(p, block, k);
+        p += k; size -= k;
+    }
+    /* fast key erasure: the next 32 keystream bytes replace the key, so earlier output cannot be recomputed from a later state */
+    chacha20_block(cc_state, block);
+    memcpy(&cc_state[4], block, 32);
+    cc_state[12] = 0;
+    memset(block, 0, sizeof block);
+}
+
 void randombytes_buf(void *buf, size_t size)
 {
     unsigned char *p = (unsigned char *)buf;
+    if (!shim_deterministic) { secure_bytes(p, size); return; }
     for (size_t i = 0; i < size; ++i) {
         shim_rng_state ^= shim_rng_state << 13;
         shim_rng_state ^= shim_rng_state >> 7;

@@ -7,6 +7,10 @@ import pytest
 sys.path.insert(0, os.path.dirname(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(__file__)))
 
+# Parity flag: zero-knowledge proofs of the drop-in harness draw their masks and salts from the seeded stream the CPU
+# reference was run with (libiop_b200/dropin/shims/sodium_shim.c); without it they come from the ChaCha20/getrandom generator.
+os.environ.setdefault("B200_DETERMINISTIC_RNG", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

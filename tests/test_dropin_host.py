@@ -49,6 +49,30 @@ def test_shim_randombytes_stream_is_the_seeded_xorshift(shim):
     assert bytes(buf)[:37] == stream(12345, 37)
 
 
+def test_shim_randombytes_is_unpredictable_unless_the_parity_switch_is_thrown(shim):
+    """the default randombytes_buf must not be the seeded stream — zk masks and Merkle salts come from it.
+    Default = ChaCha20 keyed from getrandom(2); the xorshift stream only after b200_shim_randombytes_deterministic/seed."""
+    a, b = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+    fresh = C.CDLL(shim._name)                       # same mapping, state as loaded: nothing has switched the mode yet in a new process
+    fresh.b200_shim_randombytes_secure()
+    assert fresh.b200_shim_randombytes_is_deterministic() == 0
+    fresh.randombytes_buf(a, C.c_size_t(64)); fresh.randombytes_buf(b, C.c_size_t(64))
+    assert bytes(a) != bytes(b) and len(set(bytes(a))) > 16
+    fresh.b200_shim_randombytes_deterministic(C.c_uint64(7))
+    assert fresh.b200_shim_randombytes_is_deterministic() == 1
+    fresh.randombytes_buf(a, C.c_size_t(64))
+    fresh.b200_shim_randombytes_deterministic(C.c_uint64(7))
+    fresh.randombytes_buf(b, C.c_size_t(64))
+    assert bytes(a) == bytes(b)
+    fresh.b200_shim_randombytes_secure()
+    fresh.randombytes_buf(b, C.c_size_t(64))
+    assert bytes(a) != bytes(b)
+    # a process that never calls the switch starts in the secure mode
+    code = ("import ctypes as C; l = C.CDLL(%r); print(l.b200_shim_randombytes_is_deterministic())" % shim._name)
+    out = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert out.stdout.strip() == "0", out.stderr
+
+
 def test_dropin_library_exports_prover_entry_points():
     from libiop_b200 import prover
     if not prover.available():

@@ -453,6 +453,35 @@ def test_dropin_provers_match_cpu_reference_fingerprints(case):
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == (case["bytes"], case["sha256"])
 
 
+def _config_fingerprints():
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prover_fingerprints_config.json")
+    return json.load(open(path)) if os.path.exists(path) else []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _config_fingerprints(), ids=lambda c: f"{c['config']}-{c['prover']}-2^{c['log_n']}{'-zk' if c['zk'] else ''}")
+def test_dropin_provers_at_baseline_config_sizes(case):
+    """BASELINE.json configs 2-5 at FULL size (Aurora GF(2^192) N=2^20, Fractal edwards N=2^18, Ligero GF(2^192) N=2^18, Aurora
+    N=2^22 = one rank of config 5, and the zero-knowledge Aurora with the same 2^23-point codeword as config 2): the transcript
+    of the drop-in prover must hash to the fingerprint of the UNMODIFIED CPU reference run recorded (with its CPU seconds) by
+    tests/golden/make_config_fingerprints.py, and the reference verifier must accept the GPU-built proof."""
+    import hashlib
+    from oracle_lib import ReferenceGpu
+    if not ReferenceGpu.available():
+        pytest.skip("libiop_b200/lib/libiop_b200_dropin.so not built (needs /root/reference at build time)")
+    g = ReferenceGpu()
+    which, log_n, zk = case["prover"], case["log_n"], case["zk"]
+    if which == "aurora_gf192":
+        _, dump, acc = g.aurora_gf192(log_n, make_zk=zk)
+    elif which == "fractal_edwards":
+        _, dump, acc, _ = g.fractal_edwards(log_n)
+    else:
+        _, dump, acc = g.ligero_gf192(log_n, make_zk=zk)
+    assert acc == 1, "reference verifier rejected the GPU-built proof"
+    assert (len(dump), hashlib.sha256(dump).hexdigest()) == (case["bytes"], case["sha256"])
+
+
 def test_device_spmv_route_of_the_dropin_is_bit_exact():
     """create_Az_Bz_Cz_from_variable_assignment goes to b200_spmv_csr only from three terms per row (measured crossover);
     B200_SPMV_MIN_TERMS_PER_ROW=0 forces that route for the one-term rows of generate_r1cs_example — same transcripts."""
