@@ -14,10 +14,13 @@ def available():
 
 
 class DropinProver:
-    def __init__(self):
-        if not available():
-            raise RuntimeError(f"{LIB_PATH} is missing: `make -C libiop_b200/dropin` (needs the reference checkout at build time)")
-        self.lib = C.CDLL(LIB_PATH)
+    def __init__(self, lib_path=None):
+        """lib_path: another build of the same objects (tests/hostsim: the host-logic tests link them against a host simulator
+        of the C ABI); the product always loads LIB_PATH."""
+        lib_path = lib_path or LIB_PATH
+        if not os.path.exists(lib_path):
+            raise RuntimeError(f"{lib_path} is missing: `make -C libiop_b200/dropin` (needs the reference checkout at build time)")
+        self.lib = C.CDLL(lib_path)
         for fn in ("b200_prover_aurora_gf192", "b200_prover_aurora_edwards", "b200_prover_fractal_edwards", "b200_prover_ligero_gf192"):
             getattr(self.lib, fn).restype = C.c_double
 
