@@ -85,7 +85,13 @@ int b200_upload(b200_ctx *, b200_buf dst, size_t dst_offset, const uint64_t *src
 int b200_download(b200_ctx *, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems);
 int b200_upload_bytes(b200_ctx *, b200_bytes dst, const uint8_t *src, size_t n_bytes);
 int b200_download_bytes(b200_ctx *, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes);
+/* blocks until every b200_upload / b200_upload_bytes issued so far has left the host buffer (kernels queued behind them keep
+ * running): the point after which the caller may release or rewrite its host vectors */
+int b200_wait_uploads(b200_ctx *);
 int b200_copy(b200_ctx *, b200_buf dst, size_t dst_offset, b200_buf src, size_t src_offset, size_t n_elems);
+/* dst[i] = src[src_offset + i * stride], i < n_elems: the evaluations over a sub-coset of a multiplicative domain
+ * (IFFT_of_known_degree_over_field_subset, libiop/algebra/fft.tcc:446-455) taken from a device-resident codeword */
+int b200_copy_strided(b200_ctx *, b200_buf dst, b200_buf src, size_t src_offset, size_t stride, size_t n_elems);
 int b200_fill_zero(b200_ctx *, b200_buf dst, size_t dst_offset, size_t n_elems);
 /* iop_protocol::get_oracle_evaluation_at_point (libiop/iop/iop.tcc:670-688): query answers */
 int b200_gather(b200_ctx *, uint64_t *dst, b200_buf src, const size_t *idx, size_t k);

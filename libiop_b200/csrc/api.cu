@@ -14,6 +14,15 @@ void plans_clear(b200_ctx *c) { c->additive_plans.clear(); c->ntt_plans.clear();
 
 using namespace b200;
 
+/* dst[i] = src[i * stride] over 24-byte elements (one thread per element, three u64 words) */
+__global__ void copy_strided_kernel(uint64_t *dst, const uint64_t *src, size_t stride, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t *q = src + 3 * i * stride;
+        dst[3 * i] = q[0]; dst[3 * i + 1] = q[1]; dst[3 * i + 2] = q[2];
+    }
+}
+
 extern "C" {
 
 const char *b200_version(void) { return "libb200iop 0.1 (sm_100a)"; }
@@ -32,7 +41,8 @@ b200_ctx *b200_ctx_create(int device)
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError(); delete c; return nullptr;
     }
     const char *tr = getenv("B200_TRACE");
@@ -50,7 +60,7 @@ void b200_ctx_destroy(b200_ctx *c)
     for (auto &kv : c->live_blocks) cudaFree(kv.first);
     for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->staging) cudaFreeHost(c->staging);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_upload);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -137,6 +147,15 @@ int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *sr
     B200_TRACE_SCOPE(c, "upload", n_elems * 24);
     c->h2d_bytes += n_elems * 24;
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, src, n_elems * 24, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+    c->upload_pending = true;
+    return 0;
+}
+int b200_wait_uploads(b200_ctx *c)
+{
+    if (!c->upload_pending) return 0;
+    B200_CUDA(c, cudaEventSynchronize(c->ev_upload));
+    c->upload_pending = false;
     return 0;
 }
 int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems)
@@ -152,6 +171,8 @@ int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_
     B200_TRACE_SCOPE(c, "upload_bytes", n_bytes);
     c->h2d_bytes += n_bytes;
     B200_CUDA(c, cudaMemcpyAsync((void *)(uintptr_t)dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+    c->upload_pending = true;
     return 0;
 }
 int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes)
@@ -166,6 +187,14 @@ int b200_copy(b200_ctx *c, b200_buf dst, size_t dst_offset, b200_buf src, size_t
 {
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, (const char *)(uintptr_t)src + src_offset * 24,
                                  n_elems * 24, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int b200_copy_strided(b200_ctx *c, b200_buf dst, b200_buf src, size_t src_offset, size_t stride, size_t n_elems)
+{
+    if (!n_elems) return 0;
+    const unsigned grid = (unsigned)((n_elems + 255) / 256 < 148 * 8 ? (n_elems + 255) / 256 : 148 * 8);
+    copy_strided_kernel<<<grid, 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst, (const uint64_t *)(uintptr_t)src + 3 * src_offset, stride, n_elems);
+    B200_LAUNCH_CHECK(c);
     return 0;
 }
 int b200_fill_zero(b200_ctx *c, b200_buf dst, size_t dst_offset, size_t n_elems)

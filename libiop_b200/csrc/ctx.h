@@ -23,6 +23,8 @@ struct b200_ctx {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_upload = nullptr;   /* recorded after every host->device copy (b200_wait_uploads) */
+    bool upload_pending = false;
     char err[512] = {0};
     /* grow-only device scratch (work arrays of the FFTs), keyed by slot */
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -26,11 +26,12 @@ libiop_b200::device_view to_device(const std::vector<FieldT> &v)
     return libiop_b200::device_view(v);
 }
 
-/* result of a device pass as the shared host vector the IOP layer expects; the device copy stays resident */
+/* result of a device pass as the shared host vector the IOP layer expects: a lazy vector, i.e. the contents stay in the
+   device buffer until (unless) the host reads them (libiop_b200/host/b200_residency.hpp) */
 template<typename FieldT>
 std::shared_ptr<std::vector<FieldT>> to_host(libiop_b200::device_buffer &b, std::size_t n)
 {
-    return std::make_shared<std::vector<FieldT>>(libiop_b200::download_and_keep<FieldT>(std::move(b), n));
+    return std::make_shared<std::vector<FieldT>>(libiop_b200::make_lazy_vector<FieldT>(std::move(b), n));
 }
 
 } // namespace b200_glue

@@ -255,10 +255,18 @@ void b200_prover_arena_stats(uint64_t *slabs, uint64_t *reserved_bytes, uint64_t
     *reserved_bytes = a ? a->reserved_bytes() : 0;
     *free_bytes = a ? a->free_bytes() : 0;
 }
+/* stale = lazy vectors the host touched (each one a whole-vector download), see b200_prover_lazy_stats */
 void b200_prover_residency_stats(uint64_t *hits, uint64_t *misses, uint64_t *stale, uint64_t *resident_bytes)
 {
     libiop_b200::residency &r = libiop_b200::residency::instance();
-    *hits = r.hits(); *misses = r.misses(); *stale = r.stale(); *resident_bytes = r.resident_bytes();
+    *hits = r.hits(); *misses = r.misses(); *stale = r.faults(); *resident_bytes = r.resident_bytes();
+}
+
+/* device-resident oracles: host accesses that forced a whole-vector download (count, bytes), gathers of the query phase */
+void b200_prover_lazy_stats(uint64_t *faults, uint64_t *fault_bytes, uint64_t *gathers)
+{
+    libiop_b200::residency &r = libiop_b200::residency::instance();
+    *faults = r.faults(); *fault_bytes = r.fault_bytes(); *gathers = r.gathers();
 }
 
 } /* extern "C" */

@@ -30,24 +30,29 @@ inline void throw_status(b200_ctx *ctx, int rc)
 }
 
 /* one context per process (the reference is single-threaded, SURVEY.md §8b "Threading") */
+inline b200_ctx *make_context()
+{
+    /* device ordinal: B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun / mpirun), else 0 */
+    const char *d = std::getenv("B200_DEVICE");
+    if (!d) d = std::getenv("LOCAL_RANK");
+    b200_ctx *ctx = b200_ctx_create(d ? std::atoi(d) : 0);
+    if (!ctx) throw std::runtime_error("libiop_b200: no CUDA device (the hot path has no CPU fallback)");
+    return ctx;
+}
 inline b200_ctx *context()
 {
-    static b200_ctx *ctx = nullptr;
-    if (!ctx) {
-        /* device ordinal: B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun / mpirun), else 0 */
-        const char *d = std::getenv("B200_DEVICE");
-        if (!d) d = std::getenv("LOCAL_RANK");
-        ctx = b200_ctx_create(d ? std::atoi(d) : 0);
-        if (!ctx) throw std::runtime_error("libiop_b200: no CUDA device (the hot path has no CPU fallback)");
-    }
+    static b200_ctx *ctx = make_context();       /* C++11 one-time initialisation: safe against concurrent first calls */
     return ctx;
 }
 
 class device_buffer {
     b200_buf buf_ = 0;
     std::size_t n_ = 0;
+    bool owned_ = true;
 public:
     device_buffer() = default;
+    /* a non-owning handle on n elements of somebody else's buffer (device_view of a resident vector) */
+    static device_buffer alias(b200_buf b, std::size_t n) { device_buffer d; d.buf_ = b; d.n_ = n; d.owned_ = false; return d; }
     explicit device_buffer(std::size_t n_elems) : n_(n_elems)
     {
         buf_ = b200_alloc(context(), n_elems ? n_elems : 1);
@@ -55,14 +60,15 @@ public:
     }
     device_buffer(const device_buffer &) = delete;
     device_buffer &operator=(const device_buffer &) = delete;
-    device_buffer(device_buffer &&o) noexcept : buf_(o.buf_), n_(o.n_) { o.buf_ = 0; o.n_ = 0; }
+    device_buffer(device_buffer &&o) noexcept : buf_(o.buf_), n_(o.n_), owned_(o.owned_) { o.buf_ = 0; o.n_ = 0; o.owned_ = true; }
     device_buffer &operator=(device_buffer &&o) noexcept
     {
-        if (this != &o) { release(); buf_ = o.buf_; n_ = o.n_; o.buf_ = 0; o.n_ = 0; }
+        if (this != &o) { release(); buf_ = o.buf_; n_ = o.n_; owned_ = o.owned_; o.buf_ = 0; o.n_ = 0; o.owned_ = true; }
         return *this;
     }
     ~device_buffer() { release(); }
-    void release() { if (buf_) { b200_free(context(), buf_); buf_ = 0; } }
+    void release() { if (buf_ && owned_) b200_free(context(), buf_); buf_ = 0; owned_ = true; }
+    bool owns() const { return owned_; }
     b200_buf get() const { return buf_; }
     std::size_t size() const { return n_; }
 

@@ -78,10 +78,10 @@ std::vector<FieldT> FFT_over_field_subset_cref(const std::vector<FieldT> &coeffs
 {
     if (coeffs.size() > domain.num_elements())
         throw std::invalid_argument("FFT_over_field_subset: more coefficients than domain elements");
-    device_buffer in(coeffs.size()), out(domain.num_elements());
-    in.upload_async(coeffs);
-    FFT_over_field_subset_device<FieldT>(in, coeffs.size(), domain, out);
-    return download_and_keep<FieldT>(std::move(out), domain.num_elements());   /* the codeword stays resident for its consumers */
+    const device_view in(coeffs);
+    device_buffer out(domain.num_elements());
+    FFT_over_field_subset_device<FieldT>(in.buf(), coeffs.size(), domain, out);
+    return make_lazy_vector<FieldT>(std::move(out), domain.num_elements());   /* the codeword stays on the device for its consumers */
 }
 template<typename FieldT, typename DomainT>
 std::vector<FieldT> FFT_over_field_subset(const std::vector<FieldT> coeffs, DomainT domain)
@@ -95,10 +95,10 @@ std::vector<FieldT> IFFT_over_field_subset_cref(const std::vector<FieldT> &evals
     if (n_evals != domain.num_elements() || n_evals > evals.size())
         throw std::invalid_argument("IFFT_over_field_subset: evaluation vector does not match the domain");
     if (n_evals == 1) return std::vector<FieldT>(evals.begin(), evals.begin() + 1);           /* fft.tcc:397-401 */
-    device_buffer in(n_evals), out(n_evals);
-    throw_status(context(), b200_upload(context(), in.get(), 0, reinterpret_cast<const uint64_t *>(evals.data()), n_evals));
-    IFFT_over_field_subset_device<FieldT>(in, domain, out);
-    return out.template download<FieldT>(n_evals);
+    const device_view in(evals.data(), n_evals);              /* a prefix of a device-resident codeword is used in place */
+    device_buffer out(n_evals);
+    IFFT_over_field_subset_device<FieldT>(in.buf(), domain, out);
+    return out.template download<FieldT>(n_evals);             /* coefficients are consumed by host polynomial code */
 }
 template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_over_field_subset(const std::vector<FieldT> evals, DomainT domain)
@@ -114,9 +114,17 @@ std::vector<FieldT> IFFT_of_known_degree_over_field_subset_cref(const std::vecto
     const DomainT minimal = domain.get_subset_of_order(closest_power_of_two);
     if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE)
         return IFFT_over_field_subset_cref<FieldT>(evals, minimal, closest_power_of_two);
+    const std::size_t freq = domain.num_elements() / closest_power_of_two;
+    if (const b200_buf resident = residency::instance().find(evals.data(), evals.size())) {
+        /* device-resident codeword: take every freq-th evaluation on the device */
+        device_buffer sub(closest_power_of_two), out(closest_power_of_two);
+        throw_status(context(), b200_copy_strided(context(), sub.get(), resident, 0, freq, closest_power_of_two));
+        if (closest_power_of_two == 1) return sub.template download<FieldT>(1);
+        IFFT_over_field_subset_device<FieldT>(sub, minimal, out);
+        return out.template download<FieldT>(closest_power_of_two);
+    }
     std::vector<FieldT> sub;
     sub.reserve(closest_power_of_two);
-    const std::size_t freq = domain.num_elements() / closest_power_of_two;
     for (std::size_t i = 0; i < domain.num_elements(); i += freq) sub.emplace_back(evals[i]);
     return IFFT_over_field_subset_cref<FieldT>(sub, minimal);
 }
@@ -134,9 +142,9 @@ device_buffer encode_rows_device(const FieldT *rows, std::size_t n_rows, const D
 {
     static_assert(field_traits<FieldT>::kind == B200_FIELD_GF192, "batched row encoding is implemented for additive domains");
     const std::size_t nH = H.num_elements(), nL = L.num_elements();
-    device_buffer in(n_rows * nH), coeffs(n_rows * nH), out(n_rows * nL);
+    device_buffer coeffs(n_rows * nH), out(n_rows * nL);
     if (n_rows == 0) return out;
-    throw_status(context(), b200_upload(context(), in.get(), 0, reinterpret_cast<const uint64_t *>(rows), n_rows * nH));
+    const device_view in(rows, n_rows * nH);
     std::vector<uint64_t> store_h, store_l;
     const b200_domain dh = make_domain<FieldT>(H, store_h), dl = make_domain<FieldT>(L, store_l);
     throw_status(context(), b200_gf192_ifft_batch(context(), &dh, in.get(), n_rows, coeffs.get()));
@@ -156,7 +164,7 @@ std::vector<std::vector<FieldT>> encode_rows(const FieldT *rows, std::size_t n_r
     for (std::size_t r = 0; r < n_rows; ++r) {
         device_buffer row(nL);
         throw_status(context(), b200_copy(context(), row.get(), 0, all.get(), r * nL, nL));
-        result.emplace_back(download_and_keep<FieldT>(std::move(row), nL));
+        result.emplace_back(make_lazy_vector<FieldT>(std::move(row), nL));
     }
     return result;
 }
@@ -184,7 +192,7 @@ std::shared_ptr<std::vector<FieldT>> evaluate_next_f_i_over_entire_domain(
     const device_view in(*f_i_evals);
     device_buffer out(n / coset_size);
     evaluate_next_f_i_over_entire_domain_device<FieldT>(in.buf(), f_i_domain, coset_size, x_i, out);
-    return std::make_shared<std::vector<FieldT>>(download_and_keep<FieldT>(std::move(out), n / coset_size));
+    return std::make_shared<std::vector<FieldT>>(make_lazy_vector<FieldT>(std::move(out), n / coset_size));
 }
 
 } // namespace libiop_b200

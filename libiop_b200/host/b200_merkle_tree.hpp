@@ -85,11 +85,11 @@ public:
         for (auto &v : leaf_contents)
             if (v->size() / coset_serialization_size != num_leaves_)
                 throw std::logic_error("Attempting to construct a Merkle tree with a constituent vector of wrong size");
-        std::vector<device_buffer> bufs;
+        std::vector<device_view> bufs;                    /* the resident copies of device-resident oracles, uploads of the others */
         std::vector<const device_buffer *> ptrs;
         bufs.reserve(leaf_contents.size());
-        for (auto &v : leaf_contents) { bufs.emplace_back(v->size()); bufs.back().upload(*v); }
-        for (auto &b : bufs) ptrs.push_back(&b);
+        for (auto &v : leaf_contents) bufs.emplace_back(*v);
+        for (auto &b : bufs) ptrs.push_back(&b.buf());
         construct_with_leaves_serialized_by_cosets_device(ptrs, leaf_contents[0]->size(), coset_serialization_size);
     }
     void construct(const std::vector<std::shared_ptr<std::vector<FieldT>>> &leaf_contents) /* merkle_tree.tcc:85-90 */

@@ -1,5 +1,5 @@
 /*
- * b200_pinned_arena.hpp — page-locked host arena for the prover's large vectors.
+ * b200_pinned_arena.hpp — host memory of the prover's large vectors: a page-locked arena and a region of LAZY blocks.
  *
  * Why: the reference hands every oracle around as std::vector<FieldT> (iop/oracles.hpp:21-52,
  * SURVEY.md §8b).  With pageable vectors a 192 MiB codeword costs ~50-100 ms per host<->device
@@ -16,6 +16,20 @@
  *
  * Environment: B200_PINNED_ARENA=0 disables the arena, B200_PINNED_SLAB_MB sets the slab size
  * (default 1024).  The arena is thread-safe (one mutex); slabs are never returned to the OS.
+ *
+ * Lazy blocks (device-resident oracles).  The reference keeps every oracle as a std::vector<FieldT>
+ * (iop/oracles.hpp:21-52) but reads only ~10^2 positions of it on the host (the query phase).  make_lazy_vector() (see
+ * b200_residency.hpp) therefore hands back a vector whose storage is address space only: a block of `lazy_region`, mapped
+ * PROT_NONE, while the contents live in the device buffer registered for it.  Adapter calls that receive the vector use
+ * the device buffer; the query phase gathers the queried positions; and ANY other host access — code the drop-in does not
+ * shadow, a by-value copy, an in-place update — faults, the SIGSEGV handler downloads the whole vector into the block,
+ * forgets the device copy and resumes the access.  A device copy is thus tied to the block by ownership (it exists exactly
+ * while the block is live and untouched by the host), not by comparing contents.  B200_LAZY=0 turns lazy blocks off
+ * (every result is downloaded), B200_LAZY_TRACE=1 prints a backtrace for every materialising fault.
+ *
+ * A shared library that expands B200_DEFINE_PINNED_OPERATOR_NEW must link its C++ runtime statically and keep the
+ * operators out of its dynamic symbol table (libiop_b200/dropin/Makefile does: -static-libstdc++, exports.map), so that
+ * every allocation and release made by code of the library goes through the same pair of functions.
  */
 #ifndef LIBIOP_B200_PINNED_ARENA_HPP_
 #define LIBIOP_B200_PINNED_ARENA_HPP_
@@ -28,6 +42,11 @@
 #include <mutex>
 #include <new>
 #include <vector>
+
+#include <execinfo.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 namespace libiop_b200 {
 
@@ -50,6 +69,14 @@ public:
         void *p = take(bytes);
         if (!p && grow(bytes)) p = take(bytes);
         return p;
+    }
+
+    /* size of the live block at p (0 if p is not the start of one) */
+    std::size_t block_bytes(const void *p)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = used_.find((uintptr_t)p);
+        return it == used_.end() ? 0 : it->second;
     }
 
     /* true if p belonged to the arena (and has been released) */
@@ -171,6 +198,130 @@ inline arena_release_hook_fn &arena_release_hook()
     return hook;
 }
 
+/* What the next operator new of exactly `bytes` bytes on this thread should return (set by make_lazy_vector around the one
+   allocation it makes; consumed by the replaced operator new). */
+struct alloc_hint { enum kind_t { none, lazy } kind; std::size_t bytes; };
+inline alloc_hint &current_alloc_hint()
+{
+    static thread_local alloc_hint h = {alloc_hint::none, 0};
+    return h;
+}
+
+/* Called with a faulting address inside the lazy region; returns true when the block was materialised and the access can
+   be retried.  One hook per process (the residency table installs it). */
+typedef bool (*lazy_fault_hook_fn)(void *);
+inline lazy_fault_hook_fn &lazy_fault_hook()
+{
+    static lazy_fault_hook_fn hook = nullptr;
+    return hook;
+}
+
+/* Address space for lazy blocks: reservations of PROT_NONE, MAP_NORESERVE memory cut into page-aligned blocks by the same
+   free-list allocator as the pinned slabs.  Pages exist only for blocks the host touched (see the file comment). */
+class lazy_region {
+public:
+    static lazy_region &instance() { static lazy_region *r = new lazy_region(); return *r; }   /* never destroyed */
+
+    bool enabled() const { return enabled_; }
+    bool contains(const void *p) const { return enabled_ && blocks_.owns((uintptr_t)p); }
+
+    void *allocate(std::size_t bytes)
+    {
+        if (!enabled_) return nullptr;
+        install_handler();
+        return blocks_.allocate(bytes);
+    }
+    /* give a block back; pages the host touched are returned to the kernel and the range is protected again */
+    void release(void *p)
+    {
+        const std::size_t len = blocks_.block_bytes(p);
+        if (len && is_touched(p)) {
+            madvise(p, len, MADV_DONTNEED);
+            mprotect(p, len, PROT_NONE);
+            set_touched(p, false);
+        }
+        blocks_.release(p);
+    }
+    /* make the block at p ordinary read-write memory (the caller fills it) */
+    bool open(void *p)
+    {
+        const std::size_t len = blocks_.block_bytes(p);
+        if (!len || mprotect(p, len, PROT_READ | PROT_WRITE) != 0) return false;
+        set_touched(p, true);
+        return true;
+    }
+    std::size_t reserved_bytes() const { return blocks_.reserved_bytes(); }
+    std::size_t faults() const { return faults_; }
+
+private:
+    static void *reserve(std::size_t bytes)
+    {
+        void *p = mmap(nullptr, bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        return p == MAP_FAILED ? nullptr : p;
+    }
+    lazy_region() : blocks_(&reserve, reservation_bytes())
+    {
+        const char *e = std::getenv("B200_LAZY");
+        enabled_ = !(e && e[0] == '0');
+        const char *t = std::getenv("B200_LAZY_TRACE");
+        trace_ = t && t[0] == '1';
+    }
+    static std::size_t reservation_bytes()
+    {
+        const char *g = std::getenv("B200_LAZY_RESERVE_GB");
+        return (std::size_t)(g ? std::strtoull(g, nullptr, 10) : 64) << 30;
+    }
+    bool is_touched(void *p) { std::lock_guard<std::mutex> l(mu_); return touched_.count((uintptr_t)p) != 0; }
+    void set_touched(void *p, bool v)
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        if (v) touched_[(uintptr_t)p] = true; else touched_.erase((uintptr_t)p);
+    }
+
+    static void on_fault(int sig, siginfo_t *si, void *uctx)
+    {
+        lazy_region &r = instance();
+        void *addr = si ? si->si_addr : nullptr;
+        if (addr && r.contains(addr) && lazy_fault_hook()) {
+            if (r.trace_) {
+                void *frames[32];
+                const int n = backtrace(frames, 32);
+                static const char msg[] = "[b200 lazy] host access materialises a device-resident vector:\n";
+                if (write(2, msg, sizeof msg - 1) < 0) {}
+                backtrace_symbols_fd(frames, n, 2);
+            }
+            if (lazy_fault_hook()(addr)) { ++r.faults_; return; }
+        }
+        /* not ours: hand the signal to whoever had it before (Python's faulthandler, a debugger, the default action) */
+        if (r.previous_.sa_flags & SA_SIGINFO) {
+            if (r.previous_.sa_sigaction) { r.previous_.sa_sigaction(sig, si, uctx); return; }
+        } else if (r.previous_.sa_handler != SIG_DFL && r.previous_.sa_handler != SIG_IGN) {
+            r.previous_.sa_handler(sig);
+            return;
+        }
+        signal(sig, SIG_DFL);          /* returning re-executes the access and takes the default action */
+    }
+    void install_handler()
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        if (handler_installed_) return;
+        struct sigaction sa;
+        std::memset(&sa, 0, sizeof sa);
+        sa.sa_sigaction = &lazy_region::on_fault;
+        sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+        sigemptyset(&sa.sa_mask);
+        sigaction(SIGSEGV, &sa, &previous_);
+        handler_installed_ = true;
+    }
+
+    pinned_arena blocks_;
+    bool enabled_ = true, trace_ = false, handler_installed_ = false;
+    std::mutex mu_;
+    std::map<uintptr_t, bool> touched_;
+    std::size_t faults_ = 0;
+    struct sigaction previous_;
+};
+
 /* std::vector<T> of n elements whose storage is NOT value-initialised (the caller overwrites all of it, e.g. by a
    device->host copy).  std::vector offers no such constructor; with libstdc++ / libc++ (three-pointer layout
    {begin, end, end_of_storage}) the end pointer is advanced over reserved storage.  Any other library takes the
@@ -219,6 +370,14 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
     inline void *alloc(std::size_t n)                                                                                    \
     {                                                                                                                    \
         static thread_local bool inside = false; /* context creation / cudaHostAlloc may allocate: do not recurse */    \
+        alloc_hint &hint = current_alloc_hint();                                                                         \
+        if (hint.kind == alloc_hint::lazy && hint.bytes == n && !inside) {                                               \
+            hint.kind = alloc_hint::none;                                                                                \
+            inside = true;                                                                                               \
+            void *p = lazy_region::instance().allocate(n);                                                               \
+            inside = false;                                                                                              \
+            if (p) return p;                                                                                             \
+        }                                                                                                                \
         if (n >= B200_PINNED_MIN_BYTES && !inside) {                                                                     \
             inside = true;                                                                                               \
             pinned_arena *a = arena();                                                                                   \
@@ -231,6 +390,11 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
     inline void dealloc(void *p) noexcept                                                                                \
     {                                                                                                                    \
         if (!p) return;                                                                                                  \
+        if (lazy_region::instance().contains(p)) {                                                                       \
+            if (arena_release_hook()) arena_release_hook()(p);                                                           \
+            lazy_region::instance().release(p);                                                                          \
+            return;                                                                                                      \
+        }                                                                                                                \
         pinned_arena *a = arena();                                                                                       \
         if (a && a->owns((uintptr_t)p)) {                                                                                \
             if (arena_release_hook()) arena_release_hook()(p);                                                           \

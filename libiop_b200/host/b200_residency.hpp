@@ -1,28 +1,32 @@
 /*
- * b200_residency.hpp — keeps device copies of the prover's large host vectors so they do not cross PCIe twice.
+ * b200_residency.hpp — device-resident oracles behind the reference's std::vector interfaces.
  *
  * The reference's IOP layer owns every oracle as a host std::vector<FieldT> (iop/oracles.hpp:21-52) and hands the same
  * vectors to the next stage: an LDE result goes to the Merkle tree, to two or three virtual oracles and to the FRI fold
- * (SURVEY.md §3.1).  The adapter still returns host vectors (the reference's query phase reads them element-wise,
- * iop.tcc:670-688), but whenever it produces one from a device buffer it parks that buffer here, keyed by the vector's
- * data pointer; when a later call receives the same vector it finds the device copy and skips the upload.
- *
- * Safety: a hit requires the same address AND length AND an equal sample of 32 elements (first, last, evenly strided)
- * read from the host vector at lookup time, so an allocation recycled for different contents is never mistaken for
- * the vector that was registered.  Only codeword-domain evaluation vectors are registered (immutable once submitted,
- * iop.tcc:272-307).  When the process uses the pinned arena (b200_pinned_arena.hpp) the cache is told the moment a
- * host block is released and drops the entry, so device memory follows the lifetime of the host vectors.
- * B200_RESIDENCY_VERIFY=1 additionally compares the complete contents on every hit (debug / tests),
- * B200_RESIDENCY=0 disables the cache.  The cache is LRU with a byte budget (B200_RESIDENT_GB, default 24).
+ * (SURVEY.md §3.1); the host itself reads ~10^2 positions of each (the query phase, iop.tcc:670-688).  When the adapter
+ * produces such a vector it therefore does NOT download it: make_lazy_vector() returns a vector whose storage is a block
+ * of the lazy region (b200_pinned_arena.hpp: address space only, PROT_NONE) and registers the device buffer that holds
+ * the contents under the block's address.
+ *   - An adapter call that receives the vector (device_view) finds the buffer and uses it: no PCIe traffic.
+ *   - The query phase reads single positions through resident_element() / prefetch_elements(): one gather per oracle.
+ *   - Any OTHER host access faults; the handler downloads the whole vector into the block, drops the registration (the
+ *     host may now change the data) and the access resumes.  Code the drop-in does not know about stays correct.
+ *   - operator delete of the block drops the registration, so the buffer lives exactly as long as the vector.
+ * A registration is thus valid by construction — it exists only while the block is live and has never been visible to
+ * the host — and no contents are compared.  Without the replaced operator new (or with B200_LAZY=0) make_lazy_vector()
+ * simply downloads.  The table is guarded by a mutex; the context and its stream remain single-threaded
+ * (SURVEY.md §8b "Threading").
  */
 #ifndef LIBIOP_B200_RESIDENCY_HPP_
 #define LIBIOP_B200_RESIDENCY_HPP_
 
+#include <array>
 #include <cstdlib>
 #include <cstring>
-#include <list>
-#include <unordered_map>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "b200_device.hpp"
@@ -30,111 +34,221 @@
 namespace libiop_b200 {
 
 class residency {
-    struct entry { const void *host; std::size_t n; unsigned char sample[32 * 24]; std::size_t sample_bytes; device_buffer buf; };
-    std::list<entry> lru_;                       /* front = most recent */
-    std::unordered_map<const void *, std::list<entry>::iterator> by_host_;   /* one entry per host address */
-    std::size_t bytes_ = 0, budget_, hits_ = 0, misses_ = 0, stale_ = 0;
-    bool enabled_, verify_;
+    struct entry {
+        std::size_t n;                                        /* elements */
+        device_buffer buf;
+        std::unordered_map<std::size_t, std::array<uint64_t, 3>> fetched;   /* positions already read by the query phase */
+    };
+    std::map<uintptr_t, entry> blocks_;                       /* by block address, ordered: lookups by contained address */
+    std::mutex mu_;
+    std::size_t bytes_ = 0, hits_ = 0, misses_ = 0, faults_ = 0, fault_bytes_ = 0, gathers_ = 0;
+    std::size_t generation_ = 0;                              /* bumped by every registration */
+    const void *bulk_owner_ = nullptr;                        /* last object that ran a bulk fetch, and when */
+    std::size_t bulk_generation_ = ~std::size_t(0);
 
-    static std::size_t take_sample(const void *host, std::size_t n, unsigned char *out)
-    {
-        const unsigned char *p = static_cast<const unsigned char *>(host);
-        const std::size_t k = n < 32 ? n : 32;
-        for (std::size_t i = 0; i < k; ++i) std::memcpy(out + 24 * i, p + 24 * ((k > 1) ? (i * (n - 1)) / (k - 1) : 0), 24);
-        return 24 * k;
-    }
     residency()
     {
-        const char *e = std::getenv("B200_RESIDENCY");
-        enabled_ = !(e && e[0] == '0');
-        const char *v = std::getenv("B200_RESIDENCY_VERIFY");
-        verify_ = v && v[0] == '1';
-        const char *g = std::getenv("B200_RESIDENT_GB");
-        budget_ = (std::size_t)(g ? std::strtoull(g, nullptr, 10) : 24) << 30;
         arena_release_hook() = &residency::host_block_released;
+        lazy_fault_hook() = &residency::host_block_touched;
     }
-    /* the pinned arena is about to recycle this host block: its device copy is dead weight from now on */
     static void host_block_released(void *p) { instance().drop(p); }
+    static bool host_block_touched(void *addr) { return instance().materialise(addr); }
+
+    /* entry whose block contains [a, a + bytes) */
+    std::map<uintptr_t, entry>::iterator containing(uintptr_t a, std::size_t bytes)
+    {
+        auto it = blocks_.upper_bound(a);
+        if (it == blocks_.begin()) return blocks_.end();
+        --it;
+        if (a >= it->first && a + bytes <= it->first + it->second.n * 24) return it;
+        return blocks_.end();
+    }
+
 public:
     static residency &instance() { static residency *r = new residency(); return *r; }   /* never destroyed: outlives every vector */
+    static constexpr std::size_t min_elems = 4096;            /* smaller results are simply downloaded */
+
+    /* `buf` (n elements) holds the contents of the lazy block at `host` */
+    void put(void *host, std::size_t n, device_buffer &&buf)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        entry &e = blocks_[(uintptr_t)host];
+        e.n = n; e.buf = std::move(buf); e.fetched.clear();
+        bytes_ += n * 24;
+        ++generation_;
+    }
+
+    /* the block died (operator delete) */
     void drop(const void *host)
     {
-        auto found = by_host_.find(host);
-        if (found == by_host_.end()) return;
-        bytes_ -= found->second->n * 24;
-        lru_.erase(found->second);
-        by_host_.erase(found);
-    }
-    static constexpr std::size_t min_elems = 4096;
-
-    /* park `buf` (n elements) as the device copy of the host array at `host` */
-    void put(const void *host, std::size_t n, device_buffer &&buf)
-    {
-        if (!enabled_ || n < min_elems) return;
-        drop(host);                                               /* one entry per address */
-        lru_.emplace_front();
-        entry &e = lru_.front();
-        e.host = host; e.n = n; e.buf = std::move(buf);
-        e.sample_bytes = take_sample(host, n, e.sample);
-        by_host_[host] = lru_.begin();
-        bytes_ += n * 24;
-        while (bytes_ > budget_ && lru_.size() > 1) drop(lru_.back().host);
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end()) return;
+        bytes_ -= it->second.n * 24;
+        blocks_.erase(it);
     }
 
-    /* device copy of the n-element host array at `host`, or nullptr */
-    const device_buffer *find(const void *host, std::size_t n)
+    /* device address of the n elements at `host` if they lie in a registered block; 0 otherwise */
+    b200_buf find(const void *host, std::size_t n)
     {
-        if (!enabled_ || n < min_elems) return nullptr;
-        auto found = by_host_.find(host);
-        if (found != by_host_.end()) {
-            auto it = found->second;
-            unsigned char now[32 * 24];
-            const std::size_t nb = take_sample(host, n, now);
-            if (it->n != n || nb != it->sample_bytes || std::memcmp(now, it->sample, nb) != 0) {
-                drop(host); ++stale_; ++misses_;
-                return nullptr;
-            }
-            if (verify_) {
-                std::vector<unsigned char> dev(n * 24);
-                throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(dev.data()), it->buf.get(), 0, n));
-                if (std::memcmp(dev.data(), host, n * 24) != 0)
-                    throw std::logic_error("libiop_b200::residency: device copy differs from the host vector (B200_RESIDENCY_VERIFY)");
-            }
-            lru_.splice(lru_.begin(), lru_, it);
-            ++hits_;
-            return &lru_.front().buf;
+        if (n == 0) return 0;
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = containing((uintptr_t)host, n * 24);
+        if (it == blocks_.end()) { ++misses_; return 0; }
+        const std::size_t off = (uintptr_t)host - it->first;
+        if (off % 24) { ++misses_; return 0; }
+        ++hits_;
+        return it->second.buf.get() + off;
+    }
+    bool is_resident(const void *host) { std::lock_guard<std::mutex> lock(mu_); return containing((uintptr_t)host, 1) != blocks_.end(); }
+
+    /* the host touched a lazy block: bring the contents over, the block is an ordinary host vector from now on */
+    bool materialise(void *addr)
+    {
+        std::unique_lock<std::mutex> lock(mu_);
+        auto it = containing((uintptr_t)addr, 1);
+        if (it == blocks_.end()) return false;
+        void *base = (void *)it->first;
+        const std::size_t n = it->second.n;
+        device_buffer buf = std::move(it->second.buf);
+        bytes_ -= n * 24;
+        blocks_.erase(it);
+        ++faults_; fault_bytes_ += n * 24;
+        lock.unlock();
+        if (!lazy_region::instance().open(base)) return false;
+        return b200_download(context(), reinterpret_cast<uint64_t *>(base), buf.get(), 0, n) == B200_OK;
+    }
+
+    /* Query phase: element `position` of the vector at `host` (iop.tcc:687 reads evaluated_contents()[position]).
+       Returns false if the vector is not device-resident (the caller then reads the host memory). */
+    bool element(const void *host, std::size_t position, uint64_t out[3])
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end() || position >= it->second.n) return false;
+        auto f = it->second.fetched.find(position);
+        if (f == it->second.fetched.end()) {
+            std::array<uint64_t, 3> v;
+            throw_status(context(), b200_gather(context(), v.data(), it->second.buf.get(), &position, 1));
+            ++gathers_;
+            f = it->second.fetched.emplace(position, v).first;
         }
-        ++misses_;
-        return nullptr;
+        std::memcpy(out, f->second.data(), 24);
+        return true;
     }
-    void clear() { lru_.clear(); by_host_.clear(); bytes_ = 0; }
+    /* true when `position` of the vector at `host` would need a gather (resident and not fetched yet) */
+    bool needs_fetch(const void *host, std::size_t position)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        return it != blocks_.end() && position < it->second.n && !it->second.fetched.count(position);
+    }
+    /* A reader that is about to fetch its whole query set asks first: true once per (reader, state of the table), so a
+       position the bulk fetch did not cover costs one single gather, not another walk over all queries. */
+    bool begin_bulk_fetch(const void *owner)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (bulk_owner_ == owner && bulk_generation_ == generation_) return false;
+        bulk_owner_ = owner; bulk_generation_ = generation_;
+        return true;
+    }
+    /* fetch many positions of one vector with a single gather (no-op for vectors that are not resident) */
+    void prefetch(const void *host, const std::vector<std::size_t> &positions)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end()) return;
+        std::vector<std::size_t> want;
+        for (std::size_t p : positions)
+            if (p < it->second.n && !it->second.fetched.count(p)) want.push_back(p);
+        if (want.empty()) return;
+        std::vector<uint64_t> vals(3 * want.size());
+        throw_status(context(), b200_gather(context(), vals.data(), it->second.buf.get(), want.data(), want.size()));
+        ++gathers_;
+        for (std::size_t i = 0; i < want.size(); ++i) {
+            std::array<uint64_t, 3> v = {vals[3 * i], vals[3 * i + 1], vals[3 * i + 2]};
+            it->second.fetched.emplace(want[i], v);
+        }
+    }
+
     std::size_t hits() const { return hits_; }
     std::size_t misses() const { return misses_; }
-    std::size_t stale() const { return stale_; }
+    std::size_t faults() const { return faults_; }
+    std::size_t fault_bytes() const { return fault_bytes_; }
+    std::size_t gathers() const { return gathers_; }
     std::size_t resident_bytes() const { return bytes_; }
 };
 
-/* a device view of a host vector: the resident copy if there is one, otherwise a fresh (asynchronous) upload */
+/* a device view of host elements: the resident copy if there is one, otherwise a fresh (asynchronous) upload; the host
+   data must stay alive and unmodified until the next synchronising call on the context */
 class device_view {
-    const device_buffer *resident_ = nullptr;
-    device_buffer owned_;
+    device_buffer owned_;      /* an upload, or a non-owning alias of the resident buffer */
+    bool uploaded_ = false;
 public:
-    template<typename FieldT> explicit device_view(const std::vector<FieldT> &v)
+    device_view(const void *host, std::size_t n)
     {
-        resident_ = residency::instance().find(v.data(), v.size());
-        if (!resident_) { owned_ = device_buffer(v.size()); owned_.upload_async(v); }
+        const b200_buf resident = residency::instance().find(host, n);
+        if (resident) { owned_ = device_buffer::alias(resident, n); return; }
+        owned_ = device_buffer(n);
+        if (n) { throw_status(context(), b200_upload(context(), owned_.get(), 0, reinterpret_cast<const uint64_t *>(host), n)); uploaded_ = true; }
     }
-    const device_buffer &buf() const { return resident_ ? *resident_ : owned_; }
-    b200_buf get() const { return buf().get(); }
+    device_view(device_view &&o) noexcept : owned_(std::move(o.owned_)), uploaded_(o.uploaded_) { o.uploaded_ = false; }
+    device_view(const device_view &) = delete;
+    device_view &operator=(const device_view &) = delete;
+    /* the host data may be released by the caller once the view is gone: wait for the copy (not for the kernels behind it) */
+    ~device_view() { if (uploaded_) b200_wait_uploads(context()); }
+    template<typename FieldT> explicit device_view(const std::vector<FieldT> &v) : device_view(v.data(), v.size())
+    {
+        static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    }
+    const device_buffer &buf() const { return owned_; }
+    b200_buf get() const { return owned_.get(); }
 };
 
-/* download `buf` into a fresh host vector and park the buffer as its device copy */
+/* The host-side face of a device buffer: a vector of n elements that costs no transfer until the host reads it (see the
+   file comment).  Falls back to a plain download when lazy blocks are unavailable or the result is small. */
 template<typename FieldT>
-std::vector<FieldT> download_and_keep(device_buffer &&buf, std::size_t n)
+std::vector<FieldT> make_lazy_vector(device_buffer &&buf, std::size_t n)
 {
-    std::vector<FieldT> v = buf.template download<FieldT>(n);
-    residency::instance().put(v.data(), n, std::move(buf));
-    return v;
+    static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    if (n >= residency::min_elems && lazy_region::instance().enabled()) {
+        alloc_hint &hint = current_alloc_hint();
+        hint.kind = alloc_hint::lazy; hint.bytes = n * sizeof(FieldT);
+        std::vector<FieldT> v = make_uninitialized_vector<FieldT>(n);
+        hint.kind = alloc_hint::none;
+        if (v.size() == n && lazy_region::instance().contains(v.data())) {
+            residency::instance().put(v.data(), n, std::move(buf));
+            return v;
+        }
+        /* the hint was not honoured (operator new is not replaced in this binary, or the reservation failed) */
+        if (n) throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(v.data()), buf.get(), 0, n));
+        return v;
+    }
+    return buf.template download<FieldT>(n);
+}
+/* historical name */
+template<typename FieldT>
+std::vector<FieldT> download_and_keep(device_buffer &&buf, std::size_t n) { return make_lazy_vector<FieldT>(std::move(buf), n); }
+
+/* a copy of `src` that stays on the device when `src` does (the reference deep-copies oracles in a few places, e.g.
+   oracle(const shared_ptr&), iop/oracles.hpp:36-38; bcs_indexer.tcc:48-53) */
+template<typename FieldT>
+std::vector<FieldT> clone_vector(const std::vector<FieldT> &src)
+{
+    const b200_buf resident = residency::instance().find(src.data(), src.size());
+    if (!resident) return std::vector<FieldT>(src);
+    device_buffer copy(src.size());
+    throw_status(context(), b200_copy(context(), copy.get(), 0, resident, 0, src.size()));
+    return make_lazy_vector<FieldT>(std::move(copy), src.size());
+}
+
+/* element `position` of `v`, without materialising a device-resident vector */
+template<typename FieldT>
+FieldT resident_element(const std::vector<FieldT> &v, std::size_t position)
+{
+    FieldT out;
+    if (residency::instance().element(v.data(), position, reinterpret_cast<uint64_t *>(&out))) return out;
+    return v[position];
 }
 
 /* RAII owner of a device byte array (Merkle nodes that stay on the device: a tree of 2^23 nodes is 256 MiB of which

@@ -75,7 +75,13 @@ class DropinProver:
     def residency_stats(self):
         h, m, s, r = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.lib.b200_prover_residency_stats(C.byref(h), C.byref(m), C.byref(s), C.byref(r))
-        return {"hits": h.value, "misses": m.value, "stale": s.value, "resident_bytes": r.value}
+        return {"hits": h.value, "misses": m.value, "host_touched": s.value, "resident_bytes": r.value}
+
+    def lazy_stats(self):
+        """device-resident oracles: host touches that forced a whole-vector download, and query-phase gathers"""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.b200_prover_lazy_stats(C.byref(a), C.byref(b), C.byref(c))
+        return {"faults": a.value, "fault_bytes": b.value, "gathers": c.value}
 
     def device_stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -131,6 +131,9 @@ int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t off, s
 { c->d2h += n; std::memcpy(dst, (const uint8_t *)(uintptr_t)src + off, n); return 0; }
 int b200_copy(b200_ctx *, b200_buf dst, size_t doff, b200_buf src, size_t soff, size_t n)
 { std::memmove(E(dst) + doff, E(src) + soff, n * 24); return 0; }
+int b200_wait_uploads(b200_ctx *) { return 0; }
+int b200_copy_strided(b200_ctx *, b200_buf dst, b200_buf src, size_t soff, size_t stride, size_t n)
+{ for (size_t i = 0; i < n; ++i) E(dst)[i] = E(src)[soff + i * stride]; return 0; }
 int b200_fill_zero(b200_ctx *, b200_buf dst, size_t off, size_t n) { std::memset(E(dst) + off, 0, n * 24); return 0; }
 int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, size_t k)
 {
