@@ -21,13 +21,14 @@ namespace b200_glue {
 template<typename FieldT>
 std::vector<FieldT> inverse_and_mul(const std::vector<FieldT> &vec, const FieldT &k, const bool has_zeroes, std::true_type)
 {
-    if (vec.size() < 16384) return ref_cpu_batch_inverse_and_mul<FieldT>(vec, k, has_zeroes);
     using namespace libiop_b200;
+    /* short host vectors stay on the host; a device-resident vector is inverted where it is, whatever its length */
+    if (vec.size() < 16384 && !residency::instance().is_resident(vec.data())) return ref_cpu_batch_inverse_and_mul<FieldT>(vec, k, has_zeroes);
     const device_view in(vec);
     device_buffer out(vec.size());
     vec_inverse<FieldT>(out, in.buf(), vec.size());
     if (k != FieldT::one()) vec_affine<FieldT>(out, out, &k, nullptr, vec.size());
-    return download_and_keep<FieldT>(std::move(out), vec.size());
+    return make_lazy_vector<FieldT>(std::move(out), vec.size());
 }
 template<typename FieldT>
 std::vector<FieldT> inverse_and_mul(const std::vector<FieldT> &vec, const FieldT &k, const bool has_zeroes, std::false_type)

@@ -6,6 +6,19 @@
 #include B200_REF_FILE(libiop/protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc)
 
 namespace libiop {
+/* create_fw_prime_evals (r1cs_rs_iop.tcc:423-446) reads f_{1,v} over the whole variable domain element by element; that
+   vector is an FFT result, i.e. device-resident.  These overloads (preferred over the reference's template for the served
+   fields) hand the reference's loop a host copy fetched with one transfer. */
+#define B200_FW_PRIME_OVERLOAD(FIELD)                                                                                      \
+inline std::vector<FIELD> create_fw_prime_evals(const std::vector<FIELD> &f_1v_over_variable_domain, const std::size_t primary_input_size, \
+                                                const r1cs_auxiliary_input<FIELD> &auxiliary_input, const field_subset<FIELD> &variable_domain) \
+{                                                                                                                          \
+    const libiop_b200::host_readable<FIELD> f_1v(f_1v_over_variable_domain);                                               \
+    return create_fw_prime_evals<FIELD>(f_1v.get(), primary_input_size, auxiliary_input, variable_domain);                 \
+}
+B200_FOR_EACH_FIELD(B200_FW_PRIME_OVERLOAD)
+#undef B200_FW_PRIME_OVERLOAD
+
 #define B200_FZ_SPECIALISE(FIELD)                                                                                          \
 template<> inline std::shared_ptr<std::vector<FIELD>> fz_virtual_oracle<FIELD>::evaluated_contents(                        \
     const std::vector<std::shared_ptr<std::vector<FIELD>>> &constituent_oracle_evaluations) const                          \

@@ -242,6 +242,24 @@ std::vector<FieldT> clone_vector(const std::vector<FieldT> &src)
     return make_lazy_vector<FieldT>(std::move(copy), src.size());
 }
 
+/* `v` in a form host code may read: `v` itself, or — for a device-resident vector — a downloaded copy in page-locked
+   memory (a plain transfer at PCIe rate; reading `v` directly would fault and take the slow whole-vector path) */
+template<typename FieldT>
+class host_readable {
+    const std::vector<FieldT> *ref_;
+    std::vector<FieldT> copy_;
+public:
+    explicit host_readable(const std::vector<FieldT> &v) : ref_(&v)
+    {
+        const b200_buf resident = residency::instance().find(v.data(), v.size());
+        if (!resident) return;
+        copy_ = make_uninitialized_vector<FieldT>(v.size());
+        throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(copy_.data()), resident, 0, v.size()));
+        ref_ = &copy_;
+    }
+    const std::vector<FieldT> &get() const { return *ref_; }
+};
+
 /* element `position` of `v`, without materialising a device-resident vector */
 template<typename FieldT>
 FieldT resident_element(const std::vector<FieldT> &v, std::size_t position)
