@@ -18,7 +18,7 @@ if which == "gpu":
     run(log_n, verify=False)
     a = r.arena_stats(); s = r.residency_stats()
     print(f"pinned arena: {a['slabs']} slabs, {a['reserved_bytes'] / 2**30:.2f} GiB reserved, {a['free_bytes'] / 2**30:.2f} GiB free; "
-          f"residency: {s['hits']} hits, {s['misses']} misses, {s['stale']} stale, {s['resident_bytes'] / 2**30:.2f} GiB resident", flush=True)
+          f"residency: {s['hits']} hits, {s['misses']} misses, {s['host_touched']} host-touched, {s['resident_bytes'] / 2**30:.2f} GiB resident", flush=True)
 else:
     from oracle_lib import Reference
     os.environ["B200_REF_PROFILE"] = "1"

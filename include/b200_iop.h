@@ -89,9 +89,10 @@ int b200_download_bytes(b200_ctx *, uint8_t *dst, b200_bytes src, size_t offset,
  * running): the point after which the caller may release or rewrite its host vectors */
 int b200_wait_uploads(b200_ctx *);
 int b200_copy(b200_ctx *, b200_buf dst, size_t dst_offset, b200_buf src, size_t src_offset, size_t n_elems);
-/* dst[i] = src[src_offset + i * stride], i < n_elems: the evaluations over a sub-coset of a multiplicative domain
- * (IFFT_of_known_degree_over_field_subset, libiop/algebra/fft.tcc:446-455) taken from a device-resident codeword */
-int b200_copy_strided(b200_ctx *, b200_buf dst, b200_buf src, size_t src_offset, size_t stride, size_t n_elems);
+/* dst[i * dst_stride] = src[src_offset + i * src_stride], i < n_elems: the evaluations over a sub-coset of a multiplicative
+ * domain (IFFT_of_known_degree_over_field_subset, libiop/algebra/fft.tcc:446-455) taken from a device-resident codeword, and
+ * the placement of a sub-coset's values inside the larger coset (field_subset::reindex_by_subset, subgroup.tcc:150-173) */
+int b200_copy_strided(b200_ctx *, b200_buf dst, size_t dst_stride, b200_buf src, size_t src_offset, size_t src_stride, size_t n_elems);
 int b200_fill_zero(b200_ctx *, b200_buf dst, size_t dst_offset, size_t n_elems);
 /* iop_protocol::get_oracle_evaluation_at_point (libiop/iop/iop.tcc:670-688): query answers */
 int b200_gather(b200_ctx *, uint64_t *dst, b200_buf src, const size_t *idx, size_t k);
@@ -193,6 +194,14 @@ int b200_poly_eval(b200_ctx *, int field, const b200_fp_params *fp, b200_buf coe
  * row_ptr (n_rows+1), col (nnz), coeff (nnz*3 limbs) are host arrays; x (n_x elements) and y_out (n_rows) device buffers. */
 int b200_spmv_csr(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows, const uint64_t *row_ptr, const uint32_t *col,
                   const uint64_t *coeff, b200_buf x, size_t n_x, b200_buf y_out);
+
+/* GF(2^192) scatter-accumulate over a list of matrix entries: y[dst[k]] += scale * coeff[k] * x[src[k]], k < nnz.
+ * multi_lincheck_virtual_oracle::set_challenge's p_alpha_ABC (protocols/encoded/lincheck/basic_lincheck_aux.tcc:63-84): the
+ * transposed product (sum_m r_m M_m)^T (1, alpha, alpha^2, ...) — one call per matrix with scale = r_m, x = the powers of alpha,
+ * dst = the column's position in the summation domain, src = the row.  dst, src (nnz) and coeff (nnz*3 limbs) are host arrays;
+ * y (n_y elements, accumulated into) and x (n_x) are device buffers.  Additions are XOR, so entries may hit one y[.] in any order. */
+int b200_gf192_scatter_mul_add(b200_ctx *, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
+                               const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3]);
 
 /* polynomial_over_vanishing_polynomial (algebra/polynomials/vanishing_polynomial.tcc:312-371,
  * linearized_polynomial.tcc:238-291): P = Q*Z + R for the sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j]

@@ -14,12 +14,13 @@ void plans_clear(b200_ctx *c) { c->additive_plans.clear(); c->ntt_plans.clear();
 
 using namespace b200;
 
-/* dst[i] = src[i * stride] over 24-byte elements (one thread per element, three u64 words) */
-__global__ void copy_strided_kernel(uint64_t *dst, const uint64_t *src, size_t stride, size_t n)
+/* dst[i * dst_stride] = src[i * src_stride] over 24-byte elements (one thread per element, three u64 words) */
+__global__ void copy_strided_kernel(uint64_t *dst, size_t dst_stride, const uint64_t *src, size_t src_stride, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint64_t *q = src + 3 * i * stride;
-        dst[3 * i] = q[0]; dst[3 * i + 1] = q[1]; dst[3 * i + 2] = q[2];
+        const uint64_t *q = src + 3 * i * src_stride;
+        uint64_t *d = dst + 3 * i * dst_stride;
+        d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
     }
 }
 
@@ -189,11 +190,12 @@ int b200_copy(b200_ctx *c, b200_buf dst, size_t dst_offset, b200_buf src, size_t
                                  n_elems * 24, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
-int b200_copy_strided(b200_ctx *c, b200_buf dst, b200_buf src, size_t src_offset, size_t stride, size_t n_elems)
+int b200_copy_strided(b200_ctx *c, b200_buf dst, size_t dst_stride, b200_buf src, size_t src_offset, size_t src_stride, size_t n_elems)
 {
     if (!n_elems) return 0;
     const unsigned grid = (unsigned)((n_elems + 255) / 256 < 148 * 8 ? (n_elems + 255) / 256 : 148 * 8);
-    copy_strided_kernel<<<grid, 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst, (const uint64_t *)(uintptr_t)src + 3 * src_offset, stride, n_elems);
+    copy_strided_kernel<<<grid, 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst, dst_stride, (const uint64_t *)(uintptr_t)src + 3 * src_offset,
+                                                     src_stride, n_elems);
     B200_LAUNCH_CHECK(c);
     return 0;
 }

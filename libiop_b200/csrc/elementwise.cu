@@ -378,6 +378,23 @@ spmv_csr_kernel(typename F::T *y, const uint64_t *row_ptr, const uint32_t *col, 
     }
 }
 
+/* ---- 9. GF(2^192) scatter-accumulate over matrix entries: y[dst[k]] ^= scale * coeff[k] * x[src[k]] ------------------------
+   multi_lincheck's p_alpha_ABC (basic_lincheck_aux.tcc:63-84): addition is XOR, so colliding destinations are resolved with
+   three 64-bit atomic XORs and the result does not depend on the order of the entries. */
+__global__ void __launch_bounds__(256)
+scatter_mul_add_gf192_kernel(gf192 *y, const uint32_t *dst, const uint32_t *src, const gf192 *coeff, const gf192 *x, const gf192 scale,
+                             size_t nnz)
+{
+    const gf192_prepared sp = gf_prepare(scale);
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nnz; k += (size_t)gridDim.x * blockDim.x) {
+        const gf192 v = gf_mul(gf_mul(ld_el(coeff, k), sp), ld_el(x, src[k]));
+        unsigned long long *q = reinterpret_cast<unsigned long long *>(y + dst[k]);
+        atomicXor(q, (unsigned long long)v.w[0] | ((unsigned long long)v.w[1] << 32));
+        atomicXor(q + 1, (unsigned long long)v.w[2] | ((unsigned long long)v.w[3] << 32));
+        atomicXor(q + 2, (unsigned long long)v.w[4] | ((unsigned long long)v.w[5] << 32));
+    }
+}
+
 static bool field_ok(b200_ctx *c, int field, const b200_fp_params *fp)
 {
     if (field == B200_FIELD_GF192) return true;
@@ -577,6 +594,29 @@ int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_row
     return 0;
 }
 
+int b200_gf192_scatter_mul_add(b200_ctx *c, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
+                               const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3])
+{
+    B200_TRACE_SCOPE(c, "scatter_mul_add", nnz);
+    if (!nnz) return 0;
+    for (size_t k = 0; k < nnz; ++k)
+        if (dst[k] >= n_y || src[k] >= n_x)
+            return set_err(c, B200_ERR_INVALID, "scatter: entry %zu (%u <- %u) outside the vectors (%zu, %zu)", k, dst[k], src[k], n_y, n_x);
+    /* the entry list goes up with the call: coeff | dst | src */
+    const size_t b_cf = nnz * 24, b_ix = nnz * sizeof(uint32_t);
+    char *dev = (char *)scratch_get(c, 2, b_cf + 2 * b_ix + 64);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate %zu bytes for the entry list", b_cf + 2 * b_ix);
+    B200_CUDA(c, cudaMemcpyAsync(dev, coeff, b_cf, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaMemcpyAsync(dev + b_cf, dst, b_ix, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaMemcpyAsync(dev + b_cf + b_ix, src, b_ix, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += b_cf + 2 * b_ix;
+    scatter_mul_add_gf192_kernel<<<ew_grid(c, nnz, 256), 256, 0, c->stream>>>((gf192 *)y, (const uint32_t *)(dev + b_cf),
+                                                                             (const uint32_t *)(dev + b_cf + b_ix), (const gf192 *)dev,
+                                                                             (const gf192 *)x, host_el<gf192>(scale), nnz);
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));      /* the host arrays may be released by the caller */
+    return 0;
+}
 int b200_poly_divide_sparse(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf p, size_t n_p, size_t deg,
                             const uint64_t lead_inv[3], size_t n_terms, const uint64_t *coefs, const size_t *pows,
                             b200_buf q_out, b200_buf r_out)

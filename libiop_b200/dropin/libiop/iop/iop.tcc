@@ -13,9 +13,43 @@
 #include "libiop_b200/host/b200_residency.hpp"
 #include B200_REF_FILE(libiop/iop/iop.tcc)
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <set>
 
 namespace libiop {
+namespace b200_glue {
+/* What the query phase of ONE prover object reads from its device-resident oracles: per oracle the sorted positions and
+   their values, fetched with one gather each (see the file comment).  A read is then an index into `columns` and a search in
+   a short sorted array; get_transcript asks for ascending positions per oracle, which the `next` hint makes O(1). */
+template<typename FieldT>
+struct query_columns {
+    struct column { std::vector<std::size_t> positions; std::vector<FieldT> values; std::size_t next = 0; bool resident = false; };
+    const void *owner = nullptr;
+    std::size_t generation = ~std::size_t(0);
+    std::vector<column> columns;                 /* by oracle id */
+
+    bool lookup(std::size_t oracle_id, std::size_t position, FieldT &value)
+    {
+        if (oracle_id >= columns.size()) return false;
+        column &c = columns[oracle_id];
+        if (!c.resident) return false;
+        if (c.next < c.positions.size() && c.positions[c.next] == position) { value = c.values[c.next++]; return true; }
+        const auto it = std::lower_bound(c.positions.begin(), c.positions.end(), position);
+        if (it == c.positions.end() || *it != position) return false;
+        c.next = (std::size_t)(it - c.positions.begin());
+        value = c.values[c.next++];
+        return true;
+    }
+};
+template<typename FieldT> query_columns<FieldT> &query_cache()
+{
+    static thread_local query_columns<FieldT> cache;
+    return cache;
+}
+}
+
 #define B200_IOP_SPECIALISE(FIELD)                                                                                         \
 template<> inline FIELD iop_protocol<FIELD>::get_oracle_evaluation_at_point(                                              \
     const oracle_handle_ptr &handle, const std::size_t evaluation_position, const bool record)                             \
@@ -25,36 +59,67 @@ template<> inline FIELD iop_protocol<FIELD>::get_oracle_evaluation_at_point(    
         if (this->domains_[this->oracle_registrations_[id].domain().id()].num_elements() <= evaluation_position)          \
             throw std::invalid_argument("evaluation position is outside of domain");                                       \
         if (record) this->oracle_id_to_query_positions_[id].insert(evaluation_position);   /* iop.tcc:681-685 */           \
-        const std::shared_ptr<std::vector<FIELD>> contents = this->oracles_[id].evaluated_contents();                      \
+        const std::vector<FIELD> &contents = *this->oracles_[id].evaluated_contents();                                     \
+        if (!libiop_b200::lazy_region::instance().contains(contents.data()))                                               \
+            return contents[evaluation_position];                  /* an ordinary host vector: the reference's read */     \
         libiop_b200::residency &res = libiop_b200::residency::instance();                                                  \
+        b200_glue::query_columns<FIELD> &cache = b200_glue::query_cache<FIELD>();                                          \
+        FIELD value;                                                                                                       \
+        if (cache.owner == this && cache.generation == res.generation() && cache.lookup(id, evaluation_position, value))   \
+            return value;                                                                                                  \
         if (this->num_prover_rounds_done_ == this->num_interaction_rounds_ &&                                              \
-            res.needs_fetch(contents->data(), evaluation_position) && res.begin_bulk_fetch(this)) {                        \
-            std::map<std::size_t, std::set<std::size_t>> wanted;          /* oracle id -> positions */                       \
+            !(cache.owner == this && cache.generation == res.generation())) {                                              \
+            /* first read of this prover's query phase: fetch everything the registered queries will touch */              \
+            const auto b200_t0 = std::chrono::steady_clock::now();                                                        \
+            std::vector<std::vector<std::size_t>> wanted(this->oracles_.size());       /* oracle id -> positions */             \
+            std::vector<std::vector<std::size_t>> closure(this->virtual_oracle_registrations_.size());  /* virtual id -> oracle ids */ \
+            std::vector<char> closed(this->virtual_oracle_registrations_.size(), 0);                                       \
             for (std::size_t q = 0; q < this->query_registrations_.size(); ++q) {                                          \
                 const std::size_t pos = this->obtain_query_position(this->query_registrations_[q].query_position());       \
-                std::vector<oracle_handle_ptr> open(1, this->query_registrations_[q].oracle());                            \
-                while (!open.empty()) {                                                                                    \
-                    const oracle_handle_ptr cur = open.back();                                                             \
-                    open.pop_back();                                                                                       \
-                    if (std::dynamic_pointer_cast<oracle_handle>(cur)) wanted[cur->id()].insert(pos);                      \
-                    else if (std::dynamic_pointer_cast<virtual_oracle_handle>(cur))                                        \
-                        for (auto &c : this->virtual_oracle_registrations_[cur->id()].constituent_oracles()) open.push_back(c); \
+                const oracle_handle_ptr top = this->query_registrations_[q].oracle();                                      \
+                if (dynamic_cast<const oracle_handle *>(top.get())) { wanted[top->id()].push_back(pos); continue; }        \
+                if (!dynamic_cast<const virtual_oracle_handle *>(top.get())) continue;                                     \
+                std::vector<std::size_t> &leaves = closure[top->id()];                                                     \
+                if (!closed[top->id()]) {                         /* the oracles a virtual oracle is built from, once */   \
+                    closed[top->id()] = 1;                                                                                 \
+                    std::vector<oracle_handle_ptr> open(1, top);                                                           \
+                    while (!open.empty()) {                                                                                \
+                        const oracle_handle_ptr cur = open.back();                                                         \
+                        open.pop_back();                                                                                   \
+                        if (dynamic_cast<const oracle_handle *>(cur.get())) leaves.push_back(cur->id());                   \
+                        else if (dynamic_cast<const virtual_oracle_handle *>(cur.get()))                                   \
+                            for (auto &c : this->virtual_oracle_registrations_[cur->id()].constituent_oracles()) open.push_back(c); \
+                    }                                                                                                      \
+                    std::sort(leaves.begin(), leaves.end());                                                               \
+                    leaves.erase(std::unique(leaves.begin(), leaves.end()), leaves.end());                                 \
                 }                                                                                                          \
+                for (std::size_t o : leaves) wanted[o].push_back(pos);                                                     \
             }                                                                                                              \
             for (std::size_t round = 0; round < this->num_interaction_rounds_; ++round) {                                  \
-                for (auto &kv : this->oracles_in_round_by_domain(round)) {                                                 \
-                    std::set<std::size_t> all;                                                                             \
-                    for (auto &o : kv.second) { auto w = wanted.find(o.id()); if (w != wanted.end()) all.insert(w->second.begin(), w->second.end()); } \
-                    if (!all.empty()) for (auto &o : kv.second) wanted[o.id()].insert(all.begin(), all.end());            \
+                for (auto &kv : this->oracles_in_round_by_domain(round)) {       /* one Merkle tree: every oracle at every queried position */ \
+                    std::vector<std::size_t> all;                                                                          \
+                    for (auto &o : kv.second) all.insert(all.end(), wanted[o.id()].begin(), wanted[o.id()].end());         \
+                    std::sort(all.begin(), all.end());                                                                     \
+                    all.erase(std::unique(all.begin(), all.end()), all.end());                                             \
+                    for (auto &o : kv.second) wanted[o.id()] = all;                                                        \
                 }                                                                                                          \
             }                                                                                                              \
-            for (auto &w : wanted) {                                                                                       \
-                if (w.first >= this->oracles_.size() || !this->oracles_present_[w.first]) continue;                        \
-                const std::shared_ptr<std::vector<FIELD>> v = this->oracles_[w.first].evaluated_contents();                \
-                res.prefetch(v->data(), std::vector<std::size_t>(w.second.begin(), w.second.end()));                       \
+            cache.owner = this; cache.generation = res.generation();                                                       \
+            cache.columns.assign(this->oracles_.size(), b200_glue::query_columns<FIELD>::column());                        \
+            for (std::size_t o = 0; o < wanted.size(); ++o) {                                                              \
+                if (wanted[o].empty() || !this->oracles_present_[o]) continue;                                             \
+                const std::shared_ptr<std::vector<FIELD>> v = this->oracles_[o].evaluated_contents();                      \
+                b200_glue::query_columns<FIELD>::column &col = cache.columns[o];                                           \
+                col.positions.swap(wanted[o]);                                                                             \
+                std::sort(col.positions.begin(), col.positions.end());                                                     \
+                col.positions.erase(std::unique(col.positions.begin(), col.positions.end()), col.positions.end());         \
+                col.values.resize(col.positions.size());                                                                   \
+                col.resident = res.gather(v->data(), col.positions, reinterpret_cast<uint64_t *>(col.values.data()));      \
             }                                                                                                              \
+            if (std::getenv("B200_QUERY_TIMING")) fprintf(stderr, "[b200] bulk query fetch: %.3f ms, %zu queries\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b200_t0).count(), this->query_registrations_.size()); \
+            if (cache.lookup(id, evaluation_position, value)) return value;                                                \
         }                                                                                                                  \
-        return libiop_b200::resident_element<FIELD>(*contents, evaluation_position);                                       \
+        return libiop_b200::resident_element<FIELD>(contents, evaluation_position);   /* a position no registered query covers */ \
     }                                                                                                                      \
     if (std::dynamic_pointer_cast<virtual_oracle_handle>(handle)) {                                                        \
         std::map<std::size_t, FIELD> &cache = this->virtual_oracle_evaluation_cache_[handle->id()];                        \

@@ -118,7 +118,7 @@ std::vector<FieldT> IFFT_of_known_degree_over_field_subset_cref(const std::vecto
     if (const b200_buf resident = residency::instance().find(evals.data(), evals.size())) {
         /* device-resident codeword: take every freq-th evaluation on the device */
         device_buffer sub(closest_power_of_two), out(closest_power_of_two);
-        throw_status(context(), b200_copy_strided(context(), sub.get(), resident, 0, freq, closest_power_of_two));
+        throw_status(context(), b200_copy_strided(context(), sub.get(), 1, resident, 0, freq, closest_power_of_two));
         if (closest_power_of_two == 1) return sub.template download<FieldT>(1);
         IFFT_over_field_subset_device<FieldT>(sub, minimal, out);
         return out.template download<FieldT>(closest_power_of_two);

@@ -21,6 +21,7 @@
 #define LIBIOP_B200_RESIDENCY_HPP_
 
 #include <array>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -42,7 +43,7 @@ class residency {
     std::map<uintptr_t, entry> blocks_;                       /* by block address, ordered: lookups by contained address */
     std::mutex mu_;
     std::size_t bytes_ = 0, hits_ = 0, misses_ = 0, faults_ = 0, fault_bytes_ = 0, gathers_ = 0;
-    std::size_t generation_ = 0;                              /* bumped by every registration */
+    std::atomic<std::size_t> generation_{0};                  /* bumped by every registration */
     const void *bulk_owner_ = nullptr;                        /* last object that ran a bulk fetch, and when */
     std::size_t bulk_generation_ = ~std::size_t(0);
 
@@ -136,6 +137,21 @@ public:
         std::memcpy(out, f->second.data(), 24);
         return true;
     }
+    /* values of `positions` of the vector at `host` with one gather; false (nothing written) if it is not resident */
+    bool gather(const void *host, const std::vector<std::size_t> &positions, uint64_t *out)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end()) return false;
+        for (std::size_t p : positions) if (p >= it->second.n) return false;
+        if (!positions.empty()) {
+            throw_status(context(), b200_gather(context(), out, it->second.buf.get(), positions.data(), positions.size()));
+            ++gathers_;
+        }
+        return true;
+    }
+    /* bumped by every registration: readers that cache fetched values compare it to know their cache is current */
+    std::size_t generation() const { return generation_.load(std::memory_order_acquire); }
     /* true when `position` of the vector at `host` would need a gather (resident and not fetched yet) */
     bool needs_fetch(const void *host, std::size_t position)
     {
@@ -148,8 +164,8 @@ public:
     bool begin_bulk_fetch(const void *owner)
     {
         std::lock_guard<std::mutex> lock(mu_);
-        if (bulk_owner_ == owner && bulk_generation_ == generation_) return false;
-        bulk_owner_ = owner; bulk_generation_ = generation_;
+        if (bulk_owner_ == owner && bulk_generation_ == generation_.load()) return false;
+        bulk_owner_ = owner; bulk_generation_ = generation_.load();
         return true;
     }
     /* fetch many positions of one vector with a single gather (no-op for vectors that are not resident) */

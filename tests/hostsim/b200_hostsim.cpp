@@ -132,8 +132,8 @@ int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t off, s
 int b200_copy(b200_ctx *, b200_buf dst, size_t doff, b200_buf src, size_t soff, size_t n)
 { std::memmove(E(dst) + doff, E(src) + soff, n * 24); return 0; }
 int b200_wait_uploads(b200_ctx *) { return 0; }
-int b200_copy_strided(b200_ctx *, b200_buf dst, b200_buf src, size_t soff, size_t stride, size_t n)
-{ for (size_t i = 0; i < n; ++i) E(dst)[i] = E(src)[soff + i * stride]; return 0; }
+int b200_copy_strided(b200_ctx *, b200_buf dst, size_t dstride, b200_buf src, size_t soff, size_t sstride, size_t n)
+{ for (size_t i = 0; i < n; ++i) E(dst)[i * dstride] = E(src)[soff + i * sstride]; return 0; }
 int b200_fill_zero(b200_ctx *, b200_buf dst, size_t off, size_t n) { std::memset(E(dst) + off, 0, n * 24); return 0; }
 int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, size_t k)
 {
@@ -408,6 +408,18 @@ int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_row
             acc = f.add(acc, f.mul(el(coeff + 3 * k), E(x)[col[k]]));
         }
         E(y_out)[i] = acc;
+    }
+    return 0;
+}
+int b200_gf192_scatter_mul_add(b200_ctx *c, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
+                               const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3])
+{
+    Field f; f.kind = B200_FIELD_GF192;
+    ++c->launches;
+    c->h2d += nnz * 32;
+    for (size_t k = 0; k < nnz; ++k) {
+        if (dst[k] >= n_y || src[k] >= n_x) return fail(c, B200_ERR_INVALID, "scatter: entry %zu outside the vectors", k);
+        E(y)[dst[k]] = f.add(E(y)[dst[k]], f.mul(f.mul(el(coeff + 3 * k), el(scale)), E(x)[src[k]]));
     }
     return 0;
 }

@@ -72,6 +72,16 @@ def test_whole_provers_through_the_dropin_host_logic(sim, which, log_n, zk, nbyt
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == (nbytes, sha)
 
 
+def test_lazy_vectors_against_the_simulator():
+    """tests/hostsim/lazy_vector_test.cpp: the device-resident ("lazy") host vectors of libiop_b200/host/b200_residency.hpp —
+    registration by ownership, materialisation on any host access (read, write, by-value copy) through the SIGSEGV handler,
+    release on destruction, device-to-device clones, query gathers.  Needs only the simulator, not the reference checkout."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", SIM_DIR, "sim"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(SIM_DIR, "_build", "lazy_vector_test")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "0 failed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+
+
 def test_simulator_is_not_reachable_from_the_product():
     """nothing under libiop_b200/ or include/ names the simulator or the oracle, and the product drop-in library does not link them"""
     for base in ("libiop_b200", "include"):
