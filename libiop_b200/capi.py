@@ -462,6 +462,33 @@ class B200:
         finally:
             self.free(dx); self.free(dy)
 
+    def gf192_scatter_mul_add(self, y, dst, src, coeff, x, scale):
+        """y[dst[k]] += scale * coeff[k] * x[src[k]] (multi_lincheck's p_alpha_ABC, basic_lincheck_aux.tcc:63-84); returns the new y"""
+        y = np.ascontiguousarray(y, dtype=np.uint64).reshape(-1, 3); x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 3)
+        dst = np.ascontiguousarray(dst, dtype=np.uint32); src = np.ascontiguousarray(src, dtype=np.uint32)
+        coeff = np.ascontiguousarray(coeff, dtype=np.uint64).reshape(-1, 3); scale = np.ascontiguousarray(scale, dtype=np.uint64)
+        dy, dx = self.upload(y), self.upload(x)
+        try:
+            u32p = C.POINTER(C.c_uint32)
+            self._chk(self.lib.b200_gf192_scatter_mul_add(self.ctx, C.c_uint64(dy), C.c_size_t(len(y)), C.c_size_t(len(dst)),
+                                                          dst.ctypes.data_as(u32p), src.ctypes.data_as(u32p), coeff.ctypes.data_as(_u64p),
+                                                          C.c_uint64(dx), C.c_size_t(len(x)), scale.ctypes.data_as(_u64p)))
+            return self.download(dy, len(y))
+        finally:
+            self.free(dy); self.free(dx)
+
+    def copy_strided(self, src, n_out, dst_stride, src_offset, src_stride, n):
+        """zero-filled array of n_out elements with out[i * dst_stride] = src[src_offset + i * src_stride], i < n"""
+        src = np.ascontiguousarray(src, dtype=np.uint64).reshape(-1, 3)
+        ds, do = self.upload(src), self.alloc(max(n_out, 1))
+        try:
+            self._chk(self.lib.b200_fill_zero(self.ctx, C.c_uint64(do), C.c_size_t(0), C.c_size_t(n_out)))
+            self._chk(self.lib.b200_copy_strided(self.ctx, C.c_uint64(do), C.c_size_t(dst_stride), C.c_uint64(ds), C.c_size_t(src_offset),
+                                                 C.c_size_t(src_stride), C.c_size_t(n)))
+            return self.download(do, n_out)
+        finally:
+            self.free(ds); self.free(do)
+
     def vec_rows_dot(self, field, fp, x, y, split):
         """x, y: (rows, n, 3) -> out[a] = sum_{r<split} x[r,a]*y[r,a] - sum_{r>=split} x[r,a]*y[r,a]"""
         x = np.ascontiguousarray(x, dtype=np.uint64); y = np.ascontiguousarray(y, dtype=np.uint64)

@@ -13,67 +13,60 @@
 
 namespace libiop {
 namespace b200_glue {
-template<typename FieldT> libiop_b200::device_vector_cache<FieldT> &polynomial_cache()
-{
-    static libiop_b200::device_vector_cache<FieldT> cache(4);
-    return cache;
-}
 /* The low-degree extensions of p_alpha' and p_alpha_ABC over the codeword domain, left on the device by
    evaluated_contents.  The prover's query phase asks for both polynomials at ~100 points that all lie in the codeword
    domain (iop.tcc:670-724 passes the position along with the point): those values are already in these arrays, so a query
-   costs one 24-byte gather instead of a degree-2^20 Horner evaluation.  An entry is tied to its coefficient vector by
-   address, length and a content sample, and to the domain by value. */
-template<typename FieldT>
-class codeword_lde_cache {
-    struct entry { const FieldT *ptr; std::size_t n; std::vector<FieldT> sample; field_subset<FieldT> domain; libiop_b200::device_buffer lde; };
-    std::list<entry> entries_;
-    static std::vector<FieldT> sample_of(const std::vector<FieldT> &v)
-    {
-        std::vector<FieldT> s;
-        const std::size_t n = v.size(), k = n < 32 ? n : 32;
-        for (std::size_t i = 0; i < k; ++i) s.push_back(v[(k > 1) ? (i * (n - 1)) / (k - 1) : 0]);
-        return s;
-    }
-public:
-    void put(const std::vector<FieldT> &coefficients, const field_subset<FieldT> &domain, libiop_b200::device_buffer &&lde)
-    {
-        for (auto it = entries_.begin(); it != entries_.end();)
-            if (it->ptr == coefficients.data()) it = entries_.erase(it); else ++it;
-        if (entries_.size() >= 4) entries_.pop_back();
-        entries_.push_front(entry{coefficients.data(), coefficients.size(), sample_of(coefficients), domain, std::move(lde)});
-    }
-    const libiop_b200::device_buffer *find(const std::vector<FieldT> &coefficients, const field_subset<FieldT> &domain)
-    {
-        for (auto &e : entries_)
-            if (e.ptr == coefficients.data() && e.n == coefficients.size() && e.sample == sample_of(coefficients) && e.domain == domain)
-                return &e.lde;
-        return nullptr;
-    }
-};
-template<typename FieldT> codeword_lde_cache<FieldT> &lde_cache()
-{
-    static codeword_lde_cache<FieldT> cache;
-    return cache;
-}
-/* value of the polynomial at `x`: from its resident low-degree extension when x is element `position` of the domain */
+   costs one 24-byte gather instead of a degree-2^20 Horner evaluation.  The arrays are attached to the coefficient vector's
+   own device registration (libiop_b200/host/b200_residency.hpp): they live exactly as long as that vector and cannot be
+   mistaken for another polynomial's. */
 template<typename FieldT>
 bool evaluate_from_lde(const std::vector<FieldT> &coefficients, const field_subset<FieldT> &domain, std::size_t position, const FieldT &x,
                        FieldT &value)
 {
-    const libiop_b200::device_buffer *lde = lde_cache<FieldT>().find(coefficients, domain);
-    if (!lde || position >= domain.num_elements() || domain.element_by_index(position) != x) return false;
-    libiop_b200::throw_status(libiop_b200::context(), b200_gather(libiop_b200::context(), reinterpret_cast<uint64_t *>(&value), lde->get(), &position, 1));
+    if (position >= domain.num_elements()) return false;
+    const b200_buf lde = libiop_b200::residency::instance().attachment(coefficients.data(), "lde", domain.num_elements());
+    if (!lde || domain.element_by_index(position) != x) return false;
+    libiop_b200::throw_status(libiop_b200::context(), b200_gather(libiop_b200::context(), reinterpret_cast<uint64_t *>(&value), lde, &position, 1));
     return true;
 }
 
 template<typename FieldT> FieldT evaluate_polynomial(const std::vector<FieldT> &coefficients, const FieldT &x)
 {
-    if (coefficients.size() < 4096) {           /* not worth a launch: same Horner recurrence as polynomial.tcc:98-109 */
+    const bool resident = libiop_b200::residency::instance().is_resident(coefficients.data());
+    if (coefficients.size() < 4096 && !resident) {   /* not worth a launch: same Horner recurrence as polynomial.tcc:98-109 */
         FieldT r = FieldT::zero();
         for (auto it = coefficients.rbegin(); it != coefficients.rend(); ++it) { r *= x; r += *it; }
         return r;
     }
-    return libiop_b200::poly_eval<FieldT>(polynomial_cache<FieldT>().get(coefficients), coefficients.size(), x);
+    const libiop_b200::device_view c(coefficients);        /* set_challenge leaves the coefficients on the device */
+    return libiop_b200::poly_eval<FieldT>(c.buf(), coefficients.size(), x);
+}
+
+/* the constraint system behind an r1cs_sparse_matrix (a protected member: reached through a pointer to member formed in
+   a derived class), so that rows can be walked by reference instead of through get_row()'s by-value copies */
+template<typename FieldT>
+struct r1cs_matrix_peek : public r1cs_sparse_matrix<FieldT> {
+    static const r1cs_constraint_system<FieldT> &system(const r1cs_sparse_matrix<FieldT> &m) { return *(m.*(&r1cs_matrix_peek::constraint_system_)); }
+    static r1cs_sparse_matrix_type type(const r1cs_sparse_matrix<FieldT> &m) { return m.*(&r1cs_matrix_peek::matrix_type_); }
+};
+/* calls f(row index, term) for every entry of M */
+template<typename FieldT, typename Fn>
+void for_each_entry(const sparse_matrix<FieldT> &M, Fn f)
+{
+    if (const r1cs_sparse_matrix<FieldT> *rm = dynamic_cast<const r1cs_sparse_matrix<FieldT> *>(&M)) {
+        const r1cs_constraint_system<FieldT> &cs = r1cs_matrix_peek<FieldT>::system(*rm);
+        const r1cs_sparse_matrix_type t = r1cs_matrix_peek<FieldT>::type(*rm);
+        for (std::size_t i = 0; i < cs.constraints_.size(); ++i) {
+            const linear_combination<FieldT> &row = t == r1cs_sparse_matrix_A ? cs.constraints_[i].a_
+                                                   : t == r1cs_sparse_matrix_B ? cs.constraints_[i].b_ : cs.constraints_[i].c_;
+            for (const auto &term : row.terms) f(i, term);
+        }
+        return;
+    }
+    for (std::size_t i = 0; i < M.num_rows(); ++i) {
+        const linear_combination<FieldT> row = M.get_row(i);
+        for (const auto &term : row.terms) f(i, term);
+    }
 }
 }
 
@@ -106,10 +99,74 @@ template<> inline std::shared_ptr<std::vector<FIELD>> multi_lincheck_virtual_ora
     vec_lincomb<FIELD>(d_comb, n, this->r_Mz_, Mz_ptrs);                                                                   \
     vec_mul_add<FIELD>(d_out, d_comb, &d_p1, &d_fz.buf(), &d_p2, true, n);                                                       \
     std::shared_ptr<std::vector<FIELD>> result = b200_glue::to_host<FIELD>(d_out, n);                                      \
-    b200_glue::lde_cache<FIELD>().put(this->p_alpha_prime_.coefficients(), this->codeword_domain_, std::move(d_p1));       \
-    b200_glue::lde_cache<FIELD>().put(this->p_alpha_ABC_.coefficients(), this->codeword_domain_, std::move(d_p2));         \
+    /* keep both extensions next to their (device-resident) coefficient vectors for the query phase */                     \
+    residency::instance().attach(this->p_alpha_prime_.coefficients().data(), "lde", std::move(d_p1));                      \
+    residency::instance().attach(this->p_alpha_ABC_.coefficients().data(), "lde", std::move(d_p2));                        \
     libff::leave_block("multi_lincheck evaluated contents");                                                               \
     return result;                                                                                                         \
+}                                                                                                                          \
+/* set_challenge (basic_lincheck_aux.tcc:30-99): alpha powers over the constraint domain, p_alpha' = those powers placed in  \
+   the summation domain, p_alpha_ABC = (sum_m r_m M_m)^T applied to them, both interpolated over the summation domain.      \
+   The reference spends 0.13 s of an N = 2^20 proof here (3 * 2^20 get_row() copies, two multiplications per entry); on    \
+   the B200 the powers, the placement, the transposed product (a scatter-accumulate over the flattened entries) and the    \
+   two IFFTs run on the device and the coefficient vectors stay there. */                                                  \
+template<> inline void multi_lincheck_virtual_oracle<FIELD>::set_challenge(const FIELD &alpha, const std::vector<FIELD> r_Mz) \
+{                                                                                                                          \
+    if (r_Mz.size() != this->matrices_.size())                                                                             \
+        throw std::invalid_argument("Not enough random linear combination coefficients were provided");                    \
+    if (this->use_lagrange_) throw std::logic_error("B200 drop-in: the Lagrange variant of multi_lincheck is not wired"); \
+    this->r_Mz_ = r_Mz;                                                                                                    \
+    using namespace libiop_b200;                                                                                           \
+    const std::size_t n_H = this->constraint_domain_.num_elements(), n_S = this->summation_domain_.num_elements();         \
+    libff::enter_block("multi_lincheck compute alpha powers");                                                             \
+    device_buffer d_alpha(n_H);                                                                                            \
+    powers_of<FIELD>(d_alpha, n_H, alpha);                                                                                 \
+    libff::leave_block("multi_lincheck compute alpha powers");                                                             \
+    libff::enter_block("multi_lincheck compute p_alpha_prime");                                                            \
+    /* element i of the constraint domain sits at position i * stride of the summation domain (identity for subspaces,     \
+       every (|S|/|H|)-th element for cosets: field_subset::reindex_by_subset, subgroup.tcc:150-162) */                    \
+    const std::size_t stride = n_H > 1 ? this->summation_domain_.reindex_by_subset(this->constraint_domain_.dimension(), 1) : 1; \
+    device_buffer d_prime(n_S), d_abc(n_S);                                                                                \
+    throw_status(context(), b200_fill_zero(context(), d_prime.get(), 0, n_S));                                             \
+    throw_status(context(), b200_copy_strided(context(), d_prime.get(), stride, d_alpha.get(), 0, 1, n_H));               \
+    libff::leave_block("multi_lincheck compute p_alpha_prime");                                                            \
+    libff::enter_block("multi_lincheck compute p_alpha_ABC");                                                              \
+    throw_status(context(), b200_fill_zero(context(), d_abc.get(), 0, n_S));                                               \
+    const auto summation_index = [this](std::size_t column) {                                                              \
+        return this->summation_domain_.reindex_by_subset(this->variable_domain_.dimension(),                               \
+                                                         this->variable_domain_.reindex_by_subset(this->input_variable_dim_, column)); \
+    };                                                                                                                     \
+    if (field_traits<FIELD>::kind == B200_FIELD_GF192) {                                                                   \
+        for (std::size_t m = 0; m < this->matrices_.size(); ++m) {                                                         \
+            std::vector<uint32_t> dst, src;                                                                                \
+            std::vector<FIELD> coeff;                                                                                      \
+            const std::size_t guess = this->matrices_[m]->num_rows() + (this->matrices_[m]->num_rows() >> 3);              \
+            dst.reserve(guess); src.reserve(guess); coeff.reserve(guess);                                                  \
+            b200_glue::for_each_entry<FIELD>(*this->matrices_[m], [&](std::size_t row, const linear_term<FIELD> &term) {   \
+                dst.push_back((uint32_t)summation_index(term.index_)); src.push_back((uint32_t)row); coeff.push_back(term.coeff_); \
+            });                                                                                                            \
+            scatter_mul_add<FIELD>(d_abc, n_S, dst, src, coeff, d_alpha, n_H, this->r_Mz_[m]);                             \
+        }                                                                                                                  \
+    } else {                                                                                                               \
+        /* no atomic modular addition: accumulate on the host from the downloaded powers (rows walked by reference) */      \
+        const std::vector<FIELD> alpha_powers = d_alpha.template download<FIELD>(n_H);                                     \
+        std::vector<FIELD> p_abc(n_S, FIELD::zero());                                                                      \
+        for (std::size_t m = 0; m < this->matrices_.size(); ++m) {                                                         \
+            const FIELD r = this->r_Mz_[m];                                                                                \
+            b200_glue::for_each_entry<FIELD>(*this->matrices_[m], [&](std::size_t row, const linear_term<FIELD> &term) {   \
+                p_abc[summation_index(term.index_)] += r * term.coeff_ * alpha_powers[row];                                \
+            });                                                                                                            \
+        }                                                                                                                  \
+        d_abc.upload(p_abc);                                                                                               \
+    }                                                                                                                      \
+    libff::leave_block("multi_lincheck compute p_alpha_ABC");                                                              \
+    libff::enter_block("multi_lincheck IFFT p_alphas");                                                                    \
+    device_buffer c_abc(n_S), c_prime(n_S);                                                                                \
+    IFFT_over_field_subset_device<FIELD>(d_abc, this->summation_domain_, c_abc);                                           \
+    IFFT_over_field_subset_device<FIELD>(d_prime, this->summation_domain_, c_prime);                                       \
+    this->p_alpha_ABC_ = polynomial<FIELD>(make_lazy_vector<FIELD>(std::move(c_abc), n_S));                                \
+    this->p_alpha_prime_ = polynomial<FIELD>(make_lazy_vector<FIELD>(std::move(c_prime), n_S));                            \
+    libff::leave_block("multi_lincheck IFFT p_alphas");                                                                    \
 }                                                                                                                          \
 template<> inline FIELD multi_lincheck_virtual_oracle<FIELD>::evaluation_at_point(                                         \
     const std::size_t evaluation_position, const FIELD evaluation_point,                                                   \

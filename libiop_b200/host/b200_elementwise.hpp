@@ -13,6 +13,7 @@
 
 #include <cstring>
 #include <list>
+#include <stdexcept>
 #include <utility>
 #include <vector>
 
@@ -105,6 +106,37 @@ template<typename FieldT>
 void geometric_sequence(device_buffer &out, std::size_t n, const FieldT &a, const FieldT &r, const FieldT &add)
 {
     throw_status(context(), b200_fp_geometric(context(), field_traits<FieldT>::fp(), out.get(), n, limbs(a), limbs(r), limbs(add)));
+}
+
+/* out[i] = base^i, i < n (n a power of two for GF(2^192)): the alpha powers of multi_lincheck's set_challenge
+   (lincheck/basic_lincheck_aux.tcc:38-46).  Binary field: base^i = prod_j (bit j of i ? base^(2^j) : 1), i.e. log2(n) factors
+   that are affine in the index bits, generated by b200_gf192_subset_sum_products; prime field: a geometric sequence. */
+template<typename FieldT>
+void powers_of(device_buffer &out, std::size_t n, const FieldT &base)
+{
+    if (field_traits<FieldT>::kind != B200_FIELD_GF192) { geometric_sequence<FieldT>(out, n, FieldT::one(), base, FieldT::zero()); return; }
+    std::size_t dim = 0;
+    while ((std::size_t(1) << dim) < n) ++dim;
+    if ((std::size_t(1) << dim) != n) throw std::invalid_argument("powers_of: length must be a power of two");
+    if (dim == 0) { const std::vector<FieldT> one(1, FieldT::one()); out.upload(one); return; }
+    std::vector<std::vector<FieldT>> tables(dim, std::vector<FieldT>(dim + 1, FieldT::zero()));
+    FieldT sq = base;
+    for (std::size_t j = 0; j < dim; ++j) {
+        tables[j][0] = FieldT::one();
+        tables[j][1 + j] = sq - FieldT::one();          /* factor j is 1 when bit j is clear, base^(2^j) when it is set */
+        sq *= sq;
+    }
+    subspace_function_product<FieldT>(out, dim, tables);
+}
+
+/* GF(2^192): y[dst[k]] += scale * coeff[k] * x[src[k]] over a list of matrix entries (b200_gf192_scatter_mul_add) */
+template<typename FieldT>
+void scatter_mul_add(device_buffer &y, std::size_t n_y, const std::vector<uint32_t> &dst, const std::vector<uint32_t> &src,
+                     const std::vector<FieldT> &coeff, const device_buffer &x, std::size_t n_x, const FieldT &scale)
+{
+    static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    throw_status(context(), b200_gf192_scatter_mul_add(context(), y.get(), n_y, dst.size(), dst.data(), src.data(),
+                                                       reinterpret_cast<const uint64_t *>(coeff.data()), x.get(), n_x, limbs(scale)));
 }
 
 /* scale * x^exponent for every element x of the domain, in domain order

@@ -39,6 +39,7 @@ class residency {
         std::size_t n;                                        /* elements */
         device_buffer buf;
         std::unordered_map<std::size_t, std::array<uint64_t, 3>> fetched;   /* positions already read by the query phase */
+        std::map<std::string, device_buffer> attached;       /* device arrays derived from this vector (e.g. its extension over L) */
     };
     std::map<uintptr_t, entry> blocks_;                       /* by block address, ordered: lookups by contained address */
     std::mutex mu_;
@@ -136,6 +137,25 @@ public:
         }
         std::memcpy(out, f->second.data(), 24);
         return true;
+    }
+    /* Keep `buf` next to the registered vector at `host` under `key`: it is released with the vector.  Returns false (and
+       drops `buf`) when the vector is not device-resident. */
+    bool attach(const void *host, const std::string &key, device_buffer &&buf)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end()) return false;
+        it->second.attached[key] = std::move(buf);
+        return true;
+    }
+    /* device address of the attachment `key` (of exactly n elements) of the vector at `host`, or 0 */
+    b200_buf attachment(const void *host, const std::string &key, std::size_t n)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        if (it == blocks_.end()) return 0;
+        auto a = it->second.attached.find(key);
+        return (a != it->second.attached.end() && a->second.size() == n) ? a->second.get() : 0;
     }
     /* values of `positions` of the vector at `host` with one gather; false (nothing written) if it is not resident */
     bool gather(const void *host, const std::vector<std::size_t> &positions, uint64_t *out)

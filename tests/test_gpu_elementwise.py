@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from oracle_lib import el, rand_elems, standard_basis
+from oracle_lib import el, elems, rand_elems, standard_basis
 
 pytestmark = pytest.mark.gpu
 
@@ -328,3 +328,63 @@ def test_vec_rows_dot(dev, oracle, fp, field, rows, split, n):
     assert (got == want).all()
     with pytest.raises(Exception):
         dev.vec_rows_dot(field, fp if field == FP else None, x, y, rows + 1)
+
+
+# ------------------------------------------------------------------ N3: transposed sparse product of multi_lincheck (p_alpha_ABC)
+@pytest.mark.parametrize("n_y,n_x,nnz", [(1 << 10, 1 << 10, 3000), (1 << 12, 1 << 11, 1), (64, 64, 0), (1 << 14, 1 << 14, 50000)])
+def test_gf192_scatter_mul_add(dev, oracle, n_y, n_x, nnz):
+    """b200_gf192_scatter_mul_add: y[dst[k]] += scale * coeff[k] * x[src[k]] — the loop of multi_lincheck_virtual_oracle::set_challenge
+    (protocols/encoded/lincheck/basic_lincheck_aux.tcc:63-84) over the flattened entries of one matrix; heavy collisions on a
+    few destinations included (atomic XOR accumulation)."""
+    rng = np.random.default_rng(n_y + nnz)
+    y, x = rand_elems(rng, n_y), rand_elems(rng, n_x)
+    dst = rng.integers(0, n_y, size=nnz, dtype=np.uint32); src = rng.integers(0, n_x, size=nnz, dtype=np.uint32)
+    if nnz > 100:
+        dst[:nnz // 4] = dst[0]                       # a quarter of the entries hit one destination
+    coeff, scale = rand_elems(rng, nnz), rand_elems(rng, 1)[0]
+    want = y.copy()
+    if nnz:
+        prod = oracle.gf192_mul(oracle.gf192_mul(coeff, np.repeat(scale.reshape(1, 3), nnz, 0)), x[src])
+        for k in range(nnz):
+            want[dst[k]] ^= prod[k]
+    assert (dev.gf192_scatter_mul_add(y, dst, src, coeff, x, scale) == want).all()
+
+
+def test_gf192_scatter_rejects_out_of_range_entries(dev):
+    import libiop_b200 as L
+    rng = np.random.default_rng(3)
+    y, x = rand_elems(rng, 16), rand_elems(rng, 16)
+    with pytest.raises(L.B200Error):
+        dev.gf192_scatter_mul_add(y, [16], [0], rand_elems(rng, 1), x, rand_elems(rng, 1)[0])
+    with pytest.raises(L.B200Error):
+        dev.gf192_scatter_mul_add(y, [0], [99], rand_elems(rng, 1), x, rand_elems(rng, 1)[0])
+
+
+@pytest.mark.parametrize("n_src,n_out,ds,so,ss,n", [(1 << 12, 1 << 9, 1, 0, 8, 1 << 9), (1 << 9, 1 << 12, 8, 0, 1, 1 << 9), (100, 40, 2, 3, 5, 19), (8, 8, 1, 0, 1, 0)])
+def test_copy_strided(dev, n_src, n_out, ds, so, ss, n):
+    """b200_copy_strided: sub-coset gather (fft.tcc:446-455) and placement of a sub-coset inside the larger one (subgroup.tcc:150-162)"""
+    rng = np.random.default_rng(n_src + n)
+    src = rand_elems(rng, n_src)
+    want = elems(n_out)
+    for i in range(n):
+        want[i * ds] = src[so + i * ss]
+    assert (dev.copy_strided(src, n_out, ds, so, ss, n) == want).all()
+
+
+@pytest.mark.parametrize("dim", [1, 5, 12])
+def test_powers_by_subset_sum_products(dev, oracle, dim):
+    """alpha^i for i < 2^dim as a product of dim index-bit-affine factors (libiop_b200/host/b200_elementwise.hpp powers_of):
+    factor j is 1 when bit j of i is clear and alpha^(2^j) when it is set."""
+    rng = np.random.default_rng(dim)
+    alpha = rand_elems(rng, 1)[0]
+    tables = np.zeros((dim, dim + 1, 3), dtype=np.uint64)
+    sq = alpha.copy()
+    for j in range(dim):
+        tables[j, 0] = el(1)
+        tables[j, 1 + j] = sq ^ el(1)
+        sq = oracle.gf192_mul(sq.reshape(1, 3), sq.reshape(1, 3))[0]
+    got = dev.gf192_subset_sum_products(dim, tables)
+    want = elems(1 << dim); want[0] = el(1)
+    for i in range(1, 1 << dim):
+        want[i] = oracle.gf192_mul(want[i - 1].reshape(1, 3), alpha.reshape(1, 3))[0]
+    assert (got == want).all()
