@@ -20,6 +20,7 @@
  * shared memory in the same launch and only the top of the tree runs as small per-level launches.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
@@ -345,6 +346,115 @@ __global__ void __launch_bounds__(128) merkle_leaf8_kernel(const LeafParams P)
     reduce8_32(P.nodes, d, P.leaves, t * 8);
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/* wide leaves (Ligero: one column of several hundred interleaved rows = ~12 KB = 96 compressions per leaf,
+   merkle_tree.tcc:123-145, and only 2^13 leaves): WARP-COOPERATIVE BLAKE2b.  Four lanes ("a quad") share one hash
+   state, lane q holding column q of the 4x4 state matrix (a, b, c, d = v[q], v[4+q], v[8+q], v[12+q]).  The column step of
+   a round is one G per lane; for the diagonal step b, c, d are rotated by 1, 2, 3 lanes inside the quad with shuffles,
+   one G, and rotated back.  The 128-byte message block is fetched by the quad together (lane q loads words q, q+4, q+8,
+   q+12 of the block: consecutive leaves of one row are consecutive in memory, so the 8 quads of a warp read 192
+   contiguous bytes per row) and parked in shared memory, from which every lane picks the two words each of its G's
+   needs.  8 leaves per warp instead of 8 leaves per THREAD: 2^13 leaves give 1024 warps (7 per SM) instead of 32.   */
+__constant__ uint8_t c_blake_sigma[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+
+#define QUAD_MSG_STRIDE 17   /* u64 words per quad in shared memory (16 + 1 of padding: quads land on different banks) */
+
+__device__ __forceinline__ uint64_t quad_shfl(uint64_t v, int src_lane)
+{
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src_lane);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src_lane);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+/* One compression by a quad.  h0 / h1: this lane's two words of the chaining value (h[q], h[4+q]); msg: the quad's block in
+   shared memory; sig[r] packs this lane's four message indices of round r (4 bits each: column x, y, diagonal x, y). */
+__device__ __forceinline__ void quad_compress(uint64_t &h0, uint64_t &h1, const uint64_t *msg, const uint32_t sig[12], uint32_t q,
+                                              uint64_t t, bool last)
+{
+    uint64_t a = h0, b = h1;
+    uint64_t c = q == 0 ? BLAKE_IV0 : q == 1 ? BLAKE_IV1 : q == 2 ? BLAKE_IV2 : BLAKE_IV3;
+    uint64_t d = q == 0 ? (BLAKE_IV4 ^ t) : q == 1 ? BLAKE_IV5 : q == 2 ? (last ? ~BLAKE_IV6 : BLAKE_IV6) : BLAKE_IV7;
+    const int lane = threadIdx.x & 31, base = lane & ~3;
+    const int up1 = base | ((q + 1) & 3), up2 = base | ((q + 2) & 3), up3 = base | ((q + 3) & 3);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+        const uint32_t s = sig[r];
+        BLAKE_G(a, b, c, d, msg[s & 15u], msg[(s >> 4) & 15u]);
+        /* diagonalise: lane q takes b of column q+1, c of column q+2, d of column q+3 */
+        b = quad_shfl(b, up1); c = quad_shfl(c, up2); d = quad_shfl(d, up3);
+        BLAKE_G(a, b, c, d, msg[(s >> 8) & 15u], msg[(s >> 12) & 15u]);
+        b = quad_shfl(b, up3); c = quad_shfl(c, up2); d = quad_shfl(d, up1);
+    }
+    h0 ^= a ^ c;
+    h1 ^= b ^ d;
+}
+
+__global__ void __launch_bounds__(128) merkle_leaf_quad_kernel(const LeafParams P)
+{
+    __shared__ uint64_t smsg[(128 / 4) * QUAD_MSG_STRIDE];
+    const uint32_t q = threadIdx.x & 3;
+    const size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 2;     /* leaf of this quad */
+    const bool active = i < P.leaves;                                          /* whole quads only: leaves is a power of two >= 8 */
+    uint64_t *msg = smsg + (threadIdx.x >> 2) * QUAD_MSG_STRIDE;
+    uint32_t sig[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r)
+        sig[r] = (uint32_t)c_blake_sigma[r][2 * q] | ((uint32_t)c_blake_sigma[r][2 * q + 1] << 4) |
+                 ((uint32_t)c_blake_sigma[r][8 + 2 * q] << 8) | ((uint32_t)c_blake_sigma[r][8 + 2 * q + 1] << 12);
+
+    const size_t n_words = (size_t)3 * P.n_oracles * P.coset;
+    const uint32_t cmask = P.coset - 1;
+    /* chaining value: lane q holds h[q] and h[4+q] */
+    uint64_t h0 = (q == 0 ? (BLAKE_IV0 ^ 0x01010000ULL ^ 32ull) : q == 1 ? BLAKE_IV1 : q == 2 ? BLAKE_IV2 : BLAKE_IV3);
+    uint64_t h1 = (q == 0 ? BLAKE_IV4 : q == 1 ? BLAKE_IV5 : q == 2 ? BLAKE_IV6 : BLAKE_IV7);
+    size_t done = 0;
+    for (;;) {                                                                 /* uniform trip count across the grid */
+        const size_t remaining = n_words - done;
+        const bool last = remaining <= 16;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t w = done + q + 4 * u;                                 /* word of the leaf this lane fetches */
+            uint64_t v = 0;
+            if (active && w < n_words) {
+                const size_t e = w / 3;
+                const uint32_t limb = (uint32_t)(w - 3 * e);
+                const uint32_t j = (uint32_t)e & cmask;
+                const size_t k = e >> P.coset_log;
+                const size_t pos = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? (i + (size_t)j * P.leaves) : (i * P.coset + j);
+                const uint64_t *src = P.oracle_table ? P.oracle_table[k] : P.oracles[k];
+                v = __ldg(src + pos * 3 + limb);
+            }
+            msg[q + 4 * u] = v;
+        }
+        __syncwarp();
+        done += last ? remaining : 16;
+        quad_compress(h0, h1, msg, sig, q, (uint64_t)done * 8, last);
+        __syncwarp();                                                          /* the block is rewritten next iteration */
+        if (last) break;
+    }
+    if (P.salts) {                                  /* zk: H(H(leaf) || salt)  (blake2b.tcc:127-136): one more block */
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w = q + 4 * u;
+            uint64_t v = 0;
+            if (u == 0) v = h0;                                               /* words 0..3 = the inner digest (h[0..3]) */
+            else if (active && w - 4 < P.salt_words) v = P.salts[i * P.salt_words + (w - 4)];
+            msg[w] = v;
+        }
+        __syncwarp();
+        h0 = (q == 0 ? (BLAKE_IV0 ^ 0x01010000ULL ^ 32ull) : q == 1 ? BLAKE_IV1 : q == 2 ? BLAKE_IV2 : BLAKE_IV3);
+        h1 = (q == 0 ? BLAKE_IV4 : q == 1 ? BLAKE_IV5 : q == 2 ? BLAKE_IV6 : BLAKE_IV7);
+        quad_compress(h0, h1, msg, sig, q, (uint64_t)(4 + P.salt_words) * 8, true);
+    }
+    if (active) P.nodes[(P.leaves - 1 + i) * 4 + q] = h0;                      /* 32-byte digest = h[0..3], one word per lane */
+}
+
 __global__ void __launch_bounds__(128) merkle_reduce8_kernel(uint64_t *nodes, size_t width)
 {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -394,7 +504,20 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
         P.salts = (const uint64_t *)ds; P.salt_words = (uint32_t)(salt_len / 8);
     }
     size_t width;   /* nodes in the highest level already computed */
-    if (digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
+    static const bool no_quad = getenv("B200_NO_QUAD_LEAF") != nullptr;           /* ablation switch */
+    if (!no_quad && digest_len == 32 && leaves >= 8 && n_oracles * coset * 24 >= 1024 && leaves * 4 <= ((size_t)1 << 22) &&
+        (!salts || salt_len <= 96)) {
+        /* wide leaves, few of them: four lanes per leaf (merkle_leaf_quad_kernel), then the usual 8-to-1 reductions */
+        merkle_leaf_quad_kernel<<<(unsigned)((leaves * 4 + 127) / 128), 128, 0, c->stream>>>(P);
+        B200_LAUNCH_CHECK(c);
+        width = leaves;
+        while (width > 2048) {
+            const size_t th = width / 8;
+            merkle_reduce8_kernel<<<(unsigned)((th + 127) / 128), 128, 0, c->stream>>>(P.nodes, width);
+            B200_LAUNCH_CHECK(c);
+            width >>= 3;
+        }
+    } else if (digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
         /* fast path: 8 leaves + 3 levels per thread, then 3 levels per launch */
         const size_t threads = leaves / 8;
         merkle_leaf8_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(P);

@@ -331,6 +331,44 @@ def test_merkle_vs_oracle(dev, oracle, no, n, cs, kind):
     assert dev.merkle_build(orc, cs, kind, salts=salts) == oracle.merkle_build(orc, cs, kind, salts=salts)
 
 
+@pytest.mark.parametrize("no,n,cs,kind", [(130, 1 << 10, 1, 1), (43, 8, 1, 1), (20, 1 << 8, 4, 1), (44, 1 << 11, 1, 2), (12, 1 << 9, 4, 2),
+                                          (513, 1 << 9, 1, 1)])
+def test_merkle_wide_leaves_warp_cooperative(dev, oracle, no, n, cs, kind):
+    """Leaves of >= 1 KB (Ligero's interleaved rows, merkle_tree.tcc:123-145) are hashed by merkle_leaf_quad_kernel: four lanes per
+    BLAKE2b state, message blocks staged in shared memory.  Same trees as the one-thread-per-hash kernels (B200_NO_QUAD_LEAF is
+    compared in test_merkle_wide_leaves_both_kernels_agree) and as the oracle: ragged last blocks, zk salts, both leaf layouts,
+    more than 64 oracles (device pointer table)."""
+    rng = np.random.default_rng(900 + no + n + cs + kind)
+    orc = [rand_elems(rng, n) if kind == 1 else oracle.rand_fp(rng, n) for _ in range(no)]
+    assert dev.merkle_build(orc, cs, kind) == oracle.merkle_build(orc, cs, kind)
+    salts = rng.bytes((n // cs) * 32)
+    assert dev.merkle_build(orc, cs, kind, salts=salts) == oracle.merkle_build(orc, cs, kind, salts=salts)
+
+
+def test_merkle_wide_leaves_both_kernels_agree():
+    """Ligero's tree at full size (512 rows x 2^13, BASELINE config 4) with and without the warp-cooperative leaf kernel."""
+    import subprocess, sys, os
+    code = r"""
+import sys, hashlib
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np
+import libiop_b200 as L
+dev = L.B200(0)
+rng = np.random.default_rng(11)
+rows = [dev.upload(rng.integers(0, 2**64, size=(1 << 13, 3), dtype=np.uint64)) for _ in range(512)]
+nodes = dev.alloc_bytes(32 * (2 * (1 << 13) - 1))
+dev.merkle_build_dev(rows, 1 << 13, 1, 1, nodes)
+print('TREE', hashlib.sha256(dev.download_bytes(nodes, 32 * (2 * (1 << 13) - 1))).hexdigest())
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = []
+    for env in ({"B200_NO_QUAD_LEAF": "1"}, {}):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "TREE" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+        got.append(r.stdout.split("TREE")[1].split()[0])
+    assert got[0] == got[1]
+
+
 def test_merkle_errors(dev):
     import libiop_b200 as L
     with pytest.raises(L.B200Error):
