@@ -1,32 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — Aurora prover hot path (LDE / FRI fold / Merkle) on B200, one JSON line on stdout.
+"""bench.py — Aurora prover over GF(2^192) at N = 2^20 constraints on B200 (BASELINE.json configs[1]); one JSON line on stdout.
 
-A "step" is one pass of the hot path of ONE Aurora proof over GF(2^192) at N = 2^20 constraints,
-RS rate 1/8 (|L| = 2^23), FRI localization [1,2,2,...], non-zk — BASELINE.json configs[1] — i.e. exactly
-the sequence of star calls the reference prover makes (traced from the unmodified reference at N = 2^12
-and scaled: see WORKLOAD below and DESIGN.md §4):
-   9 additive FFTs   (8 onto L = 2^23, 1 onto H = 2^20)          libiop/algebra/fft.tcc:39-124
-  11 additive IFFTs  (6 x 2^20, 1 x 2^21, small ones)            libiop/algebra/fft.tcc:126-204
-  10 FRI folds       (2^23 -> 2^22 -> 2^20 -> ... -> 2^4)        libiop/protocols/ldt/fri/fri_aux.tcc:37-103
-  11 Merkle trees    (4x2^23/2, 1x2^23/2, 1x|L_i|/4, i=1..9)     libiop/bcs/merkle_tree.tcc:93-229
-on synthetic (seeded random) oracle contents.  value = N / step time (constraints/s of the hot path).
-The elementwise virtual-oracle passes, proof-of-work and transcript assembly of the full prover are
-NOT in the step — this is stated in config.workload.
+Workload (both arms): aurora_snark_prover<gf192> on generate_r1cs_example(2^20, 31, 2^20 - 1), security 128, RS rate 1/8
+(|L| = 2^23), FRI localization [1,2,2,...], non-zk, BLAKE2b.
 
-  value : inputs resident in HBM, CUDA-event timed on the context's stream.
-  e2e   : the WHOLE Aurora prover at N = 2^20 through the reference-facing API: the reference's own
-          aurora_snark_prover (unmodified libiop host code: IOP layer, protocols, BCS transformation, hash chain,
-          query phase) over host std::vectors, with this library dropped in under its hot-path headers
-          (libiop_b200/lib/libiop_b200_dropin.so, libiop_b200/dropin/).  Every oracle crosses PCIe inside the timed
-          region (h2d / d2h bytes are counted by the library).  value = 2^20 / prover wall seconds.  The transcript is
-          compared byte for byte with the CPU reference's in the whole_prover_dropin section.
-  hot_path_host_buffers : the star calls alone through the host-buffer C ABI (upload, kernel, download per call).
-  --impl reference : the unmodified reference aurora_snark_prover on the host CPU (oracle/_ref/libiopref.so, built
-          from /root/reference in the build container), single-threaded like the reference is, on a bounded sample
-          (N = 2^17) of the same workload; constraints/s.
+  value : the prover's HOT PATH with every oracle resident in HBM — exactly the sequence of LDE / FRI-fold / Merkle calls one
+          proof makes (traced from the unmodified reference; WORKLOAD below), on synthetic oracle contents, CUDA-event timed on
+          the context's stream.  constraints/s = 2^20 / step time.  This is the number the roofline explains.
+  e2e   : the WHOLE reference prover (unmodified libiop host code: IOP layer, protocols, BCS transformation, hash chain, query
+          phase) through the drop-in library (libiop_b200/lib/libiop_b200_dropin.so), R1CS instance and witness in HOST
+          memory, every host<->device byte inside the timed region, transcript compared with the CPU reference's fingerprint.
+          constraints/s = 2^20 / prover wall seconds.  This is the headline against the reference arm.
+  roofline : the dominant kernel (one butterfly tile pass of the LDE over the 2^23-point oracle) timed live with CUDA events;
+          DRAM traffic of the same launch read from the committed ncu capture (profiles/r2_ncu/ncu_lde_raw.csv).
+  cpu_baseline : the unmodified reference prover (oracle/_ref/libiopref.so, built from /root/reference in the build container)
+          on ONE host core — the reference has no threading — on a bounded sample (N = 2^18, ~15 s), and the same instance
+          through the drop-in with the transcripts compared byte for byte.
+  --impl reference : the unmodified reference prover on the host CPU at the SAME config (N = 2^20): one warm-up proof at
+          N = 2^14, then min(steps, 2) timed proofs (75 s each on the GPU box's host); `steps` reports the proofs actually timed.
+
+Under torchrun (N > 1) every rank proves its own instance (seed + rank): weak scaling, no data-path collective; NCCL carries
+the barrier, the max-over-ranks time and the gather of the real proof transcripts to rank 0.  At N = 8 the line also carries
+BASELINE config 5 (one N = 2^22 proof per GPU, verified, transcripts gathered).
 """
 import argparse
+import csv
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -42,10 +42,16 @@ sys.path.insert(0, ROOT)
 LOG_N = 20
 RHO = 3
 M = LOG_N + RHO  # |L| = 2^23
+METRIC = ("Aurora prover constraints/sec at N=2^20 (value: the prover's hot-path calls, oracles resident in HBM; "
+          "e2e: whole aurora_snark_prover, host vectors); LDE GF-ops/sec vs HBM roofline")
+CONFIG = {"workload": "aurora_gf192_N2^20_rate1/8_fri_loc2_nonzk", "log_n": LOG_N, "codeword_dim": M, "field": "GF(2^192)",
+          "security": 128, "zk": False, "instance": "generate_r1cs_example(2^20, 31, 2^20-1), seed 0x9E3779B97F4A7C15 + rank",
+          "per_gpu": "one independent proof instance",
+          "l2_policy": "working set (5 x 192 MiB oracles + inputs) exceeds the 126 MB L2"}
 
 
 def workload(log_n=LOG_N):
-    """The star-call sequence of aurora_snark_prover (non-zk, rho=3, FRI localization 2), SURVEY.md §3.1."""
+    """The hot-path call sequence of aurora_snark_prover (non-zk, rho=3, FRI localization 2), SURVEY.md §3.1."""
     n, m = log_n, log_n + RHO
     N = 1 << n
     ffts = [(32, n), (N - 32, m), (N, m), (N, m), (N, m), (32, m), (N, m), (N, m), (N - 1, m)]
@@ -62,13 +68,6 @@ def algorithmic_bytes(ffts, iffts, folds, trees):
     b += sum(24 * (1 << k) * (1 + 2.0 ** -eta) for k, eta in folds)
     b += sum(24 * no * (1 << k) + 32 * (2 * ((1 << k) // cs) - 1) for no, k, cs in trees)
     return b
-
-
-def reference_field_ops(ffts, iffts, folds):
-    """SURVEY.md §8(d) canonical op counts of the reference algorithm (multiplications only)."""
-    mul = sum(1.5 * m * (1 << m) for _, m in ffts) + sum(1.5 * k * (1 << k) for k in iffts)
-    mul += sum((208 + 4 * (1 << eta)) * ((1 << k) >> eta) for k, eta in folds)
-    return mul
 
 
 class ClockSampler(threading.Thread):
@@ -101,12 +100,59 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+class _quiet_stdout:
+    """the reference printf()s its parameter blocks; keep stdout to the one JSON line"""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.devnull = os.open(os.devnull, os.O_WRONLY); self.saved = os.dup(1); os.dup2(self.devnull, 1)
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
+
+
+def ncu_traffic(kernel_substr="additive_tile_pass<(bool)0", grid=2048):
+    """DRAM bytes (read + write) of the dominant launch from the committed `ncu --set full` capture of bench/profile_kernels.py
+    lde (bench/ncu_families.sh): the longest launch of that kernel with that grid.  None when the capture is missing."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu", "ncu_lde_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ix = {h: i for i, h in enumerate(hdr)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = None
+        for r in rows[2:]:
+            if kernel_substr not in r[ix["Kernel Name"]] or int(float(r[ix["launch__grid_size"]])) != grid:
+                continue
+            dur = float(r[ix["gpu__time_duration.sum"]])
+            tot = sum(float(r[ix[k]]) * scale[units[ix[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            if best is None or dur > best[0]:
+                best = (dur, tot)
+        return (best[1], os.path.relpath(path, ROOT)) if best else (None, None)
+    except Exception:
+        return None, None
+
+
+def pin_rank_to_cores(local_rank, world):
+    """one disjoint slice of the host cores per rank: the reference's host code is single-threaded and every rank also drives
+    its own PCIe traffic — unpinned, 8 ranks migrate over the same cores (round-1 SCALE: e2e efficiency 0.856 at N = 8)"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            mine = cores[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, set(mine))
+            return mine
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args):
     import libiop_b200 as L
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = pin_rank_to_cores(local_rank, world)
     dist = None
     if world > 1:
         import torch
@@ -132,8 +178,7 @@ def run_gpu(args):
     # ---- device-resident state: 5 full-size oracles + inputs ----
     dom_L = L.Domain.standard(M)
     dom_of = {k: L.Domain.standard(k) for k in set([n for _, n in ffts] + iffts)}
-    # FRI domains L_i have non-standard bases (fri_ldt.tcc:310-338); the fold cost does not depend on the basis
-    # values, so synthetic random bases are used
+    # FRI domains L_i have non-standard bases (fri_ldt.tcc:310-338); the fold cost does not depend on the basis values
     fold_doms = {k: L.Domain.affine(rng.integers(0, 2**64, size=(k, 3), dtype=np.uint64),
                                     rng.integers(0, 2**64, size=3, dtype=np.uint64)) for k, _ in folds}
     coeff_in = rand_dev(1 << LOG_N)
@@ -145,7 +190,6 @@ def run_gpu(args):
         fri_bufs[k - eta] = dev.alloc(1 << (k - eta))
     node_bufs = [dev.alloc_bytes(32 * (2 * ((1 << k) // cs) - 1)) for _, k, cs in trees]
     x_chal = rng.integers(0, 2**64, size=3, dtype=np.uint64)
-    launches = [0]
 
     def step_resident():
         oi = 0
@@ -169,53 +213,7 @@ def run_gpu(args):
                 srcs = [fri_bufs[k]]
             dev.merkle_build_dev(srcs, 1 << k, cs, 1, nb)
 
-    # ---- e2e: host buffers through the C ABI (what the C++ adapter does per call) ----
     lib, ctx = dev.lib, dev.ctx
-    host_bytes = 24 * n_l
-    hp = lib.b200_host_alloc(ctx, C.c_size_t(host_bytes))
-    hin = lib.b200_host_alloc(ctx, C.c_size_t(24 << (LOG_N + 1)))
-    if not hp or not hin:
-        raise RuntimeError("pinned host allocation failed")
-    hp_p = C.cast(hp, C.POINTER(C.c_uint64)); hin_p = C.cast(hin, C.POINTER(C.c_uint64))
-    np.ctypeslib.as_array(hin_p, shape=(3 << (LOG_N + 1),))[:] = rng.integers(0, 2**64, size=3 << (LOG_N + 1), dtype=np.uint64)
-    h2d = [0]; d2h = [0]
-
-    CH = 1 << (LOG_N + 1)
-
-    def up(buf, n):
-        for off in range(0, n, CH):
-            k = min(CH, n - off)
-            dev._chk(lib.b200_upload(ctx, C.c_uint64(buf), C.c_size_t(off), hin_p, C.c_size_t(k))); h2d[0] += 24 * k
-
-    def down(buf, n):
-        dev._chk(lib.b200_download(ctx, hp_p, C.c_uint64(buf), C.c_size_t(0), C.c_size_t(n))); d2h[0] += 24 * n
-
-    def step_e2e():
-        h2d[0] = d2h[0] = 0
-        oi = 0
-        for nc, m in ffts:                       # FFT_over_field_subset(host vector, domain) -> host vector
-            up(coeff_in, nc)
-            out = oracles[oi % 5] if m == M else small_out
-            oi += (m == M)
-            dev.gf192_fft_dev(dom_L if m == M else dom_of[m], coeff_in, nc, out)
-            down(out, 1 << m)
-        for k in iffts:
-            up(evals_in, 1 << k)
-            dev.gf192_ifft_dev(dom_of[k], evals_in, small_out)
-            down(small_out, 1 << k)
-        cur, cur_n = oracles[4], n_l
-        for k, eta in folds:                     # evaluate_next_f_i_over_entire_domain(host vector) -> host vector
-            up(cur, cur_n)
-            dev.fri_fold_dev(1, None, fold_doms[k], eta, x_chal, cur, fri_bufs[k - eta])
-            cur, cur_n = fri_bufs[k - eta], 1 << (k - eta)
-            down(cur, cur_n)
-        for (no, k, cs), nb in zip(trees, node_bufs):   # merkle_tree::construct(host vectors) -> root to host
-            srcs = oracles[:4] if no == 4 else ([oracles[4]] if k == M else [fri_bufs[k]])
-            for s in srcs:
-                up(s, 1 << k)
-            dev.merkle_build_dev(srcs, 1 << k, cs, 1, nb)
-            root = (C.c_uint8 * 32)()
-            dev._chk(lib.b200_merkle_root(ctx, C.c_uint64(nb), root, C.c_size_t(32))); d2h[0] += 32
 
     def barrier():
         dev.sync()
@@ -227,24 +225,22 @@ def run_gpu(args):
             fn()
         barrier()
         dev.timer_start()
-        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
         ms = dev.timer_stop()
-        wall = (time.perf_counter() - t0) * 1e3
         barrier()
         if dist:
             import torch
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, wall
+        return ms
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, _ = timed(step_resident, args.steps, args.warmup)
-    # dominant kernel share: one 2^20 -> 2^23 LDE timed alone with events on the same stream
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    # the dominant kernel, timed live: one 2^20 -> 2^23 LDE with per-launch CUDA events on the context's stream
     for _ in range(2):
         dev.gf192_fft_dev(dom_L, coeff_in, 1 << LOG_N, oracles[0])
     dev.sync(); dev.timer_start()
@@ -252,15 +248,8 @@ def run_gpu(args):
     for _ in range(reps):
         dev.gf192_fft_dev(dom_L, coeff_in, 1 << LOG_N, oracles[0])
     lde_ms = dev.timer_stop() / reps
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_ms, _ = timed(step_e2e, e2e_steps, 1)
-    if rank == 0:
-        sampler.stop_flag.set(); sampler.join()
-
-    # launches of our kernels inside one step, counted by the library itself
     lib.b200_launch_count.restype = C.c_ulonglong
     dev.sync(); l0 = lib.b200_launch_count(ctx); step_resident(); dev.sync(); launches_per_step = lib.b200_launch_count(ctx) - l0
-    # per-launch CUDA-event timing of the tile passes of one LDE (events on the context's stream)
     lib.b200_profile_begin(ctx)
     dev.gf192_fft_dev(dom_L, coeff_in, 1 << LOG_N, oracles[0])
     pbuf = C.create_string_buffer(1 << 16)
@@ -270,16 +259,19 @@ def run_gpu(args):
     dom_label, dom_ms = max(bf_passes, key=lambda x: x[1]) if bf_passes else ("", float("nan"))
     fwd_ms = sum(t for lab, t in passes if "cosets=1" in lab)
     bwd_ms = sum(t for lab, t in passes if "cosets=8" in lab)
-
-    # final transcript gather (the only exchange between ranks): each rank's 11 Merkle roots -> rank 0
-    from libiop_b200 import sharding
-    roots = b"".join(dev.download_bytes(nb, 32) for nb in node_bufs)
-    all_roots = sharding.gather_transcripts(roots)
+    # the field multiplier's own rate, measured live (element-wise product of two resident 2^22-element vectors)
+    mul_n = 1 << 22
+    dev._chk(lib.b200_gf192_mul(ctx, C.c_uint64(oracles[1]), C.c_uint64(oracles[2]), C.c_uint64(oracles[3]), C.c_size_t(mul_n)))
+    dev.sync(); dev.timer_start()
+    for _ in range(3):
+        dev._chk(lib.b200_gf192_mul(ctx, C.c_uint64(oracles[1]), C.c_uint64(oracles[2]), C.c_uint64(oracles[3]), C.c_size_t(mul_n)))
+    mul_rate = 3 * mul_n / (dev.timer_stop() * 1e-3)
+    if rank == 0:
+        sampler.stop_flag.set(); sampler.join()
 
     ms_per_step = ms / args.steps
     N = 1 << LOG_N
     value = world * N / (ms_per_step * 1e-3)
-    e2e_value = world * N / (e2e_ms / e2e_steps * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -289,44 +281,42 @@ def run_gpu(args):
     lde_bytes = 24 * ((1 << LOG_N) + n_l)
     lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9
     # dominant kernel: one in-place butterfly tile pass over the 2^23-element oracle (8 stages, 8 cosets):
-    # algorithmic bytes per launch = read 24*2^23 + write 24*2^23
+    # algorithmic bytes per launch = read 24*2^23 + write 24*2^23 (2*24*2^m per pass over 2^m points)
     pass_bytes = 2 * 24 * n_l
     achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
     out = {
-        "metric": "Aurora prover constraints/sec at N=2^20 (hot path: LDE + FRI fold + Merkle); LDE GF-ops/sec vs HBM roofline",
-        "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "gf2^192 (carry-less u32 limbs) + u64 BLAKE2b", "data": "synthetic",
-        "config": {"workload": "aurora_gf192_N2^20_rate1/8_fri_loc2_nonzk: hot-path star calls of one proof "
-                               "(9 FFT, 10 IFFT, 10 FRI folds, 11 Merkle trees); elementwise virtual oracles, PoW and transcript "
-                               "assembly excluded", "log_n": LOG_N, "codeword_dim": M, "per_gpu": "one independent proof instance",
-                   "l2_policy": "working set (5 x 192 MiB oracles + inputs) exceeds the 126 MB L2"},
+        "config": dict(CONFIG),
+        "value_scope": "hot-path calls of one proof (9 FFT, 10 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
+                       "the whole prover is `e2e`",
         "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                     "traffic": 350.5e6, "traffic_source": "ncu --set full, profiles/r1_ncu_summary_v2.md (dram read+write of one butterfly pass)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": pass_bytes, "launch_ms": dom_ms, "launch_label": dom_label,
-                     "gf_mul_per_s_in_kernel": 8 * (n_l // 2) / (dom_ms * 1e-3), "gf_mul_peak_measured": 20.2e9,
-                     "frac_of_multiplier_peak": 8 * (n_l // 2) / (dom_ms * 1e-3) / 20.2e9,
+                     "gf_mul_per_s_in_kernel": 8 * (n_l // 2) / (dom_ms * 1e-3),
+                     "gf_mul_per_s_elementwise_kernel_live": mul_rate,
                      "lde": {"ms": lde_ms, "forward_half_ms": fwd_ms, "butterfly_half_ms": bwd_ms, "n_launches": len(passes),
                              "algorithmic_bytes": lde_bytes, "achieved_gbs": lde_gbs, "frac": lde_gbs / peak,
                              "gf_mul_per_s_reference_count": 1.5 * M * n_l / (lde_ms * 1e-3),
                              "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
-                     "note": "integer-pipe bound, not HBM bound: ~950 warp instructions (289 IMAD.WIDE) per GF(2^192) multiplication-butterfly, "
-                             "100 multiplications per 24-byte coefficient; see DESIGN.md 3.1-3.2 and profiles/r1_ncu_summary_v2.md"},
-        "hot_path_host_buffers": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
-                                  "ms_per_step": e2e_ms / e2e_steps,
-                                  "what": "the star calls alone through the host-buffer C ABI (upload, kernel, download per call)"},
-        "gpu_launches": None,
-        "transcript_gather": {"ranks": len(all_roots), "bytes_per_rank": len(roots),
-                              "distinct_instances": len(set(all_roots)) == len(all_roots)},
+                     "note": "integer-pipe bound, not HBM bound: ~950 instructions (289 IMAD.WIDE, quarter-rate) per GF(2^192) "
+                             "multiplication, 100 multiplications per 24-byte coefficient; DESIGN.md 3.1-3.2, profiles/r2_variants.md"},
+        "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary() if rank == 0 else None,
+        "host_cores_of_rank": cores,
     }
-    # launches per step: counted from the scheduler; measured with ncu in profiles/
-    out["gpu_launches"] = int(launches_per_step) * args.steps
-    out["gpu_launches_per_step"] = int(launches_per_step)
-    # e2e: the whole reference prover over host vectors with the library dropped in, one proof per rank
-    e2e = whole_prover_e2e(LOG_N, runs=max(1, min(args.steps, 3)), warmup=2, seed_offset=rank)
+    # free the synthetic state before the whole provers run
+    for b in oracles + [coeff_in, evals_in, small_out] + list(fri_bufs.values()):
+        dev.free(b)
+    dev.sync()
+
+    # ---- e2e: the whole reference prover over host vectors with the library dropped in, one proof per rank ----
+    e2e = whole_prover_e2e(LOG_N, runs=max(1, min(args.steps, 3)), warmup=2, seed_offset=rank, verify_last=(world > 1))
+    transcript = e2e.pop("_transcript", b"")
     if dist:
         import torch
         t = torch.tensor([e2e.get("prover_s", float("inf"))], device="cuda")
@@ -337,15 +327,22 @@ def run_gpu(args):
         secs = e2e.get("prover_s_max_over_ranks", e2e["prover_s"])
         e2e = dict({"value": world * N / secs, "unit": "constraints/s"}, **e2e)
     out["e2e"] = e2e
+    # final transcript gather (the only exchange between ranks): every rank's real proof transcript -> rank 0
+    from libiop_b200 import sharding
+    payload = bytes([1 if e2e.get("reference_verifier_accepts") else 0]) + transcript
+    gathered = sharding.gather_transcripts(payload)
+    out["transcript_gather"] = {"ranks": len(gathered), "bytes_per_rank": len(transcript),
+                                "distinct_instances": len(set(gathered)) == len(gathered),
+                                "accepted_by_reference_verifier": (sum(g[0] for g in gathered) if world > 1 else None),
+                                "sha256_per_rank": [hashlib.sha256(g[1:]).hexdigest()[:16] for g in gathered]}
+    if world >= 8 or args.config5:
+        out["config5"] = config5_leg(rank, world, dist)
     if rank == 0 and world == 1 and args.concurrency > 1:
-        # throughput with several prover processes sharing this GPU (the reference's host code is single-threaded and
-        # leaves the device idle 60 % of a proof): P independent instances proving back to back
+        # throughput with several prover processes sharing this GPU (the reference's host code is single-threaded and leaves the
+        # device idle most of a proof): P independent instances proving back to back
         out["e2e_throughput"] = whole_prover_throughput("dropin", LOG_N, runs=3, procs=args.concurrency)
-    if rank == 0 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(sample_log_n=args.cpu_sample_log_n)
-        out["cpu_baseline_hot_path"] = cpu_baseline_hot_path(sample_log_n=args.cpu_sample_log_n)
-    if rank == 0 and args.dropin_log_n:
-        out["whole_prover_dropin"] = whole_prover_dropin(args.dropin_log_n)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_sample_log_n)
     if rank == 0:
         print(json.dumps(out))
     dev.close()
@@ -353,56 +350,17 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def estimate_launches(ffts, iffts, folds, trees):
-    """Upper-level count of our kernels per step (tile passes per transform are scheduler dependent;
-    the ncu launch list under profiles/ is the evidence)."""
-    n = 0
-    for nc, m in ffts:
-        d = max(1, int(np.ceil(np.log2(max(nc, 2)))))
-        n += 3 * max(0, d - 12) + 1 + (3 if d > 12 else 1)
-    for k in iffts:
-        n += 3 * max(0, k - 12) + 1 + (3 if k > 12 else 1)
-    n += len(folds)
-    for no, k, cs in trees:
-        leaves = (1 << k) // cs
-        n += 1 + max(0, int(np.log2(max(leaves >> 8, 1))) - 11) + 1
-    return n
+def golden_fingerprint(prover, log_n, zk=False):
+    try:
+        for c in json.load(open(os.path.join(ROOT, "tests", "golden", "prover_fingerprints_config.json"))):
+            if (c["prover"], c["log_n"], c["zk"]) == (prover, log_n, zk):
+                return c
+    except Exception:
+        pass
+    return None
 
 
-def cpu_reference_times(sample_log_n, use_ref=True):
-    """Times the CPU implementation of the same star calls at N = 2^sample_log_n (bounded sample)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import Oracle, Reference, el, rand_elems, standard_basis
-    impl = Reference() if (use_ref and Reference.available()) else Oracle()
-    kind = "reference" if isinstance(impl, Reference) else "port"
-    rng = np.random.default_rng(5)
-    ffts, iffts, folds, trees = workload(sample_log_n)
-    t0 = time.perf_counter()
-    cache = {}
-    for nc, m in ffts:
-        c = rand_elems(rng, nc)
-        impl.additive_fft(c, m, standard_basis(m), el(1 << m))
-    for k in iffts:
-        impl.additive_ifft(rand_elems(rng, 1 << k), k, standard_basis(k), el(1 << k))
-    for k, eta in folds:
-        impl.fri_fold_additive(rand_elems(rng, 1 << k), k, rand_elems(rng, k), rand_elems(rng, 1)[0], eta, rand_elems(rng, 1)[0])
-    for no, k, cs in trees:
-        orc = [rand_elems(rng, 1 << k) for _ in range(no)]
-        impl.merkle_build(orc, cs, 1)
-    secs = time.perf_counter() - t0
-    return kind, secs
-
-
-class _quiet_stdout:
-    """the reference printf()s its parameter blocks; keep stdout to the one JSON line"""
-    def __enter__(self):
-        sys.stdout.flush()
-        self.devnull = os.open(os.devnull, os.O_WRONLY); self.saved = os.dup(1); os.dup2(self.devnull, 1)
-    def __exit__(self, *a):
-        os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
-
-
-def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0):
+def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0, verify_last=False):
     """The reference's aurora_snark_prover over host vectors with the B200 library dropped in (libiop_b200/prover.py):
     wall seconds of the prover call (instance generation excluded, get_transcript included — SURVEY.md §8d metric 1)."""
     try:
@@ -414,20 +372,58 @@ def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0):
             seed = prover.DEFAULT_SEED + seed_offset          # one independent instance per rank (BASELINE config 5: seeds s, s+1, ...)
             for _ in range(warmup):
                 p.aurora_gf192(log_n, seed=seed, verify=False)
-            s0 = p.device_stats()
-            times, dump = [], b""
-            for _ in range(runs):
-                secs, dump, _ = p.aurora_gf192(log_n, seed=seed, verify=False)
+            s0, l0 = p.device_stats(), p.lazy_stats()
+            times, dump, acc = [], b"", -1
+            for r in range(runs):
+                secs, dump, acc = p.aurora_gf192(log_n, seed=seed, verify=(verify_last and r == runs - 1))
                 times.append(secs)
-            s1 = p.device_stats()
-        import hashlib
+            s1, l1 = p.device_stats(), p.lazy_stats()
+        sha = hashlib.sha256(dump).hexdigest()
+        g = golden_fingerprint("aurora_gf192", log_n) if seed_offset == 0 else None
         return {"prover_s": float(np.median(times)), "prover_s_all": times,
                 "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // runs, "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // runs,
                 "gpu_launches_per_proof": (s1["launches"] - s0["launches"]) // runs,
-                "transcript_bytes": len(dump), "transcript_sha256": hashlib.sha256(dump).hexdigest(), "instance_seed": hex(seed),
+                "transcript_bytes": len(dump), "transcript_sha256": sha, "instance_seed": hex(seed),
+                "equals_cpu_reference_transcript": (sha == g["sha256"]) if g else None,
+                "cpu_reference_fingerprint": "tests/golden/prover_fingerprints_config.json (unmodified reference, CPU)" if g else None,
+                "reference_verifier_accepts": (acc == 1) if acc >= 0 else None,
                 "api": "aurora_snark_prover<gf192, binary_hash_digest>(constraint_system, primary_input, auxiliary_input, params), N=2^%d, "
-                       "rho=3, FRI localization 2, non-zk, host std::vector oracles" % log_n,
-                "residency": p.residency_stats(), "pinned_arena": p.arena_stats()}
+                       "rho=3, FRI localization 2, non-zk, host std::vector inputs" % log_n,
+                "device_resident_oracles": {"host_touched_vectors": (l1["faults"] - l0["faults"]) // runs,
+                                            "query_gathers": (l1["gathers"] - l0["gathers"]) // runs, "residency": p.residency_stats()},
+                "pinned_arena": p.arena_stats(), "_transcript": dump}
+    except Exception as e:
+        return {"unavailable": repr(e)}
+
+
+def config5_leg(rank, world, dist):
+    """BASELINE config 5: one Aurora N = 2^22 proof per GPU (seed + rank), verified by the reference verifier on its own rank,
+    transcripts gathered on rank 0; rank 0's transcript is compared with the CPU reference's fingerprint."""
+    try:
+        import psutil
+        need = 14 << 30
+        if psutil.virtual_memory().available < need * max(1, min(world, 8)):
+            return {"skipped": "not enough free host memory for %d provers at N = 2^22" % world}
+        from libiop_b200 import prover, sharding
+        with _quiet_stdout():
+            p = prover.DropinProver()
+            seed = prover.DEFAULT_SEED + rank
+            p.aurora_gf192(22, seed=seed, verify=False)
+            secs, dump, acc = p.aurora_gf192(22, seed=seed, verify=True)
+        if dist:
+            import torch
+            t = torch.tensor([secs], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs_max = float(t.item())
+        else:
+            secs_max = secs
+        gathered = sharding.gather_transcripts(bytes([1 if acc == 1 else 0]) + dump)
+        g = golden_fingerprint("aurora_gf192", 22)
+        return {"workload": "aurora_gf192_N2^22_rate1/8_fri_loc2_nonzk, one proof per GPU", "log_n": 22, "prover_s_max_over_ranks": secs_max,
+                "value": world * (1 << 22) / secs_max, "unit": "constraints/s",
+                "transcript_gather": {"ranks": len(gathered), "bytes_per_rank": len(dump), "accepted_by_reference_verifier": sum(x[0] for x in gathered),
+                                      "distinct_instances": len(set(gathered)) == len(gathered)},
+                "rank0_equals_cpu_reference_transcript": (hashlib.sha256(dump).hexdigest() == g["sha256"]) if (g and rank == 0) else None}
     except Exception as e:
         return {"unavailable": repr(e)}
 
@@ -446,97 +442,61 @@ def whole_prover_throughput(impl, log_n, runs, procs):
         return {"unavailable": repr(e)}
 
 
-def cpu_reference_prover(sample_log_n):
-    """The unmodified reference aurora_snark_prover on one host core (the reference is single-threaded)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import Reference
-    if not Reference.available():
-        return None
-    with _quiet_stdout():
-        secs, dump, _ = Reference().aurora_gf192(sample_log_n, verify=False)
-    return secs
-
-
-def cpu_baseline(sample_log_n=17):
-    secs = cpu_reference_prover(sample_log_n)
-    if secs is None:
-        return cpu_baseline_hot_path(sample_log_n)
-    return {"value": (1 << sample_log_n) / secs, "unit": "constraints/s", "cores": 1, "kind": "reference",
-            "sample": f"whole unmodified aurora_snark_prover at N=2^{sample_log_n} ({secs:.2f} s on 1 core; the reference has no threading); "
-                      f"same binary measured at N=2^20: 74.6 s = 14.05k constraints/s (profiles/r1_dropin_whole_prover_v2.jsonl)"}
-
-
-def cpu_baseline_hot_path(sample_log_n=14):
-    with _quiet_stdout():
-        kind, secs = cpu_reference_times(sample_log_n)
-    # extrapolate by the reference's own multiplication counts (O(N log N))
-    f_s, i_s, fo_s, _ = workload(sample_log_n)
-    f_f, i_f, fo_f, _ = workload(LOG_N)
-    scale = reference_field_ops(f_f, i_f, fo_f) / reference_field_ops(f_s, i_s, fo_s)
-    est_full = secs * scale
-    return {"value": (1 << LOG_N) / est_full, "unit": "constraints/s", "cores": 1, "kind": kind,
-            "sample": f"same star-call sequence at N=2^{sample_log_n} ({secs:.2f} s on 1 core incl. input generation), "
-                      f"extrapolated x{scale:.1f} by the reference's multiplication count to N=2^{LOG_N}",
-            "measured_constraints_per_s_at_sample": (1 << sample_log_n) / secs}
-
-
-def whole_prover_dropin(log_n):
-    """The UNMODIFIED reference aurora_snark_prover (host C++ of libiop) with this library dropped in under its three
-    hot-path headers (libiop_b200/lib/libiop_b200_dropin.so, built in the build container) next to the plain CPU reference
-    (oracle/_ref/libiopref.so) on the same instance: whole-prover seconds and transcript equality."""
+def cpu_baseline(sample_log_n=18):
+    """The unmodified reference aurora_snark_prover on one host core (the reference is single-threaded) on a bounded sample of the
+    workload, and the same instance through the drop-in with the transcripts compared byte for byte."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     try:
-        import hashlib
         from oracle_lib import Reference
         from libiop_b200 import prover
-        if not (Reference.available() and prover.available()):
-            return {"unavailable": "oracle/_ref/libiopref.so or libiop_b200/lib/libiop_b200_dropin.so was not built (need /root/reference at build time)"}
+        if not Reference.available():
+            return {"unavailable": "oracle/_ref/libiopref.so was not built (needs /root/reference at build time)"}
         with _quiet_stdout():
-            g, r = prover.DropinProver(), Reference()
-            g.aurora_gf192(log_n, verify=False)
-            gs, gd, acc = g.aurora_gf192(log_n, verify=True)
-            cs, cd, _ = r.aurora_gf192(log_n, verify=False)
-        return {"log_n": log_n, "cpu_reference_prover_s": cs, "dropin_prover_s": gs, "bit_exact_transcript": cd == gd,
-                "transcript_sha256": hashlib.sha256(gd).hexdigest(), "reference_verifier_accepts": acc == 1,
-                "cpu_constraints_per_s": (1 << log_n) / cs, "dropin_constraints_per_s": (1 << log_n) / gs,
-                "note": "same instance, CPU reference vs drop-in, transcripts compared byte for byte; host-side IOP code is the unmodified "
-                        "single-threaded reference in both"}
-    except Exception as e:  # never let the optional section break the bench line
+            cs, cd, _ = Reference().aurora_gf192(sample_log_n, verify=False)
+            g = prover.DropinProver()
+            g.aurora_gf192(sample_log_n, verify=False)
+            gs, gd, acc = g.aurora_gf192(sample_log_n, verify=True)
+        return {"value": (1 << sample_log_n) / cs, "unit": "constraints/s", "cores": 1, "kind": "reference",
+                "sample": f"whole unmodified aurora_snark_prover at N=2^{sample_log_n} ({cs:.2f} s on 1 core; the reference has no threading); "
+                          f"the full N=2^20 CPU run is the reference arm (bench.py --impl reference)",
+                "same_instance_through_dropin": {"prover_s": gs, "bit_exact_transcript": cd == gd, "reference_verifier_accepts": acc == 1,
+                                                 "transcript_sha256": hashlib.sha256(gd).hexdigest()}}
+    except Exception as e:
         return {"unavailable": repr(e)}
 
 
 def run_reference(args):
-    """Reference arm: the unmodified reference aurora_snark_prover on the host CPU, bounded sample N = 2^cpu_sample_log_n."""
+    """Reference arm: the unmodified reference aurora_snark_prover on the host CPU at the bench's own config (N = 2^20)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Reference
+    if not Reference.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libiopref.so was not built (needs /root/reference at build time)"}))
+        return
     t0 = time.perf_counter()
-    n = args.cpu_sample_log_n
-    if args.warmup:
-        cpu_reference_prover(max(10, n - 3))
-    times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        secs = cpu_reference_prover(n)
-        if secs is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libiopref.so was not built (needs /root/reference at build time)"}))
-            return
-        times.append(secs)
+    ref = Reference()
+    steps_run = max(1, min(args.steps, args.reference_proofs))
+    with _quiet_stdout():
+        for _ in range(args.warmup):                            # warm-up proofs on a small instance (~1 s each)
+            ref.aurora_gf192(14, verify=False)
+        times = ref.aurora_gf192_repeat(LOG_N, steps_run)       # one generated instance, `steps_run` proofs
     secs = float(np.median(times))
-    v = (1 << n) / secs
-    out = {"impl": "reference",
-           "metric": "Aurora prover constraints/sec at N=2^20 (hot path: LDE + FRI fold + Merkle); LDE GF-ops/sec vs HBM roofline",
-           "value": v, "unit": "constraints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    v = (1 << LOG_N) / secs
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "constraints/s", "n_gpus": args.gpus,
+           "steps": steps_run, "steps_requested": args.steps, "warmup": args.warmup, "warmup_what": "proofs at N=2^14",
            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "gf2^192 (PCLMULQDQ)", "data": "synthetic",
-           "config": {"workload": f"aurora_gf192 rate1/8 fri_loc2 nonzk: whole unmodified aurora_snark_prover on the host CPU, bounded sample N=2^{n} "
-                                  f"(N=2^20 takes 75 s per proof: 14.05k constraints/s, profiles/r1_dropin_whole_prover_v2.jsonl)",
-                      "log_n": n, "codeword_dim": n + RHO},
+           "dtype": "gf2^192 (PCLMULQDQ)", "data": "synthetic", "config": dict(CONFIG),
+           "value_scope": "whole unmodified aurora_snark_prover on the host CPU, one core (the reference has no threading); "
+                          "a proof takes ~75 s, so min(steps, %d) proofs are timed (warm-up proofs run at N=2^14)" % args.reference_proofs,
+           "prover_s_all": times,
            "cpu_baseline": {"value": v, "unit": "constraints/s", "cores": 1, "kind": "reference",
-                            "sample": f"whole aurora_snark_prover at N=2^{n}, median of {len(times)} runs, single thread (the reference has no threading)"},
+                            "sample": f"whole aurora_snark_prover at N=2^{LOG_N}, median of {steps_run} proof(s), single thread"},
            "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if args.concurrency > 1:
-        # the reference has no threading: one proof uses one core.  For a per-socket figure, one independent prover per core.
-        out["cpu_all_cores"] = whole_prover_throughput("cpu", n, runs=1, procs=os.cpu_count() or 1)
+    if args.concurrency > 1 and args.cpu_all_cores:
+        # the reference has no threading: one proof uses one core.  For a per-socket figure, one independent prover per core (N = 2^17).
+        out["cpu_all_cores"] = whole_prover_throughput("cpu", 17, runs=1, procs=os.cpu_count() or 1)
     out["wall_s"] = time.perf_counter() - t0
     print(json.dumps(out))
 
@@ -547,10 +507,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample-log-n", type=int, default=17)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-proofs", type=int, default=2, help="N=2^20 CPU proofs timed by the reference arm (75 s each)")
+    ap.add_argument("--cpu-all-cores", action="store_true", help="reference arm: also one CPU prover per core at N=2^17")
+    ap.add_argument("--config5", action="store_true", help="also prove BASELINE config 5 (N=2^22 per GPU); default at 8 GPUs")
     ap.add_argument("--concurrency", type=int, default=8, help="prover processes sharing the GPU in the e2e_throughput section (1 = skip)")
-    ap.add_argument("--dropin-log-n", type=int, default=18, help="side-by-side CPU reference vs drop-in prover with transcript comparison at this size (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,6 +22,13 @@ for v in "$@"; do
     s4)     build s4     -DB200_GF_SPACING=4 ;;
     s5)     build s5     -DB200_GF_SPACING=5 ;;
     t384)   build t384   -DB200_TILE_THREADS=384 -DB200_TILE_MINBLOCKS=2 -DB200_ILP=1 ;;
+    vec64)  build vec64  -DB200_TILE_VEC128=0 ;;          # round 2: 64-bit tile loads / stores (the round-1 kernel)
+    vec128) build vec128 -DB200_TILE_VEC128=1 ;;
+    blake0) build blake0 -DB200_BLAKE_IMAD=0 ;;           # round 2: BLAKE2b additions on the ALU pipe (round-1 kernel)
+    blake1) build blake1 -DB200_BLAKE_IMAD=1 ;;           #          c += d on the FMA pipe
+    blake2) build blake2 -DB200_BLAKE_IMAD=2 ;;           #          all additions on the FMA pipe
+    ntt11)  build ntt11  -DB200_NTT_TILE_BITS=11 ;;       # round 2: NTT tiles of 2^11 elements (4 CTAs per SM)
+    ntt12)  build ntt12  -DB200_NTT_TILE_BITS=12 ;;
   esac
 done
 wait

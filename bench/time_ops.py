@@ -36,6 +36,9 @@ e2 = [rnd(1 << m) for _ in range(3)]
 res["merkle 4x2^23 c2"] = t(lambda: dev.merkle_build_dev([e] + e2, 1 << m, 2, 1, nodes))
 res["merkle 1x2^23 c2"] = t(lambda: dev.merkle_build_dev([e], 1 << m, 2, 1, nodes))
 res["merkle 1x2^22 c4"] = t(lambda: dev.merkle_build_dev([e], 1 << 22, 4, 1, nodes))
+rows = [rnd(1 << 13) for _ in range(512)]
+nodes_l = dev.alloc_bytes(32 * (2 * (1 << 13) - 1))
+res["merkle ligero 512x2^13 c1"] = t(lambda: dev.merkle_build_dev(rows, 1 << 13, 1, 1, nodes_l))
 # prime-field NTT (BASELINE config 3 shape: 2^20 coefficients onto the 2^23 coset, and the 2^20 inverse)
 fp = L.FpParams.edwards_fr()
 gen = np.array(fp.to_mont(19), dtype=np.uint64)

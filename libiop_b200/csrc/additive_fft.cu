@@ -44,6 +44,9 @@ enum : uint32_t { OP_TW = 1, OP_TAY = 2, OP_BF = 3 };
 #define B200_TILE_MINBLOCKS 2
 #endif
 #define B200_SMEM_PAD 4 /* u64 words of padding between planes */
+#ifndef B200_TILE_VEC128
+#define B200_TILE_VEC128 1 /* 128-bit tile loads / stores (LDG.E.128 / STG.E.128): measured against the 64-bit variant, profiles/r2_variants.md */
+#endif
 #define B200_SUM_CHUNKS 4 /* 8-bit chunks of the butterfly index: stages up to 2^32 */
 
 struct PassParams {
@@ -127,7 +130,7 @@ __device__ __forceinline__ uint32_t insert_zero(uint32_t k, uint32_t pos)
 template <bool INV, int NT, int MB>
 __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
 {
-    extern __shared__ uint64_t smem[];
+    extern __shared__ __align__(16) uint64_t smem[];
 
     const uint32_t mainb = P.hi - P.lo;
     const uint32_t tbw = mainb + P.c + P.ctop;              /* index bits of one coset inside the tile */
@@ -167,6 +170,23 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
         return w | (mid << P.c) | (u << P.lo) | (top << P.hi) | (P.ctop ? (tbv << (d - P.ctop)) : 0u);
     };
 
+#if B200_TILE_VEC128
+    /* 128-bit variant: a thread moves two consecutive elements (48 bytes) with three 16-byte loads and three 16-byte
+       shared-memory stores.  Index bit 0 of the tile is index bit 0 of the array in every tile shape, so elements L and L+1
+       (L even) are adjacent in memory unless the load is the bit-reversing gather. */
+    const bool vec_in = P.bitrev != 1 && tbw >= 1 && ((reinterpret_cast<uintptr_t>(P.src) & 15u) == 0);
+    if (vec_in) {
+        for (uint32_t L = 2 * threadIdx.x; L < T; L += 2 * blockDim.x) {
+            const uint32_t i = global_index(L);
+            const size_t cofs = shared_src ? 0 : ((size_t)((coset_base + (L >> tbw)) >> P.src_coset_shr) << P.src_coset_stride_log);
+            const uint4 *q = reinterpret_cast<const uint4 *>(P.src + cofs + i);
+            const uint4 x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);     /* a0 b0 | c0 a1 | b1 c1 (64-bit words) */
+            *reinterpret_cast<uint4 *>(t.p0 + L) = make_uint4(x.x, x.y, y.z, y.w);
+            *reinterpret_cast<uint4 *>(t.p1 + L) = make_uint4(x.z, x.w, z.x, z.y);
+            *reinterpret_cast<uint4 *>(t.p2 + L) = make_uint4(y.x, y.y, z.z, z.w);
+        }
+    } else
+#endif
     for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
@@ -255,6 +275,21 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
     __syncthreads();
 
     uint64_t *out = reinterpret_cast<uint64_t *>(P.dst);
+#if B200_TILE_VEC128
+    const bool vec_out = P.bitrev != 2 && tbw >= 1 && ((reinterpret_cast<uintptr_t>(P.dst) & 15u) == 0);
+    if (vec_out) {
+        for (uint32_t L = 2 * threadIdx.x; L < T; L += 2 * blockDim.x) {
+            const uint32_t i = global_index(L);
+            const uint4 a = *reinterpret_cast<const uint4 *>(t.p0 + L), b = *reinterpret_cast<const uint4 *>(t.p1 + L),
+                        c2 = *reinterpret_cast<const uint4 *>(t.p2 + L);
+            uint4 *q = reinterpret_cast<uint4 *>(out + (((size_t)(coset_base + (L >> tbw)) << d) + i) * 3);
+            q[0] = make_uint4(a.x, a.y, b.x, b.y);
+            q[1] = make_uint4(c2.x, c2.y, a.z, a.w);
+            q[2] = make_uint4(b.z, b.w, c2.z, c2.w);
+        }
+        return;
+    }
+#endif
     for (uint32_t L = threadIdx.x; L < T; L += blockDim.x) {
         const uint32_t i = global_index(L);
         const uint32_t a = (P.bitrev == 2) ? (__brev(i) >> (32 - d)) : i;

@@ -54,12 +54,46 @@ __device__ __forceinline__ uint64_t rotr16(uint64_t x)
     return (uint64_t)__byte_perm(lo, hi, 0x5432) | ((uint64_t)__byte_perm(lo, hi, 0x1076) << 32);
 }
 
-#define BLAKE_G(a, b, c, d, x, y)                  \
-    do {                                           \
-        a = a + b + (x); d = rotr32x(d ^ a);       \
-        c = c + d;       b = rotr24(b ^ c);        \
-        a = a + b + (y); d = rotr16(d ^ a);        \
-        c = c + d;       b = rotr64(b ^ c, 63);    \
+/* BLAKE2b is 64-bit add / xor / rotate: on this SM all three run on the ALU pipe (IADD3 + IADD3.X, LOP3, SHF/PRMT), which the
+   hash kernels saturate (ncu, round 2: pow_grind_kernel ALU pipe 97.6 %, FMA pipe 9.6 %).  B200_BLAKE_IMAD moves 64-bit
+   additions to the idle FMA pipe: x + y = mad.wide.u32(y.lo, 1, x) then hi += y.hi as mad.lo.u32, with the multiplier 1
+   read from constant memory so that ptxas keeps the multiply-adds (IMAD.WIDE.U32 + IMAD).  Level 1: the two c += d of each
+   G; level 2: all four additions.  Measured in profiles/r2_variants.md. */
+#ifndef B200_BLAKE_IMAD
+#define B200_BLAKE_IMAD 0
+#endif
+__constant__ uint32_t c_blake_one = 1;
+__device__ __forceinline__ uint64_t add64_fma(uint64_t x, uint64_t y, uint32_t one)
+{
+    uint64_t r;
+    asm("{\n\t.reg .u32 ylo, yhi, tlo, thi, rhi;\n\t.reg .u64 t;\n\t"
+        "mov.b64 {ylo, yhi}, %2;\n\t"
+        "mad.wide.u32 t, ylo, %3, %1;\n\t"
+        "mov.b64 {tlo, thi}, t;\n\t"
+        "mad.lo.u32 rhi, yhi, %3, thi;\n\t"
+        "mov.b64 %0, {tlo, rhi};\n\t}"
+        : "=l"(r) : "l"(x), "l"(y), "r"(one));
+    return r;
+}
+#if B200_BLAKE_IMAD >= 2
+#define BLAKE_ADD3(a, b, x) add64_fma(add64_fma(a, b, blake_one), (x), blake_one)
+#else
+#define BLAKE_ADD3(a, b, x) ((a) + (b) + (x))
+#endif
+#if B200_BLAKE_IMAD >= 1
+#define BLAKE_ADD2(c, d) add64_fma(c, d, blake_one)
+#define BLAKE_ONE_DECL const uint32_t blake_one = c_blake_one;
+#else
+#define BLAKE_ADD2(c, d) ((c) + (d))
+#define BLAKE_ONE_DECL
+#endif
+
+#define BLAKE_G(a, b, c, d, x, y)                              \
+    do {                                                       \
+        a = BLAKE_ADD3(a, b, x); d = rotr32x(d ^ a);           \
+        c = BLAKE_ADD2(c, d);    b = rotr24(b ^ c);            \
+        a = BLAKE_ADD3(a, b, y); d = rotr16(d ^ a);            \
+        c = BLAKE_ADD2(c, d);    b = rotr64(b ^ c, 63);        \
     } while (0)
 
 #define BLAKE_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
@@ -77,6 +111,7 @@ __device__ __forceinline__ uint64_t rotr16(uint64_t x)
 /* one BLAKE2b compression; m[] must be indexable with compile-time constants (registers) */
 __device__ __forceinline__ void blake2b_compress(uint64_t h[8], const uint64_t m[16], uint64_t t, bool last)
 {
+    BLAKE_ONE_DECL
     uint64_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
     uint64_t v8 = BLAKE_IV0, v9 = BLAKE_IV1, v10 = BLAKE_IV2, v11 = BLAKE_IV3;
     uint64_t v12 = BLAKE_IV4 ^ t, v13 = BLAKE_IV5, v14 = last ? ~BLAKE_IV6 : BLAKE_IV6, v15 = BLAKE_IV7;
@@ -377,6 +412,7 @@ __device__ __forceinline__ uint64_t quad_shfl(uint64_t v, int src_lane)
 __device__ __forceinline__ void quad_compress(uint64_t &h0, uint64_t &h1, const uint64_t *msg, const uint32_t sig[12], uint32_t q,
                                               uint64_t t, bool last)
 {
+    BLAKE_ONE_DECL
     uint64_t a = h0, b = h1;
     uint64_t c = q == 0 ? BLAKE_IV0 : q == 1 ? BLAKE_IV1 : q == 2 ? BLAKE_IV2 : BLAKE_IV3;
     uint64_t d = q == 0 ? (BLAKE_IV4 ^ t) : q == 1 ? BLAKE_IV5 : q == 2 ? (last ? ~BLAKE_IV6 : BLAKE_IV6) : BLAKE_IV7;

@@ -24,8 +24,12 @@ namespace b200 {
 struct NttPlan {
     uint32_t logn = 0;
     fp192 g, ginv;
-    fp192 *w = nullptr;     /* g^k,  k < n/2 */
-    fp192 *winv = nullptr;  /* g^-k, k < n/2 */
+    /* Twiddles, one contiguous table per butterfly level: level s (half-size 2^s) uses w_s^j, j < 2^s, with w_s the
+       primitive 2^(s+1)-th root g^(2^(logn-1-s)); table s starts at entry 2^s - 1 (2^logn - 1 entries in all).  A single
+       table g^k read with stride 2^(logn-1-s) costs a separate 32-byte sector per butterfly at every level but the last
+       (ncu, round 2: 589 MB of DRAM reads for a pass whose data is 192 MB); per-level tables are read in runs. */
+    fp192 *w = nullptr;
+    fp192 *winv = nullptr;
     ~NttPlan() { cudaFree(w); cudaFree(winv); }
 };
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) ntt_tile_pass(const NttPassParams P)
             const uint32_t j = global_index(L0) & ((1u << s) - 1u);
             const fp192 a = t.ld(L0);
             fp192 b = t.ld(L1);
-            if (j != 0) b = fp_mul(b, ldg_fp(P.w + ((size_t)j << (P.logn - 1 - s))), P.fp);
+            if (j != 0) b = fp_mul(b, ldg_fp(P.w + (((size_t)1 << s) - 1) + j), P.fp);
             t.st(L0, fp_add(a, b, P.fp));
             t.st(L1, fp_sub(a, b, P.fp));
         }
@@ -186,16 +190,21 @@ static int get_ntt_plan(b200_ctx *c, const b200_fp_params *P, const b200_domain 
         c->ntt_plans[key] = pl;
     }
     const uint32_t logn = D->dim;
-    const size_t half = logn ? ((size_t)1 << (logn - 1)) : 1;
     fp192 **slot = inverse ? &pl->winv : &pl->w;
     if (!*slot) {
         fp192 *tab = nullptr;
-        if (cudaMalloc(&tab, half * sizeof(fp192)) != cudaSuccess) {
+        const size_t entries = ((size_t)1 << logn);           /* sum over levels of 2^s, rounded up */
+        if (cudaMalloc(&tab, entries * sizeof(fp192)) != cudaSuccess) {
             cudaGetLastError();
-            return set_err(c, B200_ERR_NOMEM, "cannot allocate NTT twiddle table");
+            return set_err(c, B200_ERR_NOMEM, "cannot allocate NTT twiddle tables");
         }
-        int rc = build_fp_power_table(c, tab, fp_one(fp), inverse ? pl->ginv : pl->g, logn ? logn - 1 : 0, fp);
-        if (rc) { cudaFree(tab); return rc; }
+        /* level s: powers of w_s = g^(2^(logn-1-s)); computed from the top level down by squaring the root */
+        fp192 root = inverse ? pl->ginv : pl->g;               /* w_(logn-1) = g */
+        for (uint32_t s = logn; s-- > 0;) {
+            int rc = build_fp_power_table(c, tab + (((size_t)1 << s) - 1), fp_one(fp), root, s, fp);
+            if (rc) { cudaFree(tab); return rc; }
+            root = fp_mul(root, root, fp);
+        }
         B200_CUDA(c, cudaStreamSynchronize(c->stream));
         *slot = tab;
     }
@@ -203,7 +212,10 @@ static int get_ntt_plan(b200_ctx *c, const b200_fp_params *P, const b200_domain 
     return 0;
 }
 
-static const uint32_t kNttTileBits = 12;
+#ifndef B200_NTT_TILE_BITS
+#define B200_NTT_TILE_BITS 11   /* 48 KiB tiles, 4 CTAs per SM: 2^20 -> 2^23 in 1.92 ms vs 2.14 ms with 2^12 (profiles/r2_variants.md) */
+#endif
+static const uint32_t kNttTileBits = B200_NTT_TILE_BITS;
 static const uint32_t kNttCoalesceBits = 4;
 
 static int run_stages(b200_ctx *c, NttPassParams P, uint32_t logn, uint32_t first, const fp192 *src, fp192 *dst,
