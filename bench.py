@@ -54,16 +54,20 @@ def workload(log_n=LOG_N):
     """The hot-path call sequence of aurora_snark_prover (non-zk, rho=3, FRI localization 2), SURVEY.md §3.1."""
     n, m = log_n, log_n + RHO
     N = 1 << n
-    ffts = [(32, n), (N - 32, m), (N, m), (N, m), (N, m), (32, m), (N, m), (N, m), (N - 1, m)]
-    iffts = [5, n, n, n, n, n, n, 5, n + 1, 4]
+    # f_1v over the variable domain, f_w, f_1v over L (f_z), p_alpha' and p_alpha_ABC over L, h
+    ffts = [(32, n), (N - 32, m), (32, m), (N, m), (N, m), (N - 1, m)]
+    # f_Az, f_Bz, f_Cz: evaluations over H straight to L (b200_gf192_lde; the reference's IFFT(H) + FFT(L), r1cs_rs_iop.tcc:449-479)
+    ldes = [(n, m)] * 3
+    # f_1v, f_w, p_alpha_ABC, p_alpha', f_1v again (f_z), sumcheck's combined f, the final FRI polynomial
+    iffts = [5, n, n, n, 5, n + 1, 4]
     folds = [(m, 1)] + [(k, 2) for k in range(m - 1, 4, -2)]        # (dim of L_i, eta)
     trees = [(4, m, 2), (1, m, 2)] + [(1, k, 4) for k in range(m - 1, 4, -2)]   # (n_oracles, dim, coset)
-    return ffts, iffts, folds, trees
+    return ffts, ldes, iffts, folds, trees
 
 
-def algorithmic_bytes(ffts, iffts, folds, trees):
-    """FFT 24*(n_coeffs + 2^m); IFFT 48*2^k; fold 24*|L_i|*(1+2^-eta); Merkle 24*n_or*|L| + 32*(2*leaves-1)."""
-    b = sum(24 * (nc + (1 << m)) for nc, m in ffts)
+def algorithmic_bytes(ffts, ldes, iffts, folds, trees):
+    """FFT / LDE 24*(n_in + 2^m); IFFT 48*2^k; fold 24*|L_i|*(1+2^-eta); Merkle 24*n_or*|L| + 32*(2*leaves-1)."""
+    b = sum(24 * (nc + (1 << m)) for nc, m in ffts) + sum(24 * ((1 << d) + (1 << m)) for d, m in ldes)
     b += sum(48 * (1 << k) for k in iffts)
     b += sum(24 * (1 << k) * (1 + 2.0 ** -eta) for k, eta in folds)
     b += sum(24 * no * (1 << k) + 32 * (2 * ((1 << k) // cs) - 1) for no, k, cs in trees)
@@ -162,7 +166,7 @@ def run_gpu(args):
         dist = dist_mod
 
     dev = L.B200(local_rank)
-    ffts, iffts, folds, trees = workload()
+    ffts, ldes, iffts, folds, trees = workload()
     rng = np.random.default_rng(1234 + rank)           # independent proof instance per GPU
     n_l = 1 << M
 
@@ -198,6 +202,8 @@ def run_gpu(args):
                 dev.gf192_fft_dev(dom_L, coeff_in, nc, oracles[oi % 5]); oi += 1
             else:
                 dev.gf192_fft_dev(dom_of[m], coeff_in, nc, small_out)
+        for d, m in ldes:
+            dev.gf192_lde_dev(dom_of[d], dom_L, evals_in, oracles[oi % 5]); oi += 1
         for k in iffts:
             dev.gf192_ifft_dev(dom_of[k], evals_in, small_out)
         cur = oracles[4]
@@ -290,7 +296,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "gf2^192 (carry-less u32 limbs) + u64 BLAKE2b", "data": "synthetic",
         "config": dict(CONFIG),
-        "value_scope": "hot-path calls of one proof (9 FFT, 10 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
+        "value_scope": "hot-path calls of one proof (6 FFT, 3 fused LDE, 7 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
                        "the whole prover is `e2e`",
         "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -305,6 +311,7 @@ def run_gpu(args):
                              "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
                      "note": "integer-pipe bound, not HBM bound: ~950 instructions (289 IMAD.WIDE, quarter-rate) per GF(2^192) "
                              "multiplication, 100 multiplications per 24-byte coefficient; DESIGN.md 3.1-3.2, profiles/r2_variants.md"},
+        "algorithmic_bytes_per_step": algorithmic_bytes(ffts, ldes, iffts, folds, trees),
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary() if rank == 0 else None,
         "host_cores_of_rank": cores,

@@ -1,6 +1,6 @@
 """One invocation of ONE kernel family at the benchmark's sizes, for ncu (`--set full`, one family per run so that the
 capture stays small).  Usage: python bench/profile_kernels.py <family> [reps]
-families: lde ifft ntt intt fold fold_fp merkle4 merkle1 merkle_ligero squeeze pow lincomb mul_add inv subset_sum"""
+families: lde lde_fused ifft ntt intt fold fold_fp merkle4 merkle1 merkle_ligero squeeze pow lincomb mul_add inv subset_sum"""
 import ctypes as C
 import os
 import sys
@@ -29,6 +29,8 @@ x = rng.integers(0, 2**64, size=3, dtype=np.uint64)
 for _ in range(reps):
     if fam == "lde":
         dev.gf192_fft_dev(L.Domain.standard(m), rnd(1 << n), 1 << n, dev.alloc(1 << m))
+    elif fam == "lde_fused":
+        dev.gf192_lde_dev(L.Domain.standard(n), L.Domain.standard(m), rnd(1 << n), dev.alloc(1 << m))
     elif fam == "ifft":
         dev.gf192_ifft_dev(L.Domain.standard(n), rnd(1 << n), dev.alloc(1 << n))
     elif fam in ("ntt", "intt", "fold_fp"):

@@ -22,6 +22,7 @@ def t(fn, reps=reps):
 dom = L.Domain.standard(m)
 res = {}
 res["fft 2^20->2^23"] = t(lambda: dev.gf192_fft_dev(dom, c, 1 << n, e))
+res["lde 2^20->2^23 fused (evals over H -> evals over L)"] = t(lambda: dev.gf192_lde_dev(L.Domain.standard(n), dom, c, e))
 res["fft 2^20->2^20"] = t(lambda: dev.gf192_fft_dev(L.Domain.standard(n), c, 1 << n, o))
 res["fft 32->2^23"] = t(lambda: dev.gf192_fft_dev(dom, c, 32, e))
 res["ifft 2^20"] = t(lambda: dev.gf192_ifft_dev(L.Domain.standard(n), c, o))

@@ -113,6 +113,13 @@ int b200_gf192_ifft(b200_ctx *, const b200_domain *H, b200_buf evals, b200_buf c
  * Row r reads coeffs + r * n_coeffs (evals + r * 2^dim) and writes evals_out + r * 2^dim (coeffs_out + r * 2^dim). */
 int b200_gf192_fft_batch(b200_ctx *, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, size_t batch, b200_buf evals_out);
 int b200_gf192_ifft_batch(b200_ctx *, const b200_domain *H, b200_buf evals, size_t batch, b200_buf coeffs_out);
+/* Fused low-degree extension: the evaluations over H (2^H->dim) of a polynomial of degree < |H| -> its evaluations over L,
+ * i.e. IFFT_over_field_subset(evals, H) followed by FFT_over_field_subset(coefficients, L) as the prover does for every
+ * witness-derived oracle (protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc:449-479; Ligero's row encodings, ligero.tcc:293-331)
+ * without forming the coefficients: the basis-only halves of the two transforms cancel.  Requires L->basis[0 .. H->dim) ==
+ * H->basis (B200_ERR_INVALID otherwise: use the two calls).  Row r of a batch reads evals + r * 2^H->dim, writes out + r * 2^L->dim. */
+int b200_gf192_lde(b200_ctx *, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf evals_out);
+int b200_gf192_lde_batch(b200_ctx *, const b200_domain *H, const b200_domain *L, b200_buf evals, size_t batch, b200_buf evals_out);
 /* element-wise helpers (gf192::operator*=, inverse: gf192.cpp:72-184, 245-288) */
 int b200_gf192_mul(b200_ctx *, b200_buf out, b200_buf a, b200_buf b, size_t n);
 int b200_gf192_inv(b200_ctx *, b200_buf out, b200_buf a, size_t n);

@@ -202,6 +202,22 @@ class B200:
     def gf192_ifft_dev(self, dom, evals, out):
         self._chk(self.lib.b200_gf192_ifft(self.ctx, C.byref(dom.c), C.c_uint64(evals), C.c_uint64(out)))
 
+    def gf192_lde_dev(self, dom_h, dom_l, evals, out, batch=1):
+        self._chk(self.lib.b200_gf192_lde_batch(self.ctx, C.byref(dom_h.c), C.byref(dom_l.c), C.c_uint64(evals), C.c_size_t(batch), C.c_uint64(out)))
+
+    def gf192_lde(self, dom_h, dom_l, rows):
+        """fused IFFT over H + FFT over L of every row: rows (batch, 2^dim_H, 3) -> (batch, 2^dim_L, 3)"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        rows = rows.reshape(-1, 1 << dom_h.dim, 3)
+        batch, nl = rows.shape[0], 1 << dom_l.dim
+        a = self.upload(rows.reshape(-1, 3)) if rows.size else self.alloc(1)
+        o = self.alloc(max(batch * nl, 1))
+        try:
+            self.gf192_lde_dev(dom_h, dom_l, a, o, batch)
+            return self.download(o, batch * nl).reshape(batch, nl, 3)
+        finally:
+            self.free(a); self.free(o)
+
     def fp_ntt_dev(self, fp, dom, coeffs, n_coeffs, out):
         self._chk(self.lib.b200_fp_ntt(self.ctx, C.byref(fp), C.byref(dom.c), C.c_uint64(coeffs), C.c_size_t(n_coeffs), C.c_uint64(out)))
 

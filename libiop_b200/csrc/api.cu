@@ -288,6 +288,16 @@ int b200_gf192_ifft_batch(b200_ctx *c, const b200_domain *H, b200_buf evals, siz
     B200_TRACE_SCOPE(c, "gf192_ifft_batch", batch << H->dim);
     return additive_ifft(c, H, evals, coeffs_out, batch);
 }
+int b200_gf192_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf evals_out)
+{
+    B200_TRACE_SCOPE(c, "gf192_lde", (size_t)1 << (L ? L->dim : 0));
+    return additive_lde(c, H, L, evals, evals_out, 1);
+}
+int b200_gf192_lde_batch(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, size_t batch, b200_buf evals_out)
+{
+    B200_TRACE_SCOPE(c, "gf192_lde_batch", batch << (L ? L->dim : 0));
+    return additive_lde(c, H, L, evals, evals_out, batch);
+}
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { return gf192_mul_vec(c, out, a, b, n); }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
 {

@@ -19,6 +19,36 @@ inline std::vector<FIELD> create_fw_prime_evals(const std::vector<FIELD> &f_1v_o
 B200_FOR_EACH_FIELD(B200_FW_PRIME_OVERLOAD)
 #undef B200_FW_PRIME_OVERLOAD
 
+/* encoded_aurora_protocol::compute_fprime_ABCz_over_codeword_domain (r1cs_rs_iop.tcc:449-479): Az, Bz, Cz over the constraint
+   domain -> f_Az, f_Bz, f_Cz over the codeword domain.  The reference interpolates each (IFFT over H), adds Z_H * R in the
+   zero-knowledge case, and evaluates over L (FFT).  Without zero knowledge nothing happens between the two transforms, and
+   the B200 library extends evaluations over H straight to L (b200_gf192_lde: the basis-only halves of the two transforms
+   cancel) — 3 of the proof's 8 codeword-size LDEs, with no coefficient vector crossing PCIe.  The zero-knowledge case keeps
+   the reference's three steps. */
+#define B200_ABCZ_SPECIALISE(FIELD)                                                                                        \
+template<> inline void encoded_aurora_protocol<FIELD>::compute_fprime_ABCz_over_codeword_domain(                           \
+    std::vector<FIELD> &Az, std::vector<FIELD> &Bz, std::vector<FIELD> &Cz)                                                \
+{                                                                                                                          \
+    if (!this->params_.make_zk()) {                                                                                        \
+        this->fprime_Az_over_codeword_domain_ = libiop_b200::LDE_over_field_subsets<FIELD>(Az, this->constraint_domain_, this->codeword_domain_); \
+        this->fprime_Bz_over_codeword_domain_ = libiop_b200::LDE_over_field_subsets<FIELD>(Bz, this->constraint_domain_, this->codeword_domain_); \
+        this->fprime_Cz_over_codeword_domain_ = libiop_b200::LDE_over_field_subsets<FIELD>(Cz, this->constraint_domain_, this->codeword_domain_); \
+        return;                                                                                                            \
+    }                                                                                                                      \
+    polynomial<FIELD> f_Az(IFFT_over_field_subset<FIELD>(Az, this->constraint_domain_));                                   \
+    polynomial<FIELD> f_Bz(IFFT_over_field_subset<FIELD>(Bz, this->constraint_domain_));                                   \
+    polynomial<FIELD> f_Cz(IFFT_over_field_subset<FIELD>(Cz, this->constraint_domain_));                                   \
+    const vanishing_polynomial<FIELD> constraint_vp(this->constraint_domain_);                                             \
+    f_Az += constraint_vp * this->R_Az_;                                                                                   \
+    f_Bz += constraint_vp * this->R_Bz_;                                                                                   \
+    f_Cz += constraint_vp * this->R_Cz_;                                                                                   \
+    this->fprime_Az_over_codeword_domain_ = FFT_over_field_subset<FIELD>(f_Az.coefficients(), this->codeword_domain_);     \
+    this->fprime_Bz_over_codeword_domain_ = FFT_over_field_subset<FIELD>(f_Bz.coefficients(), this->codeword_domain_);     \
+    this->fprime_Cz_over_codeword_domain_ = FFT_over_field_subset<FIELD>(f_Cz.coefficients(), this->codeword_domain_);     \
+}
+B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
+#undef B200_ABCZ_SPECIALISE
+
 #define B200_FZ_SPECIALISE(FIELD)                                                                                          \
 template<> inline std::shared_ptr<std::vector<FIELD>> fz_virtual_oracle<FIELD>::evaluated_contents(                        \
     const std::vector<std::shared_ptr<std::vector<FIELD>>> &constituent_oracle_evaluations) const                          \

@@ -70,6 +70,38 @@ void IFFT_over_field_subset_device(const device_buffer &evals, const DomainT &do
     throw_status(context(), rc);
 }
 
+/* Fused low-degree extension (b200_gf192_lde): evaluations over H -> evaluations over L, equal to
+   FFT_over_field_subset(IFFT_over_field_subset(evals, H), L).  Returns false — nothing done — when the pair of domains does
+   not qualify (prime field, or L does not extend H's basis) and the caller should run the two transforms. */
+template<typename FieldT, typename DomainT>
+bool LDE_over_field_subsets_device(const device_buffer &evals, const DomainT &H, const DomainT &L, device_buffer &evals_out)
+{
+    if (field_traits<FieldT>::kind != B200_FIELD_GF192) return false;
+    if ((int)H.type() != B200_DOMAIN_AFFINE_SUBSPACE || (int)L.type() != B200_DOMAIN_AFFINE_SUBSPACE) return false;
+    if (H.dimension() > L.dimension()) return false;
+    const std::vector<FieldT> &bh = H.basis(), &bl = L.basis();
+    for (std::size_t k = 0; k < bh.size(); ++k)
+        if (!(bh[k] == bl[k])) return false;
+    std::vector<uint64_t> store_h, store_l;
+    const b200_domain dh = make_domain<FieldT>(H, store_h), dl = make_domain<FieldT>(L, store_l);
+    throw_status(context(), b200_gf192_lde(context(), &dh, &dl, evals.get(), evals_out.get()));
+    return true;
+}
+/* host vectors in, a (device-resident) codeword vector out */
+template<typename FieldT, typename DomainT>
+std::vector<FieldT> LDE_over_field_subsets(const std::vector<FieldT> &evals, const DomainT &H, const DomainT &L)
+{
+    if (evals.size() != H.num_elements()) throw std::invalid_argument("LDE_over_field_subsets: evaluation vector does not match the domain");
+    const device_view in(evals);
+    device_buffer out(L.num_elements());
+    if (!LDE_over_field_subsets_device<FieldT>(in.buf(), H, L, out)) {
+        device_buffer coeffs(H.num_elements());
+        IFFT_over_field_subset_device<FieldT>(in.buf(), H, coeffs);
+        FFT_over_field_subset_device<FieldT>(coeffs, H.num_elements(), L, out);
+    }
+    return make_lazy_vector<FieldT>(std::move(out), L.num_elements());
+}
+
 /* The reference's signatures take the vectors BY VALUE (fft.hpp:62-88); the implementations below take references so that a
    caller that already holds the vector (the drop-in dispatchers, which received the reference's by-value copy) does not
    pay a second copy of up to 192 MiB.  The by-value overloads with the reference's names forward to them. */

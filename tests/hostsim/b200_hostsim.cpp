@@ -180,6 +180,23 @@ int b200_gf192_ifft_batch(b200_ctx *c, const b200_domain *H, b200_buf evals, siz
     return 0;
 }
 int b200_gf192_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out) { return b200_gf192_ifft_batch(c, H, evals, 1, out); }
+int b200_gf192_lde_batch(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, size_t batch, b200_buf out)
+{
+    if (check_affine(c, H, "fused extension") || check_affine(c, L, "fused extension")) return B200_ERR_INVALID;
+    if (H->dim > L->dim || (H->dim && std::memcmp(H->basis, L->basis, (size_t)H->dim * 24) != 0))
+        return fail(c, B200_ERR_INVALID, "the codeword domain does not extend the basis of the interpolation domain");
+    const size_t nh = (size_t)1 << H->dim, nl = (size_t)1 << L->dim;
+    const f192 sh = el(H->shift), sl = el(L->shift);
+    for (size_t r = 0; r < batch; ++r) {              /* the two transforms the kernel fuses */
+        ++c->launches;
+        std::vector<f192> coeffs(nh);
+        orc_additive_ifft(coeffs.data(), E(evals) + r * nh, H->dim, (const f192 *)H->basis, &sh);
+        orc_additive_fft(E(out) + r * nl, coeffs.data(), nh, L->dim, (const f192 *)L->basis, &sl);
+    }
+    return 0;
+}
+int b200_gf192_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf out)
+{ return b200_gf192_lde_batch(c, H, L, evals, 1, out); }
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { ++c->launches; orc_gf192_mul_vec(E(out), E(a), E(b), n); return 0; }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
 {

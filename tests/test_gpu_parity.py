@@ -167,6 +167,46 @@ def test_additive_batch_lde_at_ligero_size_round_trips(dev):
         assert (code[r] == dev.gf192_fft(L.Domain.standard(13), coeffs[r])).all()
 
 
+@pytest.mark.parametrize("d,m,batch,shift_h", [(10, 13, 1, None), (12, 15, 1, 5), (13, 16, 1, None), (14, 16, 2, None), (11, 13, 7, 3), (5, 8, 40, None),
+                                               (0, 4, 3, None), (9, 9, 1, None), (16, 19, 1, None), (3, 14, 2, 1)])
+def test_fused_lde_equals_ifft_then_fft(dev, oracle, d, m, batch, shift_h):
+    """b200_gf192_lde: evaluations over H -> evaluations over L without the monomial coefficients (the reference interpolates and
+    re-evaluates: r1cs_rs_iop.tcc:449-479).  Bit-exact against the oracle's additive_IFFT over H followed by additive_FFT over L,
+    Aurora-shaped domains (standard basis, shifts x^d / x^m) and other shifts of H, batches, tiny and tile-crossing sizes."""
+    import libiop_b200 as L
+    rng = np.random.default_rng(31 * d + m + batch)
+    basis_h, basis_l = standard_basis(d), standard_basis(m)
+    sh = el(1 << d) if shift_h is None else rand_elems(rng, 1)[0]
+    sl = el(1 << m)
+    dom_h = L.Domain.affine(basis_h, sh) if d else L.Domain.affine(elems(0), sh)
+    dom_l = L.Domain.affine(basis_l, sl)
+    rows = rand_elems(rng, batch << d).reshape(batch, 1 << d, 3)
+    got = dev.gf192_lde(dom_h, dom_l, rows)
+    for r in range(batch):
+        coeffs = oracle.additive_ifft(rows[r], d, basis_h, sh) if d else rows[r]
+        assert (got[r] == oracle.additive_fft(coeffs, m, basis_l, sl)).all(), r
+
+
+def test_fused_lde_rejects_unrelated_bases(dev):
+    import libiop_b200 as L
+    rng = np.random.default_rng(9)
+    dom_h = L.Domain.affine(rand_elems(rng, 6), el(7))
+    with pytest.raises(L.B200Error):
+        dev.gf192_lde(dom_h, L.Domain.standard(9), rand_elems(rng, 64))
+
+
+def test_fused_lde_at_config_size_matches_the_two_transforms(dev):
+    """2^20 -> 2^23 (BASELINE config 2): the fused extension equals IFFT over H then FFT over L computed by the device's own two
+    transforms (which the oracle pins at smaller sizes)."""
+    import libiop_b200 as L
+    rng = np.random.default_rng(20)
+    ev = rng.integers(0, 2**64, size=(1 << 20, 3), dtype=np.uint64)
+    dom_h, dom_l = L.Domain.standard(20), L.Domain.standard(23)
+    fused = dev.gf192_lde(dom_h, dom_l, ev)[0]
+    two = dev.gf192_fft(dom_l, dev.gf192_ifft(dom_h, ev))
+    assert hashlib.sha256(fused.tobytes()).hexdigest() == hashlib.sha256(two.tobytes()).hexdigest()
+
+
 def test_additive_fft_empty_and_errors(dev):
     import libiop_b200 as L
     d = L.Domain.standard(6)
