@@ -113,7 +113,7 @@ class _quiet_stdout:
         os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
 
 
-def ncu_traffic(kernel_substr="additive_tile_pass<(bool)0", grid=2048):
+def ncu_traffic(kernel_substr="additive_tile_pass<0", grid=2048):
     """DRAM bytes (read + write) of the dominant launch from the committed `ncu --set full` capture of bench/profile_kernels.py
     lde (bench/ncu_families.sh): the longest launch of that kernel with that grid.  None when the capture is missing."""
     path = os.path.join(ROOT, "profiles", "r2_ncu", "ncu_lde_raw.csv")

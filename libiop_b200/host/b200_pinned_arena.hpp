@@ -322,6 +322,79 @@ private:
     struct sigaction previous_;
 };
 
+/* Small-block pool.  The reference builds its relations and IOP bookkeeping out of millions of tiny heap objects — the R1CS
+   deep copy inside aurora_snark_prover alone is 3 * 2^20 vectors of one 32-byte term (aurora_iop's constructor,
+   relations/r1cs.hpp) plus the std::map nodes of every registered query — and at N = 2^20 their allocation and release is
+   ~0.2 s of a 0.45 s proof once the data-parallel work is on the device.  Blocks of up to 256 bytes are therefore served
+   from per-thread free lists over 64 KiB pages of one address-space reservation: a pop / push of a singly linked list
+   instead of a trip through malloc.  A page holds blocks of ONE size class, so operator delete finds the class from the
+   address alone (unsized delete works), and a block may be released by any thread (it joins that thread's list).
+   B200_SMALL_POOL=0 turns the pool off; pages are never returned to the OS (they are reused through the lists). */
+class small_pool {
+public:
+    static constexpr std::size_t kMaxBytes = 256, kStep = 16, kClasses = kMaxBytes / kStep, kPageLog = 16;
+    static small_pool &instance() { static small_pool *p = create(); return *p; }
+    bool enabled() const { return base_ != nullptr; }
+    bool contains(const void *p) const { return (uintptr_t)p - (uintptr_t)base_ < bytes_; }
+
+    void *allocate(std::size_t n)
+    {
+        const std::size_t cls = (n + kStep - 1) / kStep - (n ? 1 : 0);      /* 1..16 -> 0, 17..32 -> 1, ... */
+        cache &c = local();
+        node *head = c.free_[cls];
+        if (head) { c.free_[cls] = head->next; return head; }
+        return refill(c, cls);
+    }
+    void release(void *p)
+    {
+        const std::size_t cls = page_class_[((uintptr_t)p - (uintptr_t)base_) >> kPageLog];
+        cache &c = local();
+        node *nd = static_cast<node *>(p);
+        nd->next = c.free_[cls];
+        c.free_[cls] = nd;
+    }
+
+private:
+    struct node { node *next; };
+    struct cache { node *free_[kClasses]; };
+    /* initial-exec TLS: a plain %fs-relative access instead of a __tls_get_addr call per allocation (128 bytes of static TLS) */
+    static cache &local() { static thread_local cache c __attribute__((tls_model("initial-exec"))) = {}; return c; }
+
+    static small_pool *create()
+    {
+        void *mem = std::malloc(sizeof(small_pool));
+        small_pool *p = new (mem) small_pool();
+        const char *off = std::getenv("B200_SMALL_POOL");
+        if (off && off[0] == '0') return p;
+        const char *g = std::getenv("B200_SMALL_POOL_GB");
+        const std::size_t bytes = (std::size_t)(g ? std::strtoull(g, nullptr, 10) : 32) << 30;
+        void *r = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (r == MAP_FAILED) return p;
+        p->page_class_ = static_cast<unsigned char *>(std::malloc(bytes >> kPageLog));
+        if (!p->page_class_) { munmap(r, bytes); return p; }
+        p->base_ = static_cast<char *>(r); p->bytes_ = bytes;
+        return p;
+    }
+    /* a fresh page for class `cls`, cut into blocks that go onto the calling thread's list; nullptr when the reservation is used up */
+    void *refill(cache &c, std::size_t cls)
+    {
+        const std::size_t page = __atomic_fetch_add(&next_page_, 1, __ATOMIC_RELAXED);
+        if (((page + 1) << kPageLog) > bytes_) return nullptr;
+        page_class_[page] = (unsigned char)cls;
+        char *start = base_ + (page << kPageLog);
+        const std::size_t bs = (cls + 1) * kStep, count = (std::size_t(1) << kPageLog) / bs;
+        for (std::size_t i = count - 1; i >= 1; --i) {
+            node *nd = reinterpret_cast<node *>(start + i * bs);
+            nd->next = c.free_[cls];
+            c.free_[cls] = nd;
+        }
+        return start;
+    }
+    char *base_ = nullptr;
+    std::size_t bytes_ = 0, next_page_ = 0;
+    unsigned char *page_class_ = nullptr;
+};
+
 /* std::vector<T> of n elements whose storage is NOT value-initialised (the caller overwrites all of it, e.g. by a
    device->host copy).  std::vector offers no such constructor; with libstdc++ / libc++ (three-pointer layout
    {begin, end, end_of_storage}) the end pointer is advanced over reserved storage.  Any other library takes the
@@ -370,6 +443,10 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
     inline void *alloc(std::size_t n)                                                                                    \
     {                                                                                                                    \
         static thread_local bool inside = false; /* context creation / cudaHostAlloc may allocate: do not recurse */    \
+        if (n <= small_pool::kMaxBytes) {                     /* the common case first: tiny objects (never re-enters) */  \
+            small_pool &sp = small_pool::instance();                                                                     \
+            if (sp.enabled()) { void *p = sp.allocate(n); if (p) return p; }                                             \
+        }                                                                                                                \
         alloc_hint &hint = current_alloc_hint();                                                                         \
         if (hint.kind == alloc_hint::lazy && hint.bytes == n && !inside) {                                               \
             hint.kind = alloc_hint::none;                                                                                \
@@ -390,6 +467,7 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
     inline void dealloc(void *p) noexcept                                                                                \
     {                                                                                                                    \
         if (!p) return;                                                                                                  \
+        if (small_pool::instance().contains(p)) { small_pool::instance().release(p); return; }                           \
         if (lazy_region::instance().contains(p)) {                                                                       \
             if (arena_release_hook()) arena_release_hook()(p);                                                           \
             lazy_region::instance().release(p);                                                                          \
