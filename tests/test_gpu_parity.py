@@ -43,7 +43,7 @@ def test_gf192_field_ops(dev, oracle, golden):
     assert (dev.gf192_mul(g["gf_a"], g["gf_b"]) == g["gf_mul"]).all()
     assert (dev.gf192_inv(g["gf_a"][:8]) == g["gf_inv"]).all()
     rng = np.random.default_rng(1)
-    a, b = rand_elems(rng, 100000), rand_elems(rng, 100000)
+    a, b = rand_elems(rng, 1000000), rand_elems(rng, 1000000)     # 10^6 random pairs
     a[:4] = 0xFFFFFFFFFFFFFFFF; b[:2] = 0xFFFFFFFFFFFFFFFF
     assert (dev.gf192_mul(a, b) == oracle.gf192_mul(a, b)).all()
     assert (dev.gf192_inv(a[:2000]) == oracle.gf192_inv(a[:2000])).all()
