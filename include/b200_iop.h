@@ -202,6 +202,12 @@ int b200_poly_eval(b200_ctx *, int field, const b200_fp_params *fp, b200_buf coe
 int b200_spmv_csr(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows, const uint64_t *row_ptr, const uint32_t *col,
                   const uint64_t *coeff, b200_buf x, size_t n_x, b200_buf y_out);
 
+/* The same product with the matrix already on the device (uploaded once per constraint system and used for A z, B z, C z and,
+ * transposed, for multi_lincheck's p_alpha_ABC): row_ptr (n_rows+1 x u64), col (nnz x u32) are device byte arrays, coeff a device
+ * element array.  Indices are trusted (the host-array entry point above validates them). */
+int b200_spmv_csr_dev(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows, b200_bytes row_ptr, b200_bytes col, b200_buf coeff,
+                      b200_buf x, b200_buf y_out);
+
 /* GF(2^192) scatter-accumulate over a list of matrix entries: y[dst[k]] += scale * coeff[k] * x[src[k]], k < nnz.
  * multi_lincheck_virtual_oracle::set_challenge's p_alpha_ABC (protocols/encoded/lincheck/basic_lincheck_aux.tcc:63-84): the
  * transposed product (sum_m r_m M_m)^T (1, alpha, alpha^2, ...) — one call per matrix with scale = r_m, x = the powers of alpha,
@@ -209,6 +215,10 @@ int b200_spmv_csr(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows
  * y (n_y elements, accumulated into) and x (n_x) are device buffers.  Additions are XOR, so entries may hit one y[.] in any order. */
 int b200_gf192_scatter_mul_add(b200_ctx *, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
                                const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3]);
+
+/* the same with the entry list on the device: dst, src device byte arrays of nnz x u32, coeff a device element array (trusted) */
+int b200_gf192_scatter_mul_add_dev(b200_ctx *, b200_buf y, size_t nnz, b200_bytes dst, b200_bytes src, b200_buf coeff, b200_buf x,
+                                   const uint64_t scale[3]);
 
 /* polynomial_over_vanishing_polynomial (algebra/polynomials/vanishing_polynomial.tcc:312-371,
  * linearized_polynomial.tcc:238-291): P = Q*Z + R for the sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j]

@@ -594,6 +594,31 @@ int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_row
     return 0;
 }
 
+int b200_spmv_csr_dev(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_rows, b200_bytes row_ptr, b200_bytes col, b200_buf coeff,
+                      b200_buf x, b200_buf y_out)
+{
+    B200_TRACE_SCOPE(c, "spmv_csr_dev", n_rows);
+    if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
+    if (!n_rows) return 0;
+    if (field == B200_FIELD_GF192)
+        spmv_csr_kernel<GfF><<<ew_grid(c, n_rows, 256), 256, 0, c->stream>>>((gf192 *)y_out, (const uint64_t *)row_ptr, (const uint32_t *)col,
+                                                                            (const gf192 *)coeff, (const gf192 *)x, n_rows, GfF());
+    else
+        spmv_csr_kernel<FpF><<<ew_grid(c, n_rows, 256), 256, 0, c->stream>>>((fp192 *)y_out, (const uint64_t *)row_ptr, (const uint32_t *)col,
+                                                                            (const fp192 *)coeff, (const fp192 *)x, n_rows, make_fpf(fp));
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+int b200_gf192_scatter_mul_add_dev(b200_ctx *c, b200_buf y, size_t nnz, b200_bytes dst, b200_bytes src, b200_buf coeff, b200_buf x,
+                                   const uint64_t scale[3])
+{
+    B200_TRACE_SCOPE(c, "scatter_mul_add_dev", nnz);
+    if (!nnz) return 0;
+    scatter_mul_add_gf192_kernel<<<ew_grid(c, nnz, 256), 256, 0, c->stream>>>((gf192 *)y, (const uint32_t *)dst, (const uint32_t *)src,
+                                                                             (const gf192 *)coeff, (const gf192 *)x, host_el<gf192>(scale), nnz);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
 int b200_gf192_scatter_mul_add(b200_ctx *c, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
                                const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3])
 {

@@ -553,7 +553,7 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
             B200_LAUNCH_CHECK(c);
             width >>= 3;
         }
-    } else if (digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
+    } else if (!getenv("B200_MERKLE_FLAT") && digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
         /* fast path: 8 leaves + 3 levels per thread, then 3 levels per launch */
         const size_t threads = leaves / 8;
         merkle_leaf8_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(P);
@@ -567,7 +567,7 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
         }
     } else {
         /* generic path: a CTA of 256 leaves owns the 8 levels above them */
-        uint32_t fused = (leaves >= MERKLE_CTA) ? 8 : 0;
+        uint32_t fused = (leaves >= MERKLE_CTA && !getenv("B200_MERKLE_FLAT")) ? 8 : 0;   /* B200_MERKLE_FLAT: one launch per level (experiment) */
         P.fused_levels = fused;
         const unsigned blocks = (unsigned)((leaves + MERKLE_CTA - 1) / MERKLE_CTA);
         merkle_leaf_kernel<<<blocks, MERKLE_CTA, 0, c->stream>>>(P);

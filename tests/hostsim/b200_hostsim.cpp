@@ -428,6 +428,29 @@ int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_row
     }
     return 0;
 }
+int b200_spmv_csr_dev(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_rows, b200_bytes row_ptr, b200_bytes col, b200_buf coeff,
+                      b200_buf x, b200_buf y_out)
+{
+    Field f; if (!make_field(c, field, fp, &f)) return B200_ERR_INVALID;
+    ++c->launches;
+    const uint64_t *rp = (const uint64_t *)(uintptr_t)row_ptr;
+    const uint32_t *cl = (const uint32_t *)(uintptr_t)col;
+    for (size_t i = 0; i < n_rows; ++i) {
+        f192 acc = zero();
+        for (uint64_t k = rp[i]; k < rp[i + 1]; ++k) acc = f.add(acc, f.mul(E(coeff)[k], E(x)[cl[k]]));
+        E(y_out)[i] = acc;
+    }
+    return 0;
+}
+int b200_gf192_scatter_mul_add_dev(b200_ctx *c, b200_buf y, size_t nnz, b200_bytes dst, b200_bytes src, b200_buf coeff, b200_buf x,
+                                   const uint64_t scale[3])
+{
+    Field f; f.kind = B200_FIELD_GF192;
+    ++c->launches;
+    const uint32_t *d = (const uint32_t *)(uintptr_t)dst, *sr = (const uint32_t *)(uintptr_t)src;
+    for (size_t k = 0; k < nnz; ++k) E(y)[d[k]] = f.add(E(y)[d[k]], f.mul(f.mul(E(coeff)[k], el(scale)), E(x)[sr[k]]));
+    return 0;
+}
 int b200_gf192_scatter_mul_add(b200_ctx *c, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
                                const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3])
 {
