@@ -9,6 +9,7 @@
    codeword domain (every prover-side query), the value is simply read out of the low-degree extension that
    evaluated_contents left on the device. */
 #include "b200_dropin_common.hpp"
+#include "b200_constraint_matrices.hpp"
 #include B200_REF_FILE(libiop/protocols/encoded/lincheck/basic_lincheck_aux.tcc)
 
 namespace libiop {
@@ -138,6 +139,18 @@ template<> inline void multi_lincheck_virtual_oracle<FIELD>::set_challenge(const
     };                                                                                                                     \
     if (field_traits<FIELD>::kind == B200_FIELD_GF192) {                                                                   \
         for (std::size_t m = 0; m < this->matrices_.size(); ++m) {                                                         \
+            /* the constraint system's matrices already on the device (shared with create_Az_Bz_Cz): column index = position \
+               in the summation domain for subspaces (reindex_by_subset is the identity there, field_subset.tcc:130-142) */  \
+            if (const r1cs_sparse_matrix<FIELD> *rm = dynamic_cast<const r1cs_sparse_matrix<FIELD> *>(this->matrices_[m].get())) { \
+                const b200_glue::flat_matrix *M = this->summation_domain_.type() == affine_subspace_type                   \
+                    ? b200_glue::constraint_matrices<FIELD>::instance().get(&b200_glue::r1cs_matrix_peek<FIELD>::system(*rm)) : nullptr; \
+                if (M && this->variable_domain_.num_elements() <= n_S) {                                                   \
+                    const b200_glue::flat_matrix &F = M[(int)b200_glue::r1cs_matrix_peek<FIELD>::type(*rm) - 1];           \
+                    throw_status(context(), b200_gf192_scatter_mul_add_dev(context(), d_abc.get(), F.nnz, F.col->get(), F.row->get(), \
+                                                                           F.coeff.get(), d_alpha.get(), limbs(this->r_Mz_[m]))); \
+                    continue;                                                                                              \
+                }                                                                                                          \
+            }                                                                                                              \
             std::vector<uint32_t> dst, src;                                                                                \
             std::vector<FIELD> coeff;                                                                                      \
             const std::size_t guess = this->matrices_[m]->num_rows() + (this->matrices_[m]->num_rows() >> 3);              \

@@ -6,6 +6,7 @@
    the terms, so with the one-term rows of generate_r1cs_example the device route is slower (whole prover 0.74 -> 0.78 s);
    it is taken from three terms per row on average, where the multiplications dominate.  Small systems keep the host loop. */
 #include "b200_dropin_common.hpp"
+#include "b200_constraint_matrices.hpp"
 #include B200_REF_FILE(libiop/relations/r1cs.tcc)
 
 namespace libiop {
@@ -42,6 +43,20 @@ template<> inline void r1cs_constraint_system<FIELD>::create_Az_Bz_Cz_from_varia
     const r1cs_variable_assignment<FIELD> &variable_assignment,                                                            \
     std::vector<FIELD> &Az_out, std::vector<FIELD> &Bz_out, std::vector<FIELD> &Cz_out) const                              \
 {                                                                                                                          \
+    if (const b200_glue::flat_matrix *M = b200_glue::constraint_matrices<FIELD>::instance().get(this)) {                 \
+        /* the matrices are (or now get) resident on the device: three gather products, results stay there for the LDE */  \
+        using namespace libiop_b200;                                                                                       \
+        const device_view d_z(variable_assignment);                                                                        \
+        std::vector<FIELD> *outs[3] = { &Az_out, &Bz_out, &Cz_out };                                                       \
+        for (int m = 0; m < 3; ++m) {                                                                                      \
+            device_buffer d_y(M[m].n_rows);                                                                                \
+            throw_status(context(), b200_spmv_csr_dev(context(), field_traits<FIELD>::kind, field_traits<FIELD>::fp(), M[m].n_rows,  \
+                                                      M[m].row_ptr->get(), M[m].col->get(), M[m].coeff.get(), d_z.get(), d_y.get())); \
+            if (outs[m]->empty()) *outs[m] = make_lazy_vector<FIELD>(std::move(d_y), M[m].n_rows);                         \
+            else { const std::vector<FIELD> y = d_y.template download<FIELD>(M[m].n_rows); outs[m]->insert(outs[m]->end(), y.begin(), y.end()); } \
+        }                                                                                                                  \
+        return;                                                                                                            \
+    }                                                                                                                      \
     std::size_t n_terms = 0;                                                                                               \
     for (auto &cons : this->constraints_) n_terms += cons.a_.terms.size() + cons.b_.terms.size() + cons.c_.terms.size();   \
     if (this->constraints_.size() < 16384 || n_terms < 3 * b200_glue::spmv_min_terms_per_row() * this->constraints_.size()) { /* r1cs.tcc:243-265 */                                 \
