@@ -491,6 +491,77 @@ __global__ void __launch_bounds__(128) merkle_leaf_quad_kernel(const LeafParams 
     if (active) P.nodes[(P.leaves - 1 + i) * 4 + q] = h0;                      /* 32-byte digest = h[0..3], one word per lane */
 }
 
+/* [round 2] One hash per thread at EVERY level.  Fusing three levels into the leaf thread (merkle_leaf8_kernel above) saves
+   writing and re-reading the digests — 2 x 32 B per node, a few per cent of a pass that is ALU-bound anyway — but costs a
+   64-register digest array, 8-leaf slices that are 8 x slice bytes apart between lanes, and 1/8 of the threads.  Measured on
+   the 4 x 2^23 tree: 2.73 ms fused, 1.81 ms with one launch per level.  Leaf i is hashed by thread i, so for every word index
+   the lanes of a warp read addresses one leaf (48-192 B) apart; each level is a launch of width/2 threads reading 64
+   contiguous bytes each. */
+#ifndef B200_LEAF1_MINBLOCKS
+#define B200_LEAF1_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, B200_LEAF1_MINBLOCKS) merkle_leaf1_kernel(const LeafParams P)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= P.leaves) return;
+    const size_t n_words = (size_t)3 * P.n_oracles * P.coset;
+    uint64_t h[8];
+    blake2b_init(h, 32);
+    uint32_t k = 0, j = 0, limb = 0;
+    const uint64_t *base = P.oracle_table ? P.oracle_table[0] : P.oracles[0];
+    const size_t pos = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? i : i * P.coset;
+    const size_t jstep = (P.kind == B200_DOMAIN_MULTIPLICATIVE_COSET) ? P.leaves : 1;
+    size_t done = 0;
+    for (;;) {
+        const size_t remaining = n_words - done;
+        const bool last = remaining <= 16;
+        uint64_t m[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            uint64_t v = 0;
+            if ((size_t)w < remaining) {
+                v = __ldg(base + (pos + (size_t)j * jstep) * 3 + limb);
+                if (++limb == 3) {
+                    limb = 0;
+                    if (++j == P.coset) { j = 0; ++k; if (k < P.n_oracles) base = P.oracle_table ? P.oracle_table[k] : P.oracles[k]; }
+                }
+            }
+            m[w] = v;
+        }
+        done += last ? remaining : 16;
+        blake2b_compress(h, m, (uint64_t)done * 8, last);
+        if (last) break;
+    }
+    if (P.salts) {                                  /* zk: H(H(leaf) || salt)  (blake2b.tcc:127-136) */
+        const uint64_t *salt = P.salts + i * P.salt_words;
+        uint64_t m[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            uint64_t v = 0;
+            if (w < 4) v = h[w];
+            else if ((uint32_t)(w - 4) < P.salt_words) v = salt[w - 4];
+            m[w] = v;
+        }
+        blake2b_init(h, 32);
+        blake2b_compress(h, m, (uint64_t)(4 + P.salt_words) * 8, true);
+    }
+    store_digest32(P.nodes, P.leaves - 1 + i, h);
+}
+
+/* level of `count` nodes starting at heap index `first`: node j = H(node 2j+1 || node 2j+2), 32-byte digests */
+__global__ void __launch_bounds__(256) merkle_level32_kernel(uint64_t *nodes, size_t first, size_t count)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const size_t j = first + t;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(nodes + (2 * j + 1) * 4);     /* children are adjacent: 64 bytes */
+    const ulonglong2 a = src[0], b = src[1], c2 = src[2], d = src[3];
+    const uint64_t l[4] = {a.x, a.y, b.x, b.y}, r[4] = {c2.x, c2.y, d.x, d.y};
+    uint64_t out[4];
+    two_to_one_32(out, l, r);
+    store_digest32(nodes, j, out);
+}
+
 __global__ void __launch_bounds__(128) merkle_reduce8_kernel(uint64_t *nodes, size_t width)
 {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -553,8 +624,19 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
             B200_LAUNCH_CHECK(c);
             width >>= 3;
         }
+    } else if (!getenv("B200_MERKLE_FLAT") && !getenv("B200_MERKLE_FUSED") && digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
+        /* one hash per thread at every level (see merkle_leaf1_kernel) */
+        merkle_leaf1_kernel<<<(unsigned)((leaves + 255) / 256), 256, 0, c->stream>>>(P);
+        B200_LAUNCH_CHECK(c);
+        width = leaves;
+        while (width > 2048) {
+            const size_t count = width >> 1, first = count - 1;
+            merkle_level32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(P.nodes, first, count);
+            B200_LAUNCH_CHECK(c);
+            width = count;
+        }
     } else if (!getenv("B200_MERKLE_FLAT") && digest_len == 32 && leaves >= 4096 && (!salts || salt_len <= 96)) {
-        /* fast path: 8 leaves + 3 levels per thread, then 3 levels per launch */
+        /* round-1 path (B200_MERKLE_FUSED=1, kept for comparison): 8 leaves + 3 levels per thread */
         const size_t threads = leaves / 8;
         merkle_leaf8_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(P);
         B200_LAUNCH_CHECK(c);
@@ -567,7 +649,7 @@ int merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t 
         }
     } else {
         /* generic path: a CTA of 256 leaves owns the 8 levels above them */
-        uint32_t fused = (leaves >= MERKLE_CTA && !getenv("B200_MERKLE_FLAT")) ? 8 : 0;   /* B200_MERKLE_FLAT: one launch per level (experiment) */
+        uint32_t fused = (leaves >= MERKLE_CTA && !getenv("B200_MERKLE_FLAT")) ? 8 : 0;   /* B200_MERKLE_FLAT: generic kernels, one launch per level */
         P.fused_levels = fused;
         const unsigned blocks = (unsigned)((leaves + MERKLE_CTA - 1) / MERKLE_CTA);
         merkle_leaf_kernel<<<blocks, MERKLE_CTA, 0, c->stream>>>(P);
