@@ -38,6 +38,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <new>
@@ -335,6 +336,7 @@ public:
     static constexpr std::size_t kMaxBytes = 256, kStep = 16, kClasses = kMaxBytes / kStep, kPageLog = 16;
     static small_pool &instance() { static small_pool *p = create(); return *p; }
     bool enabled() const { return base_ != nullptr; }
+    std::size_t max_bytes() const { return max_bytes_; }
     bool contains(const void *p) const { return (uintptr_t)p - (uintptr_t)base_ < bytes_; }
 
     void *allocate(std::size_t n)
@@ -373,6 +375,8 @@ private:
         p->page_class_ = static_cast<unsigned char *>(std::malloc(bytes >> kPageLog));
         if (!p->page_class_) { munmap(r, bytes); return p; }
         p->base_ = static_cast<char *>(r); p->bytes_ = bytes;
+        const char *mx = std::getenv("B200_SMALL_POOL_MAX");          /* largest block served (bytes, <= 256) */
+        if (mx) p->max_bytes_ = std::min<std::size_t>(kMaxBytes, std::strtoull(mx, nullptr, 10));
         return p;
     }
     /* a fresh page for class `cls`, cut into blocks that go onto the calling thread's list; nullptr when the reservation is used up */
@@ -391,7 +395,7 @@ private:
         return start;
     }
     char *base_ = nullptr;
-    std::size_t bytes_ = 0, next_page_ = 0;
+    std::size_t bytes_ = 0, next_page_ = 0, max_bytes_ = kMaxBytes;
     unsigned char *page_class_ = nullptr;
 };
 
@@ -445,7 +449,7 @@ std::vector<T> make_uninitialized_vector(std::size_t n)
         static thread_local bool inside = false; /* context creation / cudaHostAlloc may allocate: do not recurse */    \
         if (n <= small_pool::kMaxBytes) {                     /* the common case first: tiny objects (never re-enters) */  \
             small_pool &sp = small_pool::instance();                                                                     \
-            if (sp.enabled()) { void *p = sp.allocate(n); if (p) return p; }                                             \
+            if (sp.enabled() && n <= sp.max_bytes()) { void *p = sp.allocate(n); if (p) return p; }                      \
         }                                                                                                                \
         alloc_hint &hint = current_alloc_hint();                                                                         \
         if (hint.kind == alloc_hint::lazy && hint.bytes == n && !inside) {                                               \
