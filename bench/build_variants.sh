@@ -29,6 +29,7 @@ for v in "$@"; do
     blake2) build blake2 -DB200_BLAKE_IMAD=2 ;;           #          all additions on the FMA pipe
     ntt11)  build ntt11  -DB200_NTT_TILE_BITS=11 ;;       # round 2: NTT tiles of 2^11 elements (4 CTAs per SM)
     ntt12)  build ntt12  -DB200_NTT_TILE_BITS=12 ;;
+    ntt10)  build ntt10  -DB200_NTT_TILE_BITS=10 ;;
     leaf2)  build leaf2  -DB200_LEAF1_MINBLOCKS=2 ;;      # round 2: register budget of merkle_leaf1_kernel (2 / 3 / 4 CTAs of 256 per SM)
     leaf3)  build leaf3  -DB200_LEAF1_MINBLOCKS=3 ;;
     leaf4)  build leaf4  -DB200_LEAF1_MINBLOCKS=4 ;;

@@ -623,7 +623,7 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
     const uint32_t tbw = (p.hi - p.lo) + p.c + p.ctop;
     const uint32_t tb = tbw + p.cb;
     const size_t smem = 3 * (((size_t)1 << tb) + B200_SMEM_PAD) * sizeof(uint64_t) + ((size_t)d << p.cb) * sizeof(gf192);
-    static bool attr_set[2] = {false, false};
+    bool *attr_set = c->attr_additive;
     if (!attr_set[INV]) {
         const int max_smem = (int)(3 * (((size_t)1 << 13) + B200_SMEM_PAD) * sizeof(uint64_t) + 8192);
         B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS>,

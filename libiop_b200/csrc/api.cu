@@ -53,6 +53,7 @@ b200_ctx *b200_ctx_create(int device)
 
 void b200_ctx_destroy(b200_ctx *c)
 {
+    B200_ENTER(c);
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -66,17 +67,19 @@ void b200_ctx_destroy(b200_ctx *c)
     delete c;
 }
 
-const char *b200_last_error(b200_ctx *c) { return c ? c->err : "no context (is a CUDA device present?)"; }
+const char *b200_last_error(b200_ctx *c) { B200_ENTER(c); return c ? c->err : "no context (is a CUDA device present?)"; }
 
 int b200_sync(b200_ctx *c)
 {
+    B200_ENTER(c);
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
-void *b200_stream(b200_ctx *c) { return (void *)c->stream; }
+void *b200_stream(b200_ctx *c) { B200_ENTER(c); return (void *)c->stream; }
 
 int b200_device_info(b200_ctx *c, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor)
 {
+    B200_ENTER(c);
     cudaDeviceProp prop;
     B200_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
     if (sm_count) *sm_count = prop.multiProcessorCount;
@@ -88,16 +91,18 @@ int b200_device_info(b200_ctx *c, int *sm_count, size_t *total_mem, int *cc_majo
 
 int b200_trim(b200_ctx *c)
 {
+    B200_ENTER(c);
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
     for (auto &kv : c->free_blocks) cudaFree(kv.second);
     c->free_blocks.clear();
     c->cached_bytes = 0;
     return 0;
 }
-b200_buf b200_alloc(b200_ctx *c, size_t n_elems) { return b200_alloc_bytes(c, n_elems * 24); }
-void b200_free(b200_ctx *c, b200_buf b) { b200_free_bytes(c, b); }
+b200_buf b200_alloc(b200_ctx *c, size_t n_elems) { B200_ENTER(c); return b200_alloc_bytes(c, n_elems * 24); }
+void b200_free(b200_ctx *c, b200_buf b) { B200_ENTER(c); b200_free_bytes(c, b); }
 b200_bytes b200_alloc_bytes(b200_ctx *c, size_t n_bytes)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "alloc", n_bytes);
     const size_t want = ((n_bytes ? n_bytes : 8) + 511) & ~(size_t)511;
     auto hit = c->free_blocks.find(want);
@@ -123,6 +128,7 @@ b200_bytes b200_alloc_bytes(b200_ctx *c, size_t n_bytes)
 }
 void b200_free_bytes(b200_ctx *c, b200_bytes b)
 {
+    B200_ENTER(c);
     if (!b) return;
     void *p = (void *)(uintptr_t)b;
     auto it = c->live_blocks.find(p);
@@ -133,6 +139,7 @@ void b200_free_bytes(b200_ctx *c, b200_bytes b)
 }
 void *b200_host_alloc(b200_ctx *c, size_t n_bytes)
 {
+    B200_ENTER(c);
     void *p = nullptr;
     if (cudaMallocHost(&p, n_bytes ? n_bytes : 8) != cudaSuccess) {
         cudaGetLastError();
@@ -145,6 +152,7 @@ void b200_host_free(b200_ctx *, void *p) { if (p) cudaFreeHost(p); }
 
 int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *src, size_t n_elems)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "upload", n_elems * 24);
     c->h2d_bytes += n_elems * 24;
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, src, n_elems * 24, cudaMemcpyHostToDevice, c->stream));
@@ -154,6 +162,7 @@ int b200_upload(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t *sr
 }
 int b200_wait_uploads(b200_ctx *c)
 {
+    B200_ENTER(c);
     if (!c->upload_pending) return 0;
     B200_CUDA(c, cudaEventSynchronize(c->ev_upload));
     c->upload_pending = false;
@@ -161,6 +170,7 @@ int b200_wait_uploads(b200_ctx *c)
 }
 int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, size_t n_elems)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "download", n_elems * 24);
     c->d2h_bytes += n_elems * 24;
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + src_offset * 24, n_elems * 24, cudaMemcpyDeviceToHost, c->stream));
@@ -169,6 +179,7 @@ int b200_download(b200_ctx *c, uint64_t *dst, b200_buf src, size_t src_offset, s
 }
 int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_bytes)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "upload_bytes", n_bytes);
     c->h2d_bytes += n_bytes;
     B200_CUDA(c, cudaMemcpyAsync((void *)(uintptr_t)dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -178,6 +189,7 @@ int b200_upload_bytes(b200_ctx *c, b200_bytes dst, const uint8_t *src, size_t n_
 }
 int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset, size_t n_bytes)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "download_bytes", n_bytes);
     c->d2h_bytes += n_bytes;
     B200_CUDA(c, cudaMemcpyAsync(dst, (const char *)(uintptr_t)src + offset, n_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -186,12 +198,14 @@ int b200_download_bytes(b200_ctx *c, uint8_t *dst, b200_bytes src, size_t offset
 }
 int b200_copy(b200_ctx *c, b200_buf dst, size_t dst_offset, b200_buf src, size_t src_offset, size_t n_elems)
 {
+    B200_ENTER(c);
     B200_CUDA(c, cudaMemcpyAsync((char *)(uintptr_t)dst + dst_offset * 24, (const char *)(uintptr_t)src + src_offset * 24,
                                  n_elems * 24, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
 int b200_copy_strided(b200_ctx *c, b200_buf dst, size_t dst_stride, b200_buf src, size_t src_offset, size_t src_stride, size_t n_elems)
 {
+    B200_ENTER(c);
     if (!n_elems) return 0;
     const unsigned grid = (unsigned)((n_elems + 255) / 256 < 148 * 8 ? (n_elems + 255) / 256 : 148 * 8);
     copy_strided_kernel<<<grid, 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst, dst_stride, (const uint64_t *)(uintptr_t)src + 3 * src_offset,
@@ -201,6 +215,7 @@ int b200_copy_strided(b200_ctx *c, b200_buf dst, size_t dst_stride, b200_buf src
 }
 int b200_fill_zero(b200_ctx *c, b200_buf dst, size_t dst_offset, size_t n_elems)
 {
+    B200_ENTER(c);
     B200_CUDA(c, cudaMemsetAsync((char *)(uintptr_t)dst + dst_offset * 24, 0, n_elems * 24, c->stream));
     return 0;
 }
@@ -213,6 +228,7 @@ __global__ void gather_kernel(uint64_t *out, const uint64_t *src, const size_t *
 
 int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, size_t k)
 {
+    B200_ENTER(c);
     if (!k) return 0;
     const size_t bytes = k * sizeof(size_t) + k * 24;
     char *dev = (char *)scratch_get(c, 3, bytes);
@@ -228,14 +244,16 @@ int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, siz
 }
 
 /* ---- instrumentation ---- */
-unsigned long long b200_launch_count(b200_ctx *c) { return c->n_launches; }
+unsigned long long b200_launch_count(b200_ctx *c) { B200_ENTER(c); return c->n_launches; }
 void b200_transfer_bytes(b200_ctx *c, unsigned long long *h2d, unsigned long long *d2h)
 {
+    B200_ENTER(c);
     if (h2d) *h2d = c->h2d_bytes;
     if (d2h) *d2h = c->d2h_bytes;
 }
 int b200_profile_begin(b200_ctx *c)
 {
+    B200_ENTER(c);
     for (auto &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     c->prof.clear();
     c->profiling = true;
@@ -244,6 +262,7 @@ int b200_profile_begin(b200_ctx *c)
 /* writes "label\tms\n" lines into buf (truncated to cap); returns the number of records */
 int b200_profile_end(b200_ctx *c, char *buf, size_t cap)
 {
+    B200_ENTER(c);
     c->profiling = false;
     cudaStreamSynchronize(c->stream);
     size_t off = 0;
@@ -259,9 +278,10 @@ int b200_profile_end(b200_ctx *c, char *buf, size_t cap)
     return n;
 }
 
-int b200_timer_start(b200_ctx *c) { B200_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
+int b200_timer_start(b200_ctx *c) { B200_ENTER(c); B200_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
 int b200_timer_stop(b200_ctx *c, float *ms)
 {
+    B200_ENTER(c);
     B200_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     B200_CUDA(c, cudaEventSynchronize(c->ev1));
     B200_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -270,59 +290,69 @@ int b200_timer_stop(b200_ctx *c, float *ms)
 
 int b200_gf192_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_fft", (size_t)1 << L->dim);
     return additive_fft(c, L, coeffs, n_coeffs, evals_out, 1);
 }
 int b200_gf192_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_ifft", (size_t)1 << H->dim);
     return additive_ifft(c, H, evals, coeffs_out, 1);
 }
 int b200_gf192_fft_batch(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, size_t batch, b200_buf evals_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_fft_batch", batch << L->dim);
     return additive_fft(c, L, coeffs, n_coeffs, evals_out, batch);
 }
 int b200_gf192_ifft_batch(b200_ctx *c, const b200_domain *H, b200_buf evals, size_t batch, b200_buf coeffs_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_ifft_batch", batch << H->dim);
     return additive_ifft(c, H, evals, coeffs_out, batch);
 }
 int b200_gf192_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf evals_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_lde", (size_t)1 << (L ? L->dim : 0));
     return additive_lde(c, H, L, evals, evals_out, 1);
 }
 int b200_gf192_lde_batch(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, size_t batch, b200_buf evals_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_lde_batch", batch << (L ? L->dim : 0));
     return additive_lde(c, H, L, evals, evals_out, batch);
 }
-int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { return gf192_mul_vec(c, out, a, b, n); }
+int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { B200_ENTER(c); return gf192_mul_vec(c, out, a, b, n); }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "gf192_inv", n);
     return gf192_inv_vec(c, out, a, n);
 }
 
 int b200_fp_ntt(b200_ctx *c, const b200_fp_params *P, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf evals_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "fp_ntt", (size_t)1 << L->dim);
     return fp_ntt(c, P, L, coeffs, n_coeffs, evals_out);
 }
 int b200_fp_intt(b200_ctx *c, const b200_fp_params *P, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "fp_intt", (size_t)1 << H->dim);
     return fp_intt(c, P, H, evals, coeffs_out);
 }
-int b200_fp_mul(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 0, out, a, b, n); }
-int b200_fp_add(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 1, out, a, b, n); }
-int b200_fp_sub(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { return fp_binop_vec(c, P, 2, out, a, b, n); }
-int b200_fp_inv(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, size_t n) { return fp_binop_vec(c, P, 3, out, a, 0, n); }
+int b200_fp_mul(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { B200_ENTER(c); return fp_binop_vec(c, P, 0, out, a, b, n); }
+int b200_fp_add(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { B200_ENTER(c); return fp_binop_vec(c, P, 1, out, a, b, n); }
+int b200_fp_sub(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, b200_buf b, size_t n) { B200_ENTER(c); return fp_binop_vec(c, P, 2, out, a, b, n); }
+int b200_fp_inv(b200_ctx *c, const b200_fp_params *P, b200_buf out, b200_buf a, size_t n) { B200_ENTER(c); return fp_binop_vec(c, P, 3, out, a, 0, n); }
 
 int b200_fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_domain *L_i, uint32_t eta,
                   const uint64_t x_i[3], b200_buf f_i, b200_buf f_next_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "fri_fold", (size_t)1 << L_i->dim);
     return fri_fold(c, field, fp, L_i, eta, x_i, f_i, f_next_out);
 }
@@ -330,11 +360,13 @@ int b200_fri_fold(b200_ctx *c, int field, const b200_fp_params *fp, const b200_d
 int b200_merkle_build(b200_ctx *c, const b200_buf *oracles, size_t n_oracles, size_t n_elems, size_t coset_size,
                       int domain_kind, const uint8_t *zk_salts_host, size_t salt_len, size_t digest_len, b200_bytes nodes_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "merkle_build", n_elems * n_oracles);
     return merkle_build(c, oracles, n_oracles, n_elems, coset_size, domain_kind, zk_salts_host, salt_len, digest_len, nodes_out);
 }
 int b200_merkle_root(b200_ctx *c, b200_bytes nodes, uint8_t *root_out, size_t digest_len)
 {
+    B200_ENTER(c);
     return b200_download_bytes(c, root_out, nodes, 0, digest_len);
 }
 
@@ -346,6 +378,7 @@ __global__ void node_gather_kernel(uint64_t *out, const uint64_t *nodes, const s
 
 int b200_merkle_nodes(b200_ctx *c, b200_bytes nodes, const size_t *node_idx, size_t k, size_t digest_len, uint8_t *out)
 {
+    B200_ENTER(c);
     if (!k) return 0;
     if (digest_len % 8) return set_err(c, B200_ERR_INVALID, "digest length must be a multiple of 8");
     const uint32_t dw = (uint32_t)(digest_len / 8);
@@ -363,6 +396,7 @@ int b200_merkle_nodes(b200_ctx *c, b200_bytes nodes, const size_t *node_idx, siz
 
 int b200_pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uint32_t pow_bitlen, uint64_t pow_upperbound, uint8_t *pow_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "pow_solve", pow_bitlen);
     return pow_solve(c, challenge, digest_len, pow_bitlen, pow_upperbound, pow_out);
 }
@@ -370,12 +404,14 @@ int b200_pow_solve(b200_ctx *c, const uint8_t *challenge, size_t digest_len, uin
 int b200_squeeze_field_elements(b200_ctx *c, int field, const b200_fp_params *fp, const uint8_t *root_plus_index, size_t msg_len,
                                 size_t n, b200_buf out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "squeeze_field_elements", n);
     return squeeze_field_elements(c, field, fp, root_plus_index, msg_len, n, out);
 }
 
 int b200_blake2b_batch(b200_ctx *c, b200_bytes in, size_t msg_len, size_t n_msgs, size_t digest_len, b200_bytes out)
 {
+    B200_ENTER(c);
     return blake2b_batch(c, in, msg_len, n_msgs, digest_len, out);
 }
 

@@ -25,6 +25,9 @@ struct b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_upload = nullptr;   /* recorded after every host->device copy (b200_wait_uploads) */
     bool upload_pending = false;
+    /* cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per context, not per process */
+    bool attr_additive[2] = {false, false};
+    bool attr_ntt = false;
     char err[512] = {0};
     /* grow-only device scratch (work arrays of the FFTs), keyed by slot */
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -62,6 +65,10 @@ inline int set_err(b200_ctx *c, int code, const char *fmt, ...)
     }
     return code;
 }
+
+/* Every C-ABI entry point makes its context's device current first: a process may hold one context per GPU (or share the
+   thread with a framework that switches devices), and allocations / launches follow the CURRENT device. */
+#define B200_ENTER(ctx) do { if (ctx) cudaSetDevice((ctx)->device); } while (0)
 
 #define B200_CUDA(ctx, call)                                                                      \
     do {                                                                                          \

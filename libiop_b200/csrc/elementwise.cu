@@ -431,6 +431,7 @@ extern "C" {
 int b200_vec_lincomb(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, size_t n, size_t k,
                      const uint64_t *coeffs, const b200_buf *vecs)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_lincomb", n * k);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (field == B200_FIELD_GF192) return lincomb_run(c, GfF(), out, n, k, coeffs, vecs);
@@ -440,6 +441,7 @@ int b200_vec_lincomb(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf 
 int b200_vec_mul_add(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf b, b200_buf cc,
                      b200_buf d, int subtract, size_t n)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_mul_add", n);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (!n) return 0;
@@ -457,6 +459,7 @@ int b200_vec_mul_add(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf 
 int b200_vec_rows_dot(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf x, b200_buf y, size_t n, size_t rows,
                       size_t split)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_rows_dot", n * rows);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (split > rows) return set_err(c, B200_ERR_INVALID, "b200_vec_rows_dot: split beyond the number of rows");
@@ -472,6 +475,7 @@ int b200_vec_rows_dot(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf
 
 int b200_vec_affine(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, const uint64_t *mul, const uint64_t *add, size_t n)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_affine", n);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (!n) return 0;
@@ -487,6 +491,7 @@ int b200_vec_affine(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf o
 
 int b200_vec_find_zero(b200_ctx *c, b200_buf a, size_t n, size_t *index_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_find_zero", n);
     unsigned long long *dev = (unsigned long long *)scratch_get(c, 3, 64);
     if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate scratch");
@@ -505,6 +510,7 @@ int b200_vec_find_zero(b200_ctx *c, b200_buf a, size_t n, size_t *index_out)
 int b200_vec_mul_table(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf out, b200_buf a, b200_buf table,
                        uint32_t shift, size_t mask, size_t n)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "vec_mul_table", n);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (!n) return 0;
@@ -518,6 +524,7 @@ int b200_vec_mul_table(b200_ctx *c, int field, const b200_fp_params *fp, b200_bu
 
 int b200_gf192_subset_sum_products(b200_ctx *c, b200_buf out, uint32_t dim, uint32_t n_factors, const uint64_t *tables)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "subset_sum_products", ((size_t)n_factors << 32) | dim);
     if (dim > 40 || n_factors == 0 || n_factors > 64) return set_err(c, B200_ERR_INVALID, "subset sums: dim <= 40 and 1..64 factors");
     const size_t n = (size_t)1 << dim;
@@ -539,6 +546,7 @@ int b200_gf192_subset_sum_products(b200_ctx *c, b200_buf out, uint32_t dim, uint
 int b200_fp_geometric(b200_ctx *c, const b200_fp_params *fp, b200_buf out, size_t n, const uint64_t a[3], const uint64_t r[3],
                       const uint64_t add[3])
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "fp_geometric", n);
     if (!fp) return set_err(c, B200_ERR_INVALID, "missing prime-field parameters");
     if (!n) return 0;
@@ -558,6 +566,7 @@ int b200_fp_geometric(b200_ctx *c, const b200_fp_params *fp, b200_buf out, size_
 
 int b200_poly_eval(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf coeffs, size_t n, const uint64_t x[3], uint64_t out[3])
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "poly_eval", n);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (field == B200_FIELD_GF192) return poly_eval_run(c, GfF(), coeffs, n, x, out);
@@ -567,6 +576,7 @@ int b200_poly_eval(b200_ctx *c, int field, const b200_fp_params *fp, b200_buf co
 int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_rows, const uint64_t *row_ptr, const uint32_t *col,
                   const uint64_t *coeff, b200_buf x, size_t n_x, b200_buf y_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "spmv_csr", n_rows);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (!n_rows) return 0;
@@ -597,6 +607,7 @@ int b200_spmv_csr(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_row
 int b200_spmv_csr_dev(b200_ctx *c, int field, const b200_fp_params *fp, size_t n_rows, b200_bytes row_ptr, b200_bytes col, b200_buf coeff,
                       b200_buf x, b200_buf y_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "spmv_csr_dev", n_rows);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (!n_rows) return 0;
@@ -612,6 +623,7 @@ int b200_spmv_csr_dev(b200_ctx *c, int field, const b200_fp_params *fp, size_t n
 int b200_gf192_scatter_mul_add_dev(b200_ctx *c, b200_buf y, size_t nnz, b200_bytes dst, b200_bytes src, b200_buf coeff, b200_buf x,
                                    const uint64_t scale[3])
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "scatter_mul_add_dev", nnz);
     if (!nnz) return 0;
     scatter_mul_add_gf192_kernel<<<ew_grid(c, nnz, 256), 256, 0, c->stream>>>((gf192 *)y, (const uint32_t *)dst, (const uint32_t *)src,
@@ -622,6 +634,7 @@ int b200_gf192_scatter_mul_add_dev(b200_ctx *c, b200_buf y, size_t nnz, b200_byt
 int b200_gf192_scatter_mul_add(b200_ctx *c, b200_buf y, size_t n_y, size_t nnz, const uint32_t *dst, const uint32_t *src,
                                const uint64_t *coeff, b200_buf x, size_t n_x, const uint64_t scale[3])
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "scatter_mul_add", nnz);
     if (!nnz) return 0;
     for (size_t k = 0; k < nnz; ++k)
@@ -646,6 +659,7 @@ int b200_poly_divide_sparse(b200_ctx *c, int field, const b200_fp_params *fp, b2
                             const uint64_t lead_inv[3], size_t n_terms, const uint64_t *coefs, const size_t *pows,
                             b200_buf q_out, b200_buf r_out)
 {
+    B200_ENTER(c);
     B200_TRACE_SCOPE(c, "poly_divide_sparse", n_p);
     if (!field_ok(c, field, fp)) return B200_ERR_INVALID;
     if (field == B200_FIELD_GF192) return divide_run(c, GfF(), p, n_p, deg, lead_inv, n_terms, coefs, pows, q_out, r_out);

@@ -221,7 +221,7 @@ static const uint32_t kNttCoalesceBits = 4;
 static int run_stages(b200_ctx *c, NttPassParams P, uint32_t logn, uint32_t first, const fp192 *src, fp192 *dst,
                       uint32_t gather_d, uint32_t n_src)
 {
-    static bool attr = false;
+    bool &attr = c->attr_ntt;
     if (!attr) {
         B200_CUDA(c, cudaFuncSetAttribute(ntt_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(3 * (((size_t)1 << 13) + B200_NTT_PAD) * sizeof(uint64_t))));
