@@ -309,8 +309,9 @@ def run_gpu(args):
                              "algorithmic_bytes": lde_bytes, "achieved_gbs": lde_gbs, "frac": lde_gbs / peak,
                              "gf_mul_per_s_reference_count": 1.5 * M * n_l / (lde_ms * 1e-3),
                              "gf_mul_per_s_executed": 100 * (1 << LOG_N) / (lde_ms * 1e-3)},
-                     "note": "integer-pipe bound, not HBM bound: ~950 instructions (289 IMAD.WIDE, quarter-rate) per GF(2^192) "
-                             "multiplication, 100 multiplications per 24-byte coefficient; DESIGN.md 3.1-3.2, profiles/r2_variants.md"},
+                     "note": "integer-pipe bound, not HBM bound: ~850 instructions (292 IMAD.WIDE at quarter rate + 512 LOP3) per GF(2^192) "
+                             "multiplication-butterfly, 100 multiplications per 24-byte coefficient; traffic below the algorithmic bytes = part of "
+                             "the array is still in the 126 MB L2 from the previous pass; DESIGN.md 3.1-3.2, profiles/r2_variants.md"},
         "algorithmic_bytes_per_step": algorithmic_bytes(ffts, ldes, iffts, folds, trees),
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary() if rank == 0 else None,
