@@ -162,6 +162,46 @@ void b200_prover_aurora_gf192_repeat(uint32_t log_n, uint32_t k_inputs, int make
     }
 }
 
+/* The steps of aurora_snark_prover (snark/aurora_snark.tcc:120-146) timed one by one on one generated instance:
+   secs_out[0] protocol construction + registrations, [1] produce_proof, [2] get_transcript, [3] destruction of the
+   protocol objects and the prover's oracles, [4] destruction of the argument.  A diagnostic for host-side work that the
+   reference's own enter_block timers do not cover (bench/dropin_phases.py); the product path is the call above. */
+void b200_prover_aurora_gf192_phases(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
+                                     uint64_t seed, uint32_t repeats, double *secs_out)
+{
+    init_once();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, n - 1);
+    aurora_snark_parameters<G, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
+        blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    arm_proof_randomness(make_zk != 0);
+    for (uint32_t r = 0; r < repeats; ++r) {
+        double *out = secs_out + 5 * r;
+        auto t0 = std::chrono::steady_clock::now();
+        {
+            std::unique_ptr<aurora_snark_argument<G, binary_hash_digest>> transcript;
+            {
+                bcs_prover<G, binary_hash_digest> IOP(params.bcs_params_);
+                aurora_iop<G> full_protocol(IOP, ex.constraint_system_, params.iop_params_);
+                full_protocol.register_interactions();
+                IOP.seal_interaction_registrations();
+                full_protocol.register_queries();
+                IOP.seal_query_registrations();
+                auto t1 = std::chrono::steady_clock::now(); out[0] = seconds(t0, t1); t0 = t1;
+                full_protocol.produce_proof(ex.primary_input_, ex.auxiliary_input_);
+                t1 = std::chrono::steady_clock::now(); out[1] = seconds(t0, t1); t0 = t1;
+                transcript.reset(new aurora_snark_argument<G, binary_hash_digest>(IOP.get_transcript()));
+                t1 = std::chrono::steady_clock::now(); out[2] = seconds(t0, t1); t0 = t1;
+            }
+            auto t1 = std::chrono::steady_clock::now(); out[3] = seconds(t0, t1); t0 = t1;
+        }
+        out[4] = seconds(t0, std::chrono::steady_clock::now());
+    }
+}
+
 /* Aurora over edwards_Fr, multiplicative cosets (README.md:160-164 `--is_multiplicative 1 --field_size=181`), non-zk */
 double b200_prover_aurora_edwards(uint32_t log_n, uint32_t k_inputs, uint32_t rs_extra, uint32_t fri_loc, uint64_t seed,
                                   int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)

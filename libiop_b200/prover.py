@@ -48,6 +48,14 @@ class DropinProver:
                                                  C.c_uint32(fri_loc), C.c_uint64(seed), C.c_uint32(repeats), secs)
         return list(secs)
 
+    def aurora_gf192_phases(self, log_n, repeats, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED):
+        """per proof: seconds of [construction + registrations, produce_proof, get_transcript, destruction of the protocol
+        objects and oracles, destruction of the argument] (diagnostic; bench/dropin_phases.py)"""
+        secs = (C.c_double * (5 * repeats))()
+        self.lib.b200_prover_aurora_gf192_phases(C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_int(1 if make_zk else 0), C.c_uint32(rs_extra),
+                                                 C.c_uint32(fri_loc), C.c_uint64(seed), C.c_uint32(repeats), secs)
+        return [list(secs[5 * r:5 * r + 5]) for r in range(repeats)]
+
     def aurora_edwards(self, log_n, k_inputs=31, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED, verify=True):
         return self._run(self.lib.b200_prover_aurora_edwards,
                          (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_uint32(rs_extra), C.c_uint32(fri_loc), C.c_uint64(seed),
