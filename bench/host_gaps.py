@@ -5,12 +5,18 @@ import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 min_gap = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-code = ("import sys,os; sys.path.insert(0,%r); from libiop_b200.prover import DropinProver; p=DropinProver();\n"
+raw_out = sys.argv[3] if len(sys.argv) > 3 else None      # also write the raw merged stream (API calls + enter/leave blocks) of the last proof
+code = ("import sys,os,ctypes as C; sys.path.insert(0,%r); from libiop_b200.prover import DropinProver; p=DropinProver();\n"
+        "libc=C.CDLL(None); libc.setvbuf(C.c_void_p.in_dll(libc,'stdout'), None, 2, 0); os.dup2(2,1)\n"
         "for r in range(3):\n    sys.stderr.write('=== proof %%d\\n' %% r); sys.stderr.flush(); s=p.aurora_gf192_phases(%d,1); sys.stderr.write('=== phases %%s\\n' %% s); sys.stderr.flush()\n" % (ROOT, log_n))
-r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_TRACE="1", B200_DETERMINISTIC_RNG="1"),
+r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_TRACE="1", B200_DETERMINISTIC_RNG="1", **({"B200_REF_PROFILE": "1"} if raw_out else {})),
                    stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
 lines = r.stderr.splitlines()
 start = max(i for i, l in enumerate(lines) if l.startswith("=== proof"))
+if raw_out:
+    with open(raw_out, "w") as f:
+        for l in lines[start:]:
+            if l.startswith("b200 ") or "(enter)" in l or "(leave)" in l or l.startswith("==="): f.write(l[:150] + "\n")
 calls = []
 for l in lines[start:]:
     m = re.match(r"b200 (\S+)\s+(\d+)\s+([\d.]+) ms\s+@\s*([\d.]+)", l)
