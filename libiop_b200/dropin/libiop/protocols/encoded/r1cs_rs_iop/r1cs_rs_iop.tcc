@@ -49,6 +49,143 @@ template<> inline void encoded_aurora_protocol<FIELD>::compute_fprime_ABCz_over_
 B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
 #undef B200_ABCZ_SPECIALISE
 
+namespace b200_glue {
+/* f_w over the codeword domain WITHOUT a coefficient vector (submit_witness_oracles, r1cs_rs_iop.tcc:497-569).
+   The reference interpolates \hat f_w = (witness - f_{1,v}) over the variable domain (IFFT), divides the coefficient vector by
+   the vanishing polynomial of the input positions, and evaluates the quotient over L (FFT).  For subspace domains over
+   GF(2^192) the same codeword comes out of evaluations alone:
+       z            = (1, primary, auxiliary) on the device (the vector create_Az_Bz_Cz multiplies next — it goes up once),
+       \hat f_w|V   = z + f_{1,v}|V         (zero at the input positions by construction: f_{1,v} interpolates them),
+       \hat f_w|L   = fused LDE V -> L      (+ Z_V|L * mask|L in the zero-knowledge case),
+       f_w|L        = \hat f_w|L / Z_in|L,  Z_in|L constant on the 2^dim(in) elements that differ only in the input basis
+                                            directions: |L| / 2^dim(in) inversions and one table-lookup multiplication.
+   Field arithmetic is exact, so the values are those of the reference's quotient polynomial; 32 ms -> 8 ms of an N = 2^20
+   proof (profiles/r2_host_gaps_N20_v1.txt vs _v2).  Returns false — nothing done — when the domains do not qualify. */
+template<typename FieldT>
+bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input, const r1cs_auxiliary_input<FieldT> &auxiliary_input,
+                                const std::vector<FieldT> &f_1v_coefficients, const field_subset<FieldT> &input_variable_domain,
+                                const field_subset<FieldT> &variable_domain, const field_subset<FieldT> &codeword_domain,
+                                const polynomial<FieldT> *fw_mask, std::vector<FieldT> &fw_over_codeword_domain,
+                                std::vector<FieldT> &variable_assignment)
+{
+    using namespace libiop_b200;
+    if (field_traits<FieldT>::kind != B200_FIELD_GF192) return false;
+    if (variable_domain.type() != affine_subspace_type || codeword_domain.type() != affine_subspace_type ||
+        input_variable_domain.type() != affine_subspace_type) return false;
+    const std::size_t n_V = variable_domain.num_elements(), n_L = codeword_domain.num_elements();
+    const std::size_t n_z = 1 + primary_input.size() + auxiliary_input.size();
+    if (n_V < 4096 || n_z > n_V || primary_input.size() + 1 != input_variable_domain.num_elements()) return false;
+
+    /* z on the device */
+    device_buffer d_z(n_z);
+    std::vector<FieldT> head({ FieldT::one() });
+    head.insert(head.end(), primary_input.begin(), primary_input.end());
+    d_z.upload_async(head);
+    d_z.upload_async(auxiliary_input, head.size());
+    throw_status(context(), b200_wait_uploads(context()));                /* `head` dies with this scope */
+
+    /* \hat f_w over V */
+    device_buffer d_f1v(n_V), d_fw(n_V);
+    { const device_view c(f_1v_coefficients); FFT_over_field_subset_device<FieldT>(c.buf(), f_1v_coefficients.size(), variable_domain, d_f1v); }
+    vec_mul_add<FieldT>(d_fw, d_z, nullptr, &d_f1v, nullptr, false, n_z);
+    if (n_z < n_V) throw_status(context(), b200_fill_zero(context(), d_fw.get(), n_z, n_V - n_z));
+
+    /* over L */
+    device_buffer d_L(n_L);
+    if (!LDE_over_field_subsets_device<FieldT>(d_fw, variable_domain, codeword_domain, d_L)) {
+        IFFT_over_field_subset_device<FieldT>(d_fw, variable_domain, d_f1v);
+        FFT_over_field_subset_device<FieldT>(d_f1v, n_V, codeword_domain, d_L);
+    }
+    if (fw_mask) {
+        device_buffer d_mask(n_L), d_Zv(n_L);
+        const device_view c(fw_mask->coefficients());
+        FFT_over_field_subset_device<FieldT>(c.buf(), fw_mask->coefficients().size(), codeword_domain, d_mask);
+        vanishing_polynomial_over_domain<FieldT>(d_Zv, vanishing_polynomial<FieldT>(variable_domain), codeword_domain);
+        vec_mul_add<FieldT>(d_L, d_L, nullptr, &d_Zv, &d_mask, false, n_L);
+    }
+
+    /* / Z_in: the table of Z_in over L collapses along the directions Z_in kills */
+    const vanishing_polynomial<FieldT> input_vp(input_variable_domain);
+    std::vector<FieldT> t = affine_function_table<FieldT>(codeword_domain, [&input_vp](const FieldT &x) { return input_vp.evaluation_at_point(x); },
+                                                          FieldT::one());
+    std::size_t lead = 0;
+    while (lead < codeword_domain.dimension() && t[1 + lead].is_zero()) ++lead;
+    t.erase(t.begin() + 1, t.begin() + 1 + lead);
+    const std::size_t q_dim = codeword_domain.dimension() - lead, n_q = std::size_t(1) << q_dim;
+    device_buffer d_q(n_q), d_qinv(n_q);
+    subspace_function_product<FieldT>(d_q, q_dim, { t });
+    vec_inverse<FieldT>(d_qinv, d_q, n_q);
+    throw_status(context(), b200_vec_mul_table(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), d_L.get(), d_L.get(),
+                                               d_qinv.get(), (uint32_t)lead, n_q - 1, n_L));
+    /* no synchronisation: the temporaries go back to the context's stream-ordered block cache */
+
+    fw_over_codeword_domain = make_lazy_vector<FieldT>(std::move(d_L), n_L);
+    variable_assignment = make_lazy_vector<FieldT>(std::move(d_z), n_z);
+    return true;
+}
+} // namespace b200_glue
+
+/* encoded_aurora_protocol::submit_witness_oracles (r1cs_rs_iop.tcc:481-614) with the witness codeword formed on the device
+   (above) and the variable assignment handed to create_Az_Bz_Cz_from_variable_assignment as the device-resident vector it
+   already is.  Domains that do not qualify run the reference's sequence of calls.  The order of the random draws
+   (R_Az, R_Bz, R_Cz, then the f_w mask) is the reference's. */
+#define B200_SUBMIT_WITNESS_SPECIALISE(FIELD)                                                                              \
+template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(                                             \
+    const r1cs_primary_input<FIELD> &primary_input, const r1cs_auxiliary_input<FIELD> &auxiliary_input)                    \
+{                                                                                                                          \
+    this->fz_oracle_->set_primary_input(primary_input);                                                                    \
+    libff::enter_block("Submit witness oracles");                                                                          \
+    if (this->params_.holographic()) this->holographic_multi_lincheck_->submit_sumcheck_masking_polynomials();             \
+    else this->multi_lincheck_->submit_sumcheck_masking_polynomials();                                                     \
+    libff::enter_block("Compute randomized f_w");                                                                          \
+    if (this->params_.make_zk()) {                                                                                         \
+        this->R_Az_ = polynomial<FIELD>::random_polynomial(this->params_.query_bound());                                   \
+        this->R_Bz_ = polynomial<FIELD>::random_polynomial(this->params_.query_bound());                                   \
+        this->R_Cz_ = polynomial<FIELD>::random_polynomial(this->params_.query_bound());                                   \
+    }                                                                                                                      \
+    std::vector<FIELD> f_1v_evaluations({ FIELD::one() });                                                                 \
+    f_1v_evaluations.insert(f_1v_evaluations.end(), primary_input.begin(), primary_input.end());                           \
+    this->f_1v_coefficients_ = IFFT_over_field_subset<FIELD>(f_1v_evaluations, this->input_variable_domain_);              \
+    if (this->params_.make_zk()) this->fw_mask_ = polynomial<FIELD>::random_polynomial(this->fw_mask_degree_);             \
+    std::vector<FIELD> variable_assignment;                                                                                \
+    if (!b200_glue::witness_codeword_on_device<FIELD>(primary_input, auxiliary_input, this->f_1v_coefficients_,            \
+            this->input_variable_domain_, this->variable_domain_, this->codeword_domain_,                                  \
+            this->params_.make_zk() ? &this->fw_mask_ : nullptr, this->fw_over_codeword_domain_, variable_assignment)) {   \
+        /* the reference's route: interpolate, add the mask, divide the coefficients, evaluate */                          \
+        const std::vector<FIELD> f_1v_over_variable_domain = FFT_over_field_subset<FIELD>(this->f_1v_coefficients_, this->variable_domain_); \
+        polynomial<FIELD> fw_prime(IFFT_over_field_subset<FIELD>(                                                          \
+            create_fw_prime_evals(f_1v_over_variable_domain, primary_input.size(), auxiliary_input, this->variable_domain_), \
+            this->variable_domain_));                                                                                      \
+        if (this->params_.make_zk()) fw_prime += vanishing_polynomial<FIELD>(this->variable_domain_) * this->fw_mask_;     \
+        fw_prime = polynomial_over_vanishing_polynomial(fw_prime, vanishing_polynomial<FIELD>(this->input_variable_domain_)).first; \
+        this->fw_over_codeword_domain_ = FFT_over_field_subset<FIELD>(fw_prime.coefficients(), this->codeword_domain_);    \
+        variable_assignment.assign(1, FIELD::one());                                                                       \
+        variable_assignment.insert(variable_assignment.end(), primary_input.begin(), primary_input.end());                 \
+        variable_assignment.insert(variable_assignment.end(), auxiliary_input.begin(), auxiliary_input.end());             \
+    }                                                                                                                      \
+    libff::leave_block("Compute randomized f_w");                                                                          \
+    libff::enter_block("Compute A/B/Cz");                                                                                  \
+    std::vector<FIELD> Az, Bz, Cz;                                                                                         \
+    this->constraint_system_->create_Az_Bz_Cz_from_variable_assignment(variable_assignment, Az, Bz, Cz);                   \
+    libff::leave_block("Compute A/B/Cz");                                                                                  \
+    libff::enter_block("Compute f_{A/B/Cz} over codeword domain");                                                         \
+    this->compute_fprime_ABCz_over_codeword_domain(Az, Bz, Cz);                                                            \
+    libff::leave_block("Compute f_{A/B/Cz} over codeword domain");                                                         \
+    libff::enter_block("Call IOP oracle submission routines");                                                             \
+    this->IOP_.submit_oracle(this->fw_handle_, std::move(this->fw_over_codeword_domain_));                                 \
+    this->IOP_.submit_oracle(this->fAz_handle_, std::move(this->fprime_Az_over_codeword_domain_));                         \
+    this->IOP_.submit_oracle(this->fBz_handle_, std::move(this->fprime_Bz_over_codeword_domain_));                         \
+    this->IOP_.submit_oracle(this->fCz_handle_, std::move(this->fprime_Cz_over_codeword_domain_));                         \
+    std::vector<FIELD>().swap(this->fw_over_codeword_domain_);                                                             \
+    std::vector<FIELD>().swap(this->fprime_Az_over_codeword_domain_);                                                      \
+    std::vector<FIELD>().swap(this->fprime_Bz_over_codeword_domain_);                                                      \
+    std::vector<FIELD>().swap(this->fprime_Cz_over_codeword_domain_);                                                      \
+    libff::leave_block("Call IOP oracle submission routines");                                                             \
+    libff::leave_block("Submit witness oracles");                                                                          \
+}
+B200_FOR_EACH_FIELD(B200_SUBMIT_WITNESS_SPECIALISE)
+#undef B200_SUBMIT_WITNESS_SPECIALISE
+
 #define B200_FZ_SPECIALISE(FIELD)                                                                                          \
 template<> inline std::shared_ptr<std::vector<FIELD>> fz_virtual_oracle<FIELD>::evaluated_contents(                        \
     const std::vector<std::shared_ptr<std::vector<FIELD>>> &constituent_oracle_evaluations) const                          \

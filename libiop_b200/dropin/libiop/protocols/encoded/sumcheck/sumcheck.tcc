@@ -48,4 +48,67 @@ template<> inline std::shared_ptr<std::vector<FIELD>> sumcheck_g_oracle<FIELD>::
 }
 B200_FOR_EACH_FIELD(B200_SUMCHECK_G_SPECIALISE)
 #undef B200_SUMCHECK_G_SPECIALISE
+
+namespace b200_glue {
+/* floor(P / Z_H) with P's n_p coefficients resident on the device (polynomial_over_vanishing_polynomial,
+   vanishing_polynomial.tcc:360-371, quotient only).  false = outside the range of the device recurrence (the conditions of
+   the shadows of vanishing_polynomial.tcc / linearized_polynomial.tcc); nothing is computed then. */
+template<typename FieldT>
+bool quotient_by_vanishing_on_device(const libiop_b200::device_buffer &d_p, std::size_t n_p, const vanishing_polynomial<FieldT> &Z,
+                                     libiop_b200::device_buffer &d_q)
+{
+    const std::size_t deg = Z.degree();
+    if (n_p <= deg || n_p - deg < 4096) return false;
+    std::vector<FieldT> coefs;
+    std::vector<std::size_t> pows;
+    FieldT lead = FieldT::one();
+    if (Z.type() == affine_subspace_type) {
+        const linearized_polynomial<FieldT> lin = Z.get_linearized_polynomial();
+        if (lin.num_terms() < 2 || lin.degree() != deg || (n_p - deg) / (deg - deg / 2) > 64) return false;
+        std::size_t p_pow = deg / 2;                       /* lin[j] multiplies y^(2^(j-1)) for j >= 1, lin[0] is the constant */
+        for (std::size_t j = lin.num_terms() - 1; j--; ) { coefs.push_back(lin[j]); pows.push_back(p_pow); p_pow /= 2; }
+        lead = lin[lin.num_terms() - 1];
+    } else {
+        if ((n_p - deg) / deg > 64) return false;
+        coefs.push_back(Z.constant_coefficient()); pows.push_back(0);
+    }
+    d_q = libiop_b200::device_buffer(n_p - deg);
+    libiop_b200::poly_divide_sparse_device<FieldT>(d_p, n_p, deg, lead, coefs, pows, d_q, nullptr);
+    return true;
+}
+} // namespace b200_glue
+
+/* batch_sumcheck_protocol::calculate_and_submit_proof (sumcheck.tcc:344-388): interpolate the combined f from its codeword,
+   divide by Z_H, submit h = the quotient over the codeword domain.  The reference moves a coefficient vector through three
+   host objects on the way (the IFFT result, the dividend, a copy of the quotient); here the chain
+       known-degree IFFT -> sparse division -> FFT
+   runs from device buffer to device buffer and h is submitted as the device-resident codeword it already is: three 24-50 MB
+   transfers each way and a 25 MB host copy less per proof at N = 2^20 (profiles/r2_host_gaps_N20_v1.txt vs _v2). */
+#define B200_SUMCHECK_PROVE_SPECIALISE(FIELD)                                                                              \
+template<> inline void batch_sumcheck_protocol<FIELD>::calculate_and_submit_proof()                                        \
+{                                                                                                                          \
+    const std::vector<FIELD> challenge = this->IOP_.obtain_verifier_random_message(this->challenge_handle_);               \
+    this->combined_f_oracle_->set_random_coefficients(challenge);                                                          \
+    const std::shared_ptr<std::vector<FIELD>> f_evaluations =                                                              \
+        this->IOP_.get_oracle_evaluations(std::make_shared<virtual_oracle_handle>(this->combined_f_oracle_handle_));       \
+    this->g_oracle_->set_claimed_sum(this->get_combined_claimed_sum(challenge));                                           \
+    using namespace libiop_b200;                                                                                           \
+    const vanishing_polynomial<FIELD> Z(this->summation_domain_);                                                          \
+    const device_buffer d_f = IFFT_of_known_degree_over_field_subset_to_device<FIELD>(*f_evaluations, this->degree_bound_, this->codeword_domain_); \
+    device_buffer d_h;                                                                                                     \
+    if (b200_glue::quotient_by_vanishing_on_device<FIELD>(d_f, this->degree_bound_, Z, d_h)) {                             \
+        const std::size_t n = this->codeword_domain_.num_elements();                                                       \
+        device_buffer d_out(n);                                                                                            \
+        FFT_over_field_subset_device<FIELD>(d_h, this->degree_bound_ - Z.degree(), this->codeword_domain_, d_out);         \
+        this->IOP_.submit_oracle(this->h_handle_, oracle<FIELD>(make_lazy_vector<FIELD>(std::move(d_out), n)));            \
+        return;                                                                                                            \
+    }                                                                                                                      \
+    std::vector<FIELD> coefficients = d_f.template download<FIELD>(d_f.size());                                            \
+    coefficients.resize(this->degree_bound_);                                                                              \
+    const std::pair<polynomial<FIELD>, polynomial<FIELD>> h_and_g =                                                        \
+        polynomial_over_vanishing_polynomial<FIELD>(polynomial<FIELD>(std::move(coefficients)), Z);                        \
+    this->IOP_.submit_oracle(this->h_handle_, oracle<FIELD>(FFT_over_field_subset<FIELD>(h_and_g.first.coefficients(), this->codeword_domain_))); \
+}
+B200_FOR_EACH_FIELD(B200_SUMCHECK_PROVE_SPECIALISE)
+#undef B200_SUMCHECK_PROVE_SPECIALISE
 } // namespace libiop

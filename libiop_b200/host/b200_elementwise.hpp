@@ -203,18 +203,25 @@ FieldT poly_eval(const device_buffer &coeffs, std::size_t n, const FieldT &x)
     return r;
 }
 
-/* P = Q*Z + R for a sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j] (b200_poly_divide_sparse);
-   returns {Q, R} with |Q| = |P| - deg and |R| = deg.  Requires |P| > deg. */
+/* P = Q*Z + R for a sparse divisor Z = lead*y^deg + sum_j coefs[j]*y^pows[j] (b200_poly_divide_sparse), device to device:
+   n_p > deg coefficients in d_p; d_q receives n_p - deg, d_r (may be null) deg coefficients */
+template<typename FieldT>
+void poly_divide_sparse_device(const device_buffer &d_p, std::size_t n_p, std::size_t deg, const FieldT &lead,
+                               const std::vector<FieldT> &coefs, const std::vector<std::size_t> &pows, device_buffer &d_q, device_buffer *d_r)
+{
+    const FieldT lead_inv = lead.inverse();
+    throw_status(context(), b200_poly_divide_sparse(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), d_p.get(), n_p, deg,
+                                                    limbs(lead_inv), coefs.size(), reinterpret_cast<const uint64_t *>(coefs.data()),
+                                                    pows.data(), d_q.get(), d_r ? d_r->get() : 0));
+}
+/* host vectors: returns {Q, R} with |Q| = |P| - deg and |R| = deg.  Requires |P| > deg. */
 template<typename FieldT>
 std::pair<std::vector<FieldT>, std::vector<FieldT>> poly_divide_sparse(const std::vector<FieldT> &P, std::size_t deg, const FieldT &lead,
                                                                        const std::vector<FieldT> &coefs, const std::vector<std::size_t> &pows)
 {
     device_buffer d_p(P.size()), d_q(P.size() - deg), d_r(deg);
     d_p.upload_async(P);
-    const FieldT lead_inv = lead.inverse();
-    throw_status(context(), b200_poly_divide_sparse(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), d_p.get(), P.size(), deg,
-                                                    limbs(lead_inv), coefs.size(), reinterpret_cast<const uint64_t *>(coefs.data()),
-                                                    pows.data(), d_q.get(), d_r.get()));
+    poly_divide_sparse_device<FieldT>(d_p, P.size(), deg, lead, coefs, pows, d_q, &d_r);
     std::vector<FieldT> q = d_q.template download<FieldT>(P.size() - deg);
     std::vector<FieldT> r = d_r.template download<FieldT>(deg);
     return std::make_pair(std::move(q), std::move(r));

@@ -136,29 +136,47 @@ template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_over_field_subset(const std::vector<FieldT> evals, DomainT domain)
 { return IFFT_over_field_subset_cref<FieldT>(evals, domain); }
 
-/* fft.hpp:78-88 (fft.tcc:435-475): additive -> first 2^k evaluations over the first k basis vectors (uploaded straight from
-   the caller's vector), multiplicative -> every (n/2^k)-th evaluation over the order-2^k sub-coset */
+/* fft.hpp:78-88 (fft.tcc:435-475): additive -> first 2^k evaluations over the first k basis vectors (a prefix of the
+   caller's vector: used in place when it is device-resident, uploaded otherwise), multiplicative -> every (n/2^k)-th
+   evaluation over the order-2^k sub-coset.  The coefficients (2^k of them) stay on the device. */
+template<typename FieldT, typename DomainT>
+device_buffer IFFT_of_known_degree_over_field_subset_to_device(const std::vector<FieldT> &evals, std::size_t degree, const DomainT &domain)
+{
+    std::size_t closest_power_of_two = 1;
+    while (closest_power_of_two < degree) closest_power_of_two <<= 1;
+    if (closest_power_of_two > evals.size() || evals.size() != domain.num_elements())
+        throw std::invalid_argument("IFFT_of_known_degree_over_field_subset: evaluation vector does not match the domain");
+    const DomainT minimal = domain.get_subset_of_order(closest_power_of_two);
+    device_buffer out(closest_power_of_two);
+    if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE) {
+        const device_view in(evals.data(), closest_power_of_two);
+        if (closest_power_of_two == 1) throw_status(context(), b200_copy(context(), out.get(), 0, in.get(), 0, 1));
+        else IFFT_over_field_subset_device<FieldT>(in.buf(), minimal, out);
+        return out;
+    }
+    const std::size_t freq = domain.num_elements() / closest_power_of_two;
+    device_buffer sub(closest_power_of_two);
+    if (const b200_buf resident = residency::instance().find(evals.data(), evals.size()))
+        throw_status(context(), b200_copy_strided(context(), sub.get(), 1, resident, 0, freq, closest_power_of_two));
+    else {
+        std::vector<FieldT> picked;
+        picked.reserve(closest_power_of_two);
+        for (std::size_t i = 0; i < domain.num_elements(); i += freq) picked.emplace_back(evals[i]);
+        sub.upload(picked);
+    }
+    if (closest_power_of_two == 1) return sub;
+    IFFT_over_field_subset_device<FieldT>(sub, minimal, out);
+    return out;
+}
 template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_of_known_degree_over_field_subset_cref(const std::vector<FieldT> &evals, std::size_t degree, const DomainT &domain)
 {
     std::size_t closest_power_of_two = 1;
     while (closest_power_of_two < degree) closest_power_of_two <<= 1;
-    const DomainT minimal = domain.get_subset_of_order(closest_power_of_two);
     if ((int)domain.type() == B200_DOMAIN_AFFINE_SUBSPACE)
-        return IFFT_over_field_subset_cref<FieldT>(evals, minimal, closest_power_of_two);
-    const std::size_t freq = domain.num_elements() / closest_power_of_two;
-    if (const b200_buf resident = residency::instance().find(evals.data(), evals.size())) {
-        /* device-resident codeword: take every freq-th evaluation on the device */
-        device_buffer sub(closest_power_of_two), out(closest_power_of_two);
-        throw_status(context(), b200_copy_strided(context(), sub.get(), 1, resident, 0, freq, closest_power_of_two));
-        if (closest_power_of_two == 1) return sub.template download<FieldT>(1);
-        IFFT_over_field_subset_device<FieldT>(sub, minimal, out);
-        return out.template download<FieldT>(closest_power_of_two);
-    }
-    std::vector<FieldT> sub;
-    sub.reserve(closest_power_of_two);
-    for (std::size_t i = 0; i < domain.num_elements(); i += freq) sub.emplace_back(evals[i]);
-    return IFFT_over_field_subset_cref<FieldT>(sub, minimal);
+        return IFFT_over_field_subset_cref<FieldT>(evals, domain.get_subset_of_order(closest_power_of_two), closest_power_of_two);
+    const device_buffer coeffs = IFFT_of_known_degree_over_field_subset_to_device<FieldT>(evals, degree, domain);
+    return coeffs.template download<FieldT>(closest_power_of_two);
 }
 template<typename FieldT, typename DomainT>
 std::vector<FieldT> IFFT_of_known_degree_over_field_subset(const std::vector<FieldT> evals, std::size_t degree, DomainT domain)
