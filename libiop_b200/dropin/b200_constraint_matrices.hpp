@@ -17,6 +17,7 @@
 #ifndef B200_DROPIN_CONSTRAINT_MATRICES_HPP_
 #define B200_DROPIN_CONSTRAINT_MATRICES_HPP_
 #include <cstdlib>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -40,10 +41,12 @@ struct flat_matrix {
 
 template<typename FieldT>
 class constraint_matrices {
+    struct host_arrays;
     struct entry {
         std::weak_ptr<r1cs_constraint_system<FieldT>> alive;
         bool built = false;
         flat_matrix M[3];
+        std::future<std::shared_ptr<host_arrays>> prep;       /* a flatten running beside the caller (prefetch) */
     };
     std::map<const void *, entry> entries_;
     std::mutex mu_;
@@ -63,40 +66,47 @@ class constraint_matrices {
         const unsigned avail = sched_getaffinity(0, sizeof set, &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
         return avail >= 4 ? 4u : (avail ? avail : 1u);
     }
+    struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
+    struct host_arrays {                                     /* the flattened matrices in (page-locked) host memory */
+        std::size_t n = 0;
+        uint64_t nnz[3] = { 0, 0, 0 };
+        std::vector<uint64_t> row_ptr[3];
+        std::unique_ptr<uint32_t[]> col[3], row[3];
+        std::unique_ptr<void, raw_free> coeff[3];
+    };
     /* Two passes over the constraints.  The first reads only the rows' term counts (the constraint array itself, sequential)
        and lays down the three row-pointer arrays; the second copies indices and coefficients into arrays of the exact size,
        row ranges split over a few threads (the pass is bound by the pointer chase into one heap block per linear
-       combination: 24.7 ms single-threaded with push_back at N = 2^20, profiles/r2_host_gaps_N20_v1.txt). */
-    static void build(entry &e, const r1cs_constraint_system<FieldT> &cs)
+       combination: 24.7 ms single-threaded with push_back at N = 2^20, profiles/r2_host_gaps_N20_v1.txt).  Host work only:
+       safe to run beside the thread that owns the device context. */
+    static std::shared_ptr<host_arrays> flatten(const r1cs_constraint_system<FieldT> &cs)
     {
-        using namespace libiop_b200;
+        std::shared_ptr<host_arrays> H = std::make_shared<host_arrays>();
         const std::size_t n = cs.constraints_.size();
-        std::vector<uint64_t> row_ptr[3];
-        for (int m = 0; m < 3; ++m) row_ptr[m].resize(n + 1);
+        H->n = n;
+        for (int m = 0; m < 3; ++m) H->row_ptr[m].resize(n + 1);
         uint64_t run[3] = { 0, 0, 0 };
         for (std::size_t i = 0; i < n; ++i) {
             const r1cs_constraint<FieldT> &c = cs.constraints_[i];
-            row_ptr[0][i] = run[0]; run[0] += c.a_.terms.size();
-            row_ptr[1][i] = run[1]; run[1] += c.b_.terms.size();
-            row_ptr[2][i] = run[2]; run[2] += c.c_.terms.size();
+            H->row_ptr[0][i] = run[0]; run[0] += c.a_.terms.size();
+            H->row_ptr[1][i] = run[1]; run[1] += c.b_.terms.size();
+            H->row_ptr[2][i] = run[2]; run[2] += c.c_.terms.size();
         }
-        struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
-        std::unique_ptr<uint32_t[]> col[3], row[3];
-        std::unique_ptr<void, raw_free> coeff_store[3];
         FieldT *coeff[3];
         for (int m = 0; m < 3; ++m) {
-            row_ptr[m][n] = run[m];
-            col[m].reset(new uint32_t[run[m] ? run[m] : 1]);
-            row[m].reset(new uint32_t[run[m] ? run[m] : 1]);
-            coeff_store[m].reset(::operator new((run[m] ? run[m] : 1) * sizeof(FieldT)));      /* every slot is written below */
-            coeff[m] = static_cast<FieldT *>(coeff_store[m].get());
+            H->row_ptr[m][n] = H->nnz[m] = run[m];
+            H->col[m].reset(new uint32_t[run[m] ? run[m] : 1]);
+            H->row[m].reset(new uint32_t[run[m] ? run[m] : 1]);
+            H->coeff[m].reset(::operator new((run[m] ? run[m] : 1) * sizeof(FieldT)));      /* every slot is written below */
+            coeff[m] = static_cast<FieldT *>(H->coeff[m].get());
         }
-        auto fill = [&](std::size_t i0, std::size_t i1) {
+        host_arrays *h = H.get();
+        auto fill = [&cs, h, &coeff](std::size_t i0, std::size_t i1) {
             for (std::size_t i = i0; i < i1; ++i) {
                 const linear_combination<FieldT> *lc[3] = { &cs.constraints_[i].a_, &cs.constraints_[i].b_, &cs.constraints_[i].c_ };
                 for (int m = 0; m < 3; ++m) {
-                    uint64_t k = row_ptr[m][i];
-                    for (const auto &t : lc[m]->terms) { col[m][k] = (uint32_t)t.index_; row[m][k] = (uint32_t)i; new (&coeff[m][k]) FieldT(t.coeff_); ++k; }
+                    uint64_t k = h->row_ptr[m][i];
+                    for (const auto &t : lc[m]->terms) { h->col[m][k] = (uint32_t)t.index_; h->row[m][k] = (uint32_t)i; new (&coeff[m][k]) FieldT(t.coeff_); ++k; }
                 }
             }
         };
@@ -108,17 +118,35 @@ class constraint_matrices {
             fill(0, n / T);
             for (auto &w : workers) w.join();
         }
+        return H;
+    }
+    static void upload(entry &e, const host_arrays &H)
+    {
+        using namespace libiop_b200;
         for (int m = 0; m < 3; ++m) {
             flat_matrix &F = e.M[m];
-            F.n_rows = n; F.nnz = run[m];
-            upload_bytes(F.row_ptr, row_ptr[m].data(), row_ptr[m].size() * sizeof(uint64_t));
-            upload_bytes(F.col, col[m].get(), F.nnz * sizeof(uint32_t));
-            upload_bytes(F.row, row[m].get(), F.nnz * sizeof(uint32_t));
+            F.n_rows = H.n; F.nnz = H.nnz[m];
+            upload_bytes(F.row_ptr, H.row_ptr[m].data(), H.row_ptr[m].size() * sizeof(uint64_t));
+            upload_bytes(F.col, H.col[m].get(), F.nnz * sizeof(uint32_t));
+            upload_bytes(F.row, H.row[m].get(), F.nnz * sizeof(uint32_t));
             F.coeff = device_buffer(F.nnz ? F.nnz : 1);
-            if (F.nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, reinterpret_cast<const uint64_t *>(coeff[m]), F.nnz));
+            if (F.nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, static_cast<const uint64_t *>(H.coeff[m].get()), F.nnz));
         }
-        throw_status(context(), b200_sync(context()));        /* the host arrays die with this scope */
+        throw_status(context(), b200_wait_uploads(context()));        /* the host arrays die with the caller's scope */
         e.built = true;
+    }
+    static bool worth_it(const r1cs_constraint_system<FieldT> &cs)
+    {
+        return cs.constraints_.size() >= 16384 && cs.num_variables() + 1 < (std::size_t(1) << 32);
+    }
+    /* the live entry of `cs` under the lock, or nullptr */
+    entry *live_entry(const r1cs_constraint_system<FieldT> *cs, std::shared_ptr<r1cs_constraint_system<FieldT>> &keep)
+    {
+        auto it = entries_.find(cs);
+        if (it == entries_.end()) return nullptr;
+        keep = it->second.alive.lock();
+        if (keep.get() != cs) { entries_.erase(it); return nullptr; }
+        return &it->second;
     }
 
 public:
@@ -132,21 +160,43 @@ public:
         for (auto it = entries_.begin(); it != entries_.end();)           /* systems that died release their device arrays */
             if (it->second.alive.expired()) it = entries_.erase(it); else ++it;
         entry &e = entries_[cs.get()];
-        const std::shared_ptr<r1cs_constraint_system<FieldT>> cur = e.alive.lock();
-        if (cur.get() != cs.get()) { e = entry(); e.alive = cs; }
+        /* the same OWNER (control block), not merely the same address: a caller's system borrowed again for the next proof
+           (aurora_iop.tcc shadow) is a new registration and is flattened anew — it may have changed in between */
+        const bool same_owner = !e.alive.expired() && !e.alive.owner_before(cs) && !cs.owner_before(e.alive);
+        if (!same_owner) { e = entry(); e.alive = cs; }
     }
     /* the flattened matrices of the constraint system at `cs` (built on first use), or nullptr if that object is not a
        registered, still-living system large enough to be worth it */
     const flat_matrix *get(const r1cs_constraint_system<FieldT> *cs)
     {
         std::lock_guard<std::mutex> lock(mu_);
+        std::shared_ptr<r1cs_constraint_system<FieldT>> keep;
+        entry *e = live_entry(cs, keep);
+        if (!e || !worth_it(*cs)) return nullptr;
+        if (!e->built) {
+            const std::shared_ptr<host_arrays> H = e->prep.valid() ? e->prep.get() : flatten(*cs);
+            upload(*e, *H);
+        }
+        return e->M;
+    }
+    /* Start flattening `cs` on another thread (host work only) if its matrices are going to be asked for and are not there
+       yet: the prover calls this before the witness codeword keeps the device — and this thread — busy, so that get()
+       finds the arrays ready.  The worker holds the owning pointer: the system cannot die under it. */
+    void prefetch(const r1cs_constraint_system<FieldT> *cs)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        std::shared_ptr<r1cs_constraint_system<FieldT>> keep;
+        entry *e = live_entry(cs, keep);
+        if (!e || e->built || e->prep.valid() || !worth_it(*cs)) return;
+        if (const char *off = std::getenv("B200_FLATTEN_ASYNC")) if (off[0] == '0') return;
+        e->prep = std::async(std::launch::async, [keep]() { return flatten(*keep); });
+    }
+    /* wait for a flatten that prefetch() started and nobody consumed (error paths) */
+    void settle(const r1cs_constraint_system<FieldT> *cs)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
         auto it = entries_.find(cs);
-        if (it == entries_.end()) return nullptr;
-        const std::shared_ptr<r1cs_constraint_system<FieldT>> cur = it->second.alive.lock();
-        if (cur.get() != cs) { entries_.erase(it); return nullptr; }
-        if (cs->constraints_.size() < 16384 || cs->num_variables() + 1 >= (std::size_t(1) << 32)) return nullptr;
-        if (!it->second.built) build(it->second, *cs);
-        return it->second.M;
+        if (it != entries_.end() && it->second.prep.valid()) it->second.prep.wait();
     }
 };
 

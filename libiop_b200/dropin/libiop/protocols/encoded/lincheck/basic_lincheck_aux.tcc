@@ -43,6 +43,35 @@ template<typename FieldT> FieldT evaluate_polynomial(const std::vector<FieldT> &
     return libiop_b200::poly_eval<FieldT>(c.buf(), coefficients.size(), x);
 }
 
+/* Coefficients of the polynomial with evaluations `evals` over `domain`, as a vector whose interpolation (one IFFT) is put
+   off until something reads the coefficients; the evaluations stay attached to it under "evals". */
+template<typename FieldT>
+std::vector<FieldT> deferred_interpolation(libiop_b200::device_buffer &&evals, const field_subset<FieldT> &domain)
+{
+    using namespace libiop_b200;
+    const std::size_t n = domain.num_elements();
+    std::map<std::string, device_buffer> inputs;
+    inputs.emplace("evals", std::move(evals));
+    return make_deferred_vector<FieldT>(n, std::move(inputs), [domain](device_buffer &out, std::map<std::string, device_buffer> &in) {
+        IFFT_over_field_subset_device<FieldT>(in.at("evals"), domain, out);
+    });
+}
+/* p over the codeword domain: straight from its evaluations over the summation domain when they are still attached to the
+   coefficient vector and the pair of domains has a fused extension, else from the coefficients */
+template<typename FieldT>
+void extend_p_alpha(const std::vector<FieldT> &coefficients, const field_subset<FieldT> &summation_domain,
+                    const field_subset<FieldT> &codeword_domain, libiop_b200::device_buffer &out)
+{
+    using namespace libiop_b200;
+    const std::size_t n_S = summation_domain.num_elements();
+    if (coefficients.size() == n_S) {
+        if (const b200_buf evals = residency::instance().attachment(coefficients.data(), "evals", n_S))
+            if (LDE_over_field_subsets_device<FieldT>(device_buffer::alias(evals, n_S), summation_domain, codeword_domain, out)) return;
+    }
+    const device_view c(coefficients);
+    FFT_over_field_subset_device<FieldT>(c.buf(), coefficients.size(), codeword_domain, out);
+}
+
 /* the constraint system behind an r1cs_sparse_matrix (a protected member: reached through a pointer to member formed in
    a derived class), so that rows can be walked by reference instead of through get_row()'s by-value copies */
 template<typename FieldT>
@@ -81,13 +110,8 @@ template<> inline std::shared_ptr<std::vector<FIELD>> multi_lincheck_virtual_ora
     using namespace libiop_b200;                                                                                           \
     const std::size_t n = this->codeword_domain_.num_elements();                                                           \
     device_buffer d_p1(n), d_p2(n), d_comb(n), d_out(n);                                                                   \
-    {                                                                                                                      \
-        device_view c1 = b200_glue::to_device(this->p_alpha_prime_.coefficients());                                            \
-        FFT_over_field_subset_device<FIELD>(c1.buf(), this->p_alpha_prime_.coefficients().size(), this->codeword_domain_, d_p1); \
-        device_view c2 = b200_glue::to_device(this->p_alpha_ABC_.coefficients());                                                \
-        FFT_over_field_subset_device<FIELD>(c2.buf(), this->p_alpha_ABC_.coefficients().size(), this->codeword_domain_, d_p2);   \
-        throw_status(context(), b200_sync(context()));                                                                     \
-    }                                                                                                                      \
+    b200_glue::extend_p_alpha<FIELD>(this->p_alpha_prime_.coefficients(), this->summation_domain_, this->codeword_domain_, d_p1); \
+    b200_glue::extend_p_alpha<FIELD>(this->p_alpha_ABC_.coefficients(), this->summation_domain_, this->codeword_domain_, d_p2); \
     device_view d_fz = b200_glue::to_device(*constituent_oracle_evaluations[0]);                                           \
     std::vector<device_view> d_Mz;                                                                                         \
     std::vector<const device_buffer *> Mz_ptrs;                                                                            \
@@ -174,11 +198,10 @@ template<> inline void multi_lincheck_virtual_oracle<FIELD>::set_challenge(const
     }                                                                                                                      \
     libff::leave_block("multi_lincheck compute p_alpha_ABC");                                                              \
     libff::enter_block("multi_lincheck IFFT p_alphas");                                                                    \
-    device_buffer c_abc(n_S), c_prime(n_S);                                                                                \
-    IFFT_over_field_subset_device<FIELD>(d_abc, this->summation_domain_, c_abc);                                           \
-    IFFT_over_field_subset_device<FIELD>(d_prime, this->summation_domain_, c_prime);                                       \
-    this->p_alpha_ABC_ = polynomial<FIELD>(make_lazy_vector<FIELD>(std::move(c_abc), n_S));                                \
-    this->p_alpha_prime_ = polynomial<FIELD>(make_lazy_vector<FIELD>(std::move(c_prime), n_S));                            \
+    /* the coefficient vectors are DEFERRED: the prover only ever needs both polynomials over the codeword domain, which the   \
+       fused LDE produces from these evaluations (extend_p_alpha); the interpolation runs if somebody asks for coefficients */ \
+    this->p_alpha_ABC_ = polynomial<FIELD>(b200_glue::deferred_interpolation<FIELD>(std::move(d_abc), this->summation_domain_)); \
+    this->p_alpha_prime_ = polynomial<FIELD>(b200_glue::deferred_interpolation<FIELD>(std::move(d_prime), this->summation_domain_)); \
     libff::leave_block("multi_lincheck IFFT p_alphas");                                                                    \
 }                                                                                                                          \
 template<> inline FIELD multi_lincheck_virtual_oracle<FIELD>::evaluation_at_point(                                         \

@@ -3,6 +3,7 @@
    domain.  On the B200: Z_{1,v} over L is generated on the device from dim(L)+1 host values, f_{1,v} is LDE'd on the
    device from its |1,v| coefficients, and one fused pass forms the result; only f_w goes up and f_z comes down. */
 #include "b200_dropin_common.hpp"
+#include "b200_constraint_matrices.hpp"
 #include B200_REF_FILE(libiop/protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc)
 
 namespace libiop {
@@ -50,6 +51,17 @@ B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
 #undef B200_ABCZ_SPECIALISE
 
 namespace b200_glue {
+/* starts constraint_matrices::prefetch for the scope's constraint system and makes sure the worker is done when the scope
+   ends, however it ends */
+template<typename FieldT>
+struct flatten_ahead {
+    const r1cs_constraint_system<FieldT> *cs;
+    explicit flatten_ahead(const r1cs_constraint_system<FieldT> *c) : cs(c) { constraint_matrices<FieldT>::instance().prefetch(cs); }
+    ~flatten_ahead() { constraint_matrices<FieldT>::instance().settle(cs); }
+    flatten_ahead(const flatten_ahead &) = delete;
+    flatten_ahead &operator=(const flatten_ahead &) = delete;
+};
+
 /* f_w over the codeword domain WITHOUT a coefficient vector (submit_witness_oracles, r1cs_rs_iop.tcc:497-569).
    The reference interpolates \hat f_w = (witness - f_{1,v}) over the variable domain (IFFT), divides the coefficient vector by
    the vanishing polynomial of the input positions, and evaluates the quotient over L (FFT).  For subspace domains over
@@ -135,6 +147,8 @@ template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(  
 {                                                                                                                          \
     this->fz_oracle_->set_primary_input(primary_input);                                                                    \
     libff::enter_block("Submit witness oracles");                                                                          \
+    /* the constraint matrices are flattened beside this thread while it forms the witness codeword */                    \
+    const b200_glue::flatten_ahead<FIELD> matrices_ahead(this->constraint_system_.get());                                  \
     if (this->params_.holographic()) this->holographic_multi_lincheck_->submit_sumcheck_masking_polynomials();             \
     else this->multi_lincheck_->submit_sumcheck_masking_polynomials();                                                     \
     libff::enter_block("Compute randomized f_w");                                                                          \

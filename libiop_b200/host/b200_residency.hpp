@@ -24,6 +24,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -40,6 +41,12 @@ class residency {
         device_buffer buf;
         std::unordered_map<std::size_t, std::array<uint64_t, 3>> fetched;   /* positions already read by the query phase */
         std::map<std::string, device_buffer> attached;       /* device arrays derived from this vector (e.g. its extension over L) */
+        std::function<void(device_buffer &, std::map<std::string, device_buffer> &)> pending;   /* contents not computed yet (put_deferred) */
+        b200_buf contents()                                   /* runs the deferred computation on first use */
+        {
+            if (pending) { auto f = std::move(pending); pending = nullptr; f(buf, attached); }
+            return buf.get();
+        }
     };
     std::map<uintptr_t, entry> blocks_;                       /* by block address, ordered: lookups by contained address */
     std::mutex mu_;
@@ -80,6 +87,26 @@ public:
         ++generation_;
     }
 
+    /* The same, with the contents still to be computed: `fill(buf, attachments)` runs — once, under the table's lock, so it
+       must not call back into the table — the first time anything asks for the contents (a device view, a query, a host
+       touch).  Consumers that only need something the producer attached (e.g. the evaluations the coefficients would be
+       interpolated from) never trigger it.  `inputs` become the entry's attachments and are what `fill` reads. */
+    void put_deferred(void *host, std::size_t n, device_buffer &&buf, std::map<std::string, device_buffer> &&inputs,
+                      std::function<void(device_buffer &, std::map<std::string, device_buffer> &)> fill)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        entry &e = blocks_[(uintptr_t)host];
+        e.n = n; e.buf = std::move(buf); e.fetched.clear(); e.attached = std::move(inputs); e.pending = std::move(fill);
+        bytes_ += n * 24;
+        ++generation_;
+    }
+    bool is_pending(const void *host)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        auto it = blocks_.find((uintptr_t)host);
+        return it != blocks_.end() && (bool)it->second.pending;
+    }
+
     /* the block died (operator delete) */
     void drop(const void *host)
     {
@@ -100,7 +127,7 @@ public:
         const std::size_t off = (uintptr_t)host - it->first;
         if (off % 24) { ++misses_; return 0; }
         ++hits_;
-        return it->second.buf.get() + off;
+        return it->second.contents() + off;
     }
     bool is_resident(const void *host) { std::lock_guard<std::mutex> lock(mu_); return containing((uintptr_t)host, 1) != blocks_.end(); }
 
@@ -112,6 +139,7 @@ public:
         if (it == blocks_.end()) return false;
         void *base = (void *)it->first;
         const std::size_t n = it->second.n;
+        it->second.contents();
         device_buffer buf = std::move(it->second.buf);
         bytes_ -= n * 24;
         blocks_.erase(it);
@@ -131,7 +159,7 @@ public:
         auto f = it->second.fetched.find(position);
         if (f == it->second.fetched.end()) {
             std::array<uint64_t, 3> v;
-            throw_status(context(), b200_gather(context(), v.data(), it->second.buf.get(), &position, 1));
+            throw_status(context(), b200_gather(context(), v.data(), it->second.contents(), &position, 1));
             ++gathers_;
             f = it->second.fetched.emplace(position, v).first;
         }
@@ -165,7 +193,7 @@ public:
         if (it == blocks_.end()) return false;
         for (std::size_t p : positions) if (p >= it->second.n) return false;
         if (!positions.empty()) {
-            throw_status(context(), b200_gather(context(), out, it->second.buf.get(), positions.data(), positions.size()));
+            throw_status(context(), b200_gather(context(), out, it->second.contents(), positions.data(), positions.size()));
             ++gathers_;
         }
         return true;
@@ -199,7 +227,7 @@ public:
             if (p < it->second.n && !it->second.fetched.count(p)) want.push_back(p);
         if (want.empty()) return;
         std::vector<uint64_t> vals(3 * want.size());
-        throw_status(context(), b200_gather(context(), vals.data(), it->second.buf.get(), want.data(), want.size()));
+        throw_status(context(), b200_gather(context(), vals.data(), it->second.contents(), want.data(), want.size()));
         ++gathers_;
         for (std::size_t i = 0; i < want.size(); ++i) {
             std::array<uint64_t, 3> v = {vals[3 * i], vals[3 * i + 1], vals[3 * i + 2]};
@@ -260,6 +288,31 @@ std::vector<FieldT> make_lazy_vector(device_buffer &&buf, std::size_t n)
         if (n) throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(v.data()), buf.get(), 0, n));
         return v;
     }
+    return buf.template download<FieldT>(n);
+}
+/* A lazy vector whose contents are not even computed until somebody asks for them (residency::put_deferred): `fill(out,
+   inputs)` writes the n elements into `out` from the device arrays in `inputs`, which stay attached to the vector under
+   their keys.  Without lazy blocks the computation runs at once and the result is downloaded (the inputs are dropped). */
+template<typename FieldT>
+std::vector<FieldT> make_deferred_vector(std::size_t n, std::map<std::string, device_buffer> &&inputs,
+                                         std::function<void(device_buffer &, std::map<std::string, device_buffer> &)> fill)
+{
+    static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    device_buffer buf(n);
+    if (n >= residency::min_elems && lazy_region::instance().enabled()) {
+        alloc_hint &hint = current_alloc_hint();
+        hint.kind = alloc_hint::lazy; hint.bytes = n * sizeof(FieldT);
+        std::vector<FieldT> v = make_uninitialized_vector<FieldT>(n);
+        hint.kind = alloc_hint::none;
+        if (v.size() == n && lazy_region::instance().contains(v.data())) {
+            residency::instance().put_deferred(v.data(), n, std::move(buf), std::move(inputs), std::move(fill));
+            return v;
+        }
+        fill(buf, inputs);
+        if (n) throw_status(context(), b200_download(context(), reinterpret_cast<uint64_t *>(v.data()), buf.get(), 0, n));
+        return v;
+    }
+    fill(buf, inputs);
     return buf.template download<FieldT>(n);
 }
 /* historical name */

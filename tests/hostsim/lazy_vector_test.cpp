@@ -4,7 +4,9 @@
    query-phase gathers.  Also built against the real library by tests/cpp (same source) for the -m gpu run. */
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../../libiop_b200/host/b200_device.hpp"
@@ -110,6 +112,38 @@ int main()
     {   /* 9. small results are simply downloaded */
         std::vector<el> s = make_lazy_vector<el>(device_pattern(100, 3), 100);
         CHECK(!lazy_region::instance().contains(s.data()) && s[99] == (el{{3 + 99, 9 + 99, ~99ull}}));
+    }
+    {   /* 10. deferred vectors: the contents are computed on first use only; inputs stay attached */
+        int runs = 0;
+        auto copy_input = [&runs](device_buffer &out, std::map<std::string, device_buffer> &in) {
+            ++runs;
+            throw_status(context(), b200_copy(context(), out.get(), 0, in.at("evals").get(), 0, out.size()));
+        };
+        {
+            std::map<std::string, device_buffer> in; in.emplace("evals", device_pattern(n, 17));
+            std::vector<el> d = make_deferred_vector<el>(n, std::move(in), copy_input);
+            CHECK(res.is_resident(d.data()) && res.is_pending(d.data()) && runs == 0);
+            CHECK(res.attachment(d.data(), "evals", n) != 0 && runs == 0);            /* reading an attachment does not trigger it */
+            { device_view view(d); CHECK(runs == 1 && !view.buf().owns()); CHECK(read_back(view.buf(), n)[9] == (el{{17 + 9, 51 + 9, ~9ull}})); }
+            CHECK(!res.is_pending(d.data()));
+            { device_view again(d); CHECK(runs == 1); }
+        }
+        {   /* never used: never computed */
+            std::map<std::string, device_buffer> in; in.emplace("evals", device_pattern(n, 19));
+            std::vector<el> d = make_deferred_vector<el>(n, std::move(in), copy_input);
+            CHECK(runs == 1);
+        }
+        CHECK(runs == 1 && res.resident_bytes() == 0);
+        {   /* a host touch computes, then downloads */
+            std::map<std::string, device_buffer> in; in.emplace("evals", device_pattern(n, 23));
+            std::vector<el> d = make_deferred_vector<el>(n, std::move(in), copy_input);
+            CHECK(d[n - 1] == (el{{23 + n - 1, 69 + n - 1, ~(uint64_t)(n - 1)}}) && runs == 2 && !res.is_resident(d.data()));
+        }
+        {   /* small: computed at once */
+            std::map<std::string, device_buffer> in; in.emplace("evals", device_pattern(64, 29));
+            std::vector<el> d = make_deferred_vector<el>(64, std::move(in), copy_input);
+            CHECK(runs == 3 && d[5] == (el{{29 + 5, 87 + 5, ~5ull}}));
+        }
     }
     CHECK(res.resident_bytes() == 0);
     std::printf("%d failed\n", failures);
