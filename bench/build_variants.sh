@@ -33,6 +33,9 @@ for v in "$@"; do
     leaf2)  build leaf2  -DB200_LEAF1_MINBLOCKS=2 ;;      # round 2: register budget of merkle_leaf1_kernel (2 / 3 / 4 CTAs of 256 per SM)
     leaf3)  build leaf3  -DB200_LEAF1_MINBLOCKS=3 ;;
     leaf4)  build leaf4  -DB200_LEAF1_MINBLOCKS=4 ;;
+    inv8)   build inv8   -DB200_INV_RUN=8 ;;              # round 2: elements per Itoh-Tsujii inversion in gf192_inv_kernel
+    inv16)  build inv16  -DB200_INV_RUN=16 ;;
+    inv32)  build inv32  -DB200_INV_RUN=32 ;;
   esac
 done
 wait

@@ -47,4 +47,7 @@ cd23, cd20 = L.Domain.coset(fp, 23, gen), L.Domain.coset(fp, 20, gen)
 res["ntt 2^20->2^23"] = t(lambda: dev.fp_ntt_dev(fp, cd23, c, 1 << n, e))
 res["intt 2^20"] = t(lambda: dev.fp_intt_dev(fp, cd20, c, o))
 res["fold fp 2^23 eta1"] = t(lambda: dev.fri_fold_dev(2, fp, cd23, 1, x, e, f))
+import ctypes as C
+res["inv 2^23"] = t(lambda: dev._chk(dev.lib.b200_gf192_inv(dev.ctx, C.c_uint64(e2[0]), C.c_uint64(e), C.c_size_t(1 << m))))
+res["inv 2^20"] = t(lambda: dev._chk(dev.lib.b200_gf192_inv(dev.ctx, C.c_uint64(o), C.c_uint64(c), C.c_size_t(1 << n))))
 print(os.environ.get("B200_LIB", "default"), " | ".join(f"{k}: {v:.3f} ms" for k, v in res.items()))

@@ -951,7 +951,9 @@ __global__ void gf192_mul_kernel(gf192 *out, const gf192 *a, const gf192 *b, siz
    the same over the whole vector sequentially): RUN consecutive elements share one Itoh-Tsujii inversion (191 squarings +
    12 multiplications) at the price of 3 multiplications each.  Zero maps to zero like x^(2^192-2) and like the
    reference's has_zeroes path (utils.tcc:73-103). */
+#ifndef B200_INV_RUN
 #define B200_INV_RUN 8
+#endif
 __global__ void __launch_bounds__(128) gf192_inv_kernel(gf192 *out, const gf192 *a, size_t n)
 {
     const size_t runs = (n + B200_INV_RUN - 1) / B200_INV_RUN;

@@ -16,6 +16,9 @@
  */
 #ifndef B200_DROPIN_CONSTRAINT_MATRICES_HPP_
 #define B200_DROPIN_CONSTRAINT_MATRICES_HPP_
+#include <array>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <future>
 #include <map>
@@ -57,41 +60,61 @@ class constraint_matrices {
         dst.reset(new device_bytes(bytes ? bytes : 8));
         if (bytes) throw_status(context(), b200_upload_bytes(context(), dst->get(), static_cast<const uint8_t *>(src), bytes));
     }
-    /* host threads for the fill pass: B200_HOST_THREADS, else up to 4 of the cores this process may run on */
+    /* host threads for the flatten: B200_HOST_THREADS, else up to 8 of the cores this process may run on */
     static unsigned fill_threads(std::size_t n)
     {
         if (const char *e = std::getenv("B200_HOST_THREADS")) { const long v = std::atol(e); return v < 1 ? 1u : (v > 64 ? 64u : (unsigned)v); }
         if (n < (std::size_t(1) << 16)) return 1;
         cpu_set_t set; CPU_ZERO(&set);
         const unsigned avail = sched_getaffinity(0, sizeof set, &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
-        return avail >= 4 ? 4u : (avail ? avail : 1u);
+        return avail >= 8 ? 8u : (avail ? avail : 1u);
     }
     struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
     struct host_arrays {                                     /* the flattened matrices in (page-locked) host memory */
         std::size_t n = 0;
         uint64_t nnz[3] = { 0, 0, 0 };
-        std::vector<uint64_t> row_ptr[3];
+        std::unique_ptr<uint64_t[]> row_ptr[3];             /* n + 1 each */
         std::unique_ptr<uint32_t[]> col[3], row[3];
         std::unique_ptr<void, raw_free> coeff[3];
     };
-    /* Two passes over the constraints.  The first reads only the rows' term counts (the constraint array itself, sequential)
-       and lays down the three row-pointer arrays; the second copies indices and coefficients into arrays of the exact size,
-       row ranges split over a few threads (the pass is bound by the pointer chase into one heap block per linear
-       combination: 24.7 ms single-threaded with push_back at N = 2^20, profiles/r2_host_gaps_N20_v1.txt).  Host work only:
-       safe to run beside the thread that owns the device context. */
+    /* runs f(t) for t = 0 .. T-1, t = 0 on the calling thread */
+    template<typename Fn> static void on_threads(unsigned T, Fn f)
+    {
+        std::vector<std::thread> workers;
+        for (unsigned t = 1; t < T; ++t) workers.emplace_back(f, t);
+        f(0u);
+        for (auto &w : workers) w.join();
+    }
+    /* Two passes over the constraints, row ranges split over a few threads.  The first reads only the rows' term counts (the
+       constraint array itself, sequential) and lays down the row pointers relative to the range's start; the second — after
+       the ranges' totals are prefix-summed and arrays of the exact size allocated — rebases them and copies indices and
+       coefficients.  The work is bound by memory traffic (~300 bytes per constraint, one heap block per linear combination:
+       24.7 ms single-threaded with push_back at N = 2^20, profiles/r2_host_gaps_N20_v1.txt).  Host work only: safe to run
+       beside the thread that owns the device context. */
     static std::shared_ptr<host_arrays> flatten(const r1cs_constraint_system<FieldT> &cs)
     {
         std::shared_ptr<host_arrays> H = std::make_shared<host_arrays>();
         const std::size_t n = cs.constraints_.size();
+        const bool trace = std::getenv("B200_FLATTEN_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         H->n = n;
-        for (int m = 0; m < 3; ++m) H->row_ptr[m].resize(n + 1);
+        for (int m = 0; m < 3; ++m) { H->row_ptr[m].reset(new uint64_t[n + 1]); }
+        const unsigned T = fill_threads(n);
+        std::vector<std::array<uint64_t, 3>> range_total(T);
+        host_arrays *h = H.get();
+        on_threads(T, [&cs, h, n, T, &range_total](unsigned t) {
+            uint64_t run[3] = { 0, 0, 0 };
+            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) {
+                const r1cs_constraint<FieldT> &c = cs.constraints_[i];
+                h->row_ptr[0][i] = run[0]; run[0] += c.a_.terms.size();
+                h->row_ptr[1][i] = run[1]; run[1] += c.b_.terms.size();
+                h->row_ptr[2][i] = run[2]; run[2] += c.c_.terms.size();
+            }
+            range_total[t] = { run[0], run[1], run[2] };
+        });
+        std::vector<std::array<uint64_t, 3>> range_base(T);
         uint64_t run[3] = { 0, 0, 0 };
-        for (std::size_t i = 0; i < n; ++i) {
-            const r1cs_constraint<FieldT> &c = cs.constraints_[i];
-            H->row_ptr[0][i] = run[0]; run[0] += c.a_.terms.size();
-            H->row_ptr[1][i] = run[1]; run[1] += c.b_.terms.size();
-            H->row_ptr[2][i] = run[2]; run[2] += c.c_.terms.size();
-        }
+        for (unsigned t = 0; t < T; ++t) for (int m = 0; m < 3; ++m) { range_base[t][m] = run[m]; run[m] += range_total[t][m]; }
         FieldT *coeff[3];
         for (int m = 0; m < 3; ++m) {
             H->row_ptr[m][n] = H->nnz[m] = run[m];
@@ -100,23 +123,24 @@ class constraint_matrices {
             H->coeff[m].reset(::operator new((run[m] ? run[m] : 1) * sizeof(FieldT)));      /* every slot is written below */
             coeff[m] = static_cast<FieldT *>(H->coeff[m].get());
         }
-        host_arrays *h = H.get();
-        auto fill = [&cs, h, &coeff](std::size_t i0, std::size_t i1) {
-            for (std::size_t i = i0; i < i1; ++i) {
+        const auto t1 = std::chrono::steady_clock::now();
+        on_threads(T, [&cs, h, n, T, &range_base, &coeff](unsigned t) {
+            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) {
                 const linear_combination<FieldT> *lc[3] = { &cs.constraints_[i].a_, &cs.constraints_[i].b_, &cs.constraints_[i].c_ };
+                if (i + 12 < end) {                            /* the term blocks are separate heap objects: ask for them early */
+                    const r1cs_constraint<FieldT> &ahead = cs.constraints_[i + 12];
+                    __builtin_prefetch(ahead.a_.terms.data()); __builtin_prefetch(ahead.b_.terms.data()); __builtin_prefetch(ahead.c_.terms.data());
+                }
                 for (int m = 0; m < 3; ++m) {
-                    uint64_t k = h->row_ptr[m][i];
-                    for (const auto &t : lc[m]->terms) { h->col[m][k] = (uint32_t)t.index_; h->row[m][k] = (uint32_t)i; new (&coeff[m][k]) FieldT(t.coeff_); ++k; }
+                    uint64_t k = (h->row_ptr[m][i] += range_base[t][m]);
+                    for (const auto &term : lc[m]->terms) { h->col[m][k] = (uint32_t)term.index_; h->row[m][k] = (uint32_t)i; new (&coeff[m][k]) FieldT(term.coeff_); ++k; }
                 }
             }
-        };
-        const unsigned T = fill_threads(n);
-        if (T <= 1) fill(0, n);
-        else {
-            std::vector<std::thread> workers;
-            for (unsigned t = 1; t < T; ++t) workers.emplace_back(fill, n * t / T, n * (t + 1) / T);
-            fill(0, n / T);
-            for (auto &w : workers) w.join();
+        });
+        if (trace) {
+            const auto t2 = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[b200] flatten: %zu rows, count pass %.2f ms, fill pass %.2f ms on %u threads\n", n,
+                         std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(), T);
         }
         return H;
     }
@@ -126,7 +150,7 @@ class constraint_matrices {
         for (int m = 0; m < 3; ++m) {
             flat_matrix &F = e.M[m];
             F.n_rows = H.n; F.nnz = H.nnz[m];
-            upload_bytes(F.row_ptr, H.row_ptr[m].data(), H.row_ptr[m].size() * sizeof(uint64_t));
+            upload_bytes(F.row_ptr, H.row_ptr[m].get(), (H.n + 1) * sizeof(uint64_t));
             upload_bytes(F.col, H.col[m].get(), F.nnz * sizeof(uint32_t));
             upload_bytes(F.row, H.row[m].get(), F.nnz * sizeof(uint32_t));
             F.coeff = device_buffer(F.nnz ? F.nnz : 1);
