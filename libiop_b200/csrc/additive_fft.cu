@@ -949,10 +949,10 @@ __global__ void gf192_mul_kernel(gf192 *out, const gf192 *a, const gf192 *b, siz
 }
 /* Element-wise inversion with Montgomery's trick per thread (the reference's batch_inverse, algebra/utils.tcc:38-69, does
    the same over the whole vector sequentially): RUN consecutive elements share one Itoh-Tsujii inversion (191 squarings +
-   12 multiplications) at the price of 3 multiplications each.  Zero maps to zero like x^(2^192-2) and like the
+   12 multiplications) at the price of 3 multiplications each (the run lives in local memory: L1-resident).  Zero maps to zero like x^(2^192-2) and like the
    reference's has_zeroes path (utils.tcc:73-103). */
 #ifndef B200_INV_RUN
-#define B200_INV_RUN 8
+#define B200_INV_RUN 32          /* measured at 2^23 elements: 8 -> 4.17 ms, 16 -> 3.21 ms, 32 -> 2.35 ms (profiles/r2_time_ops_v4.txt) */
 #endif
 __global__ void __launch_bounds__(128) gf192_inv_kernel(gf192 *out, const gf192 *a, size_t n)
 {

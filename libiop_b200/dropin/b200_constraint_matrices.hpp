@@ -4,9 +4,10 @@
  * The reference walks the constraint system's rows twice per proof with one heap-allocated row object per step:
  *   r1cs_constraint_system::create_Az_Bz_Cz_from_variable_assignment (relations/r1cs.tcc:236-266)   A z, B z, C z
  *   multi_lincheck_virtual_oracle::set_challenge (lincheck/basic_lincheck_aux.tcc:63-84)             (sum_m r_m M_m)^T alpha-powers
- * Both are products with the same three sparse matrices.  The first of the two that runs flattens them in one sequential
- * pass over the constraints into CSR arrays (row pointers, column indices, explicit row indices, coefficients), uploads
- * them, and both products run on the device from there (b200_spmv_csr_dev, b200_gf192_scatter_mul_add_dev).
+ * Both are products with the same three sparse matrices.  The first of the two that asks for a matrix flattens it into CSR
+ * arrays (row pointers, column indices, explicit row indices, coefficients: two multi-threaded passes over the
+ * constraints, no arithmetic), uploads them, and both products run on the device from there (b200_spmv_csr_dev,
+ * b200_gf192_scatter_mul_add_dev).
  *
  * Lifetime: an entry belongs to one r1cs_constraint_system OBJECT.  r1cs_sparse_matrix's constructor (shadowed in
  * relations/sparse_matrix.tcc) registers the shared_ptr it is given; the entry holds a weak_ptr and is valid only while
@@ -20,7 +21,6 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
-#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -44,12 +44,10 @@ struct flat_matrix {
 
 template<typename FieldT>
 class constraint_matrices {
-    struct host_arrays;
     struct entry {
         std::weak_ptr<r1cs_constraint_system<FieldT>> alive;
-        bool built = false;
+        bool built[3] = { false, false, false };
         flat_matrix M[3];
-        std::future<std::shared_ptr<host_arrays>> prep;       /* a flatten running beside the caller (prefetch) */
     };
     std::map<const void *, entry> entries_;
     std::mutex mu_;
@@ -69,14 +67,6 @@ class constraint_matrices {
         const unsigned avail = sched_getaffinity(0, sizeof set, &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
         return avail >= 8 ? 8u : (avail ? avail : 1u);
     }
-    struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
-    struct host_arrays {                                     /* the flattened matrices in (page-locked) host memory */
-        std::size_t n = 0;
-        uint64_t nnz[3] = { 0, 0, 0 };
-        std::unique_ptr<uint64_t[]> row_ptr[3];             /* n + 1 each */
-        std::unique_ptr<uint32_t[]> col[3], row[3];
-        std::unique_ptr<void, raw_free> coeff[3];
-    };
     /* runs f(t) for t = 0 .. T-1, t = 0 on the calling thread */
     template<typename Fn> static void on_threads(unsigned T, Fn f)
     {
@@ -85,91 +75,71 @@ class constraint_matrices {
         f(0u);
         for (auto &w : workers) w.join();
     }
-    /* Two passes over the constraints, row ranges split over a few threads.  The first reads only the rows' term counts (the
-       constraint array itself, sequential) and lays down the row pointers relative to the range's start; the second — after
-       the ranges' totals are prefix-summed and arrays of the exact size allocated — rebases them and copies indices and
-       coefficients.  The work is bound by memory traffic (~300 bytes per constraint, one heap block per linear combination:
-       24.7 ms single-threaded with push_back at N = 2^20, profiles/r2_host_gaps_N20_v1.txt).  Host work only: safe to run
-       beside the thread that owns the device context. */
-    static std::shared_ptr<host_arrays> flatten(const r1cs_constraint_system<FieldT> &cs)
+    static const linear_combination<FieldT> &row_of(const r1cs_constraint<FieldT> &c, int m) { return m == 0 ? c.a_ : m == 1 ? c.b_ : c.c_; }
+    struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
+
+    /* Matrix m of `cs` (0 = A, 1 = B, 2 = C) flattened and uploaded.  Two passes over the constraints, row ranges split
+       over a few threads: the first reads the rows' term counts and lays down the row pointers relative to the range's
+       start; the second — after the ranges' totals are prefix-summed and arrays of the exact size allocated (page-locked:
+       the uploads are DMA in place) — rebases them and copies indices and coefficients.  The work is bound by memory
+       traffic (one heap block per linear combination).  One matrix at a time so that the caller can start the device on
+       A z while B is being flattened (r1cs_rs_iop.tcc shadow); profiles/r2_host_gaps_N20_v*.txt. */
+    static void build(entry &e, const r1cs_constraint_system<FieldT> &cs, int m)
     {
-        std::shared_ptr<host_arrays> H = std::make_shared<host_arrays>();
+        using namespace libiop_b200;
         const std::size_t n = cs.constraints_.size();
         const bool trace = std::getenv("B200_FLATTEN_TRACE") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
-        H->n = n;
-        for (int m = 0; m < 3; ++m) { H->row_ptr[m].reset(new uint64_t[n + 1]); }
+        std::unique_ptr<uint64_t[]> row_ptr(new uint64_t[n + 1]);
         const unsigned T = fill_threads(n);
-        std::vector<std::array<uint64_t, 3>> range_total(T);
-        host_arrays *h = H.get();
-        on_threads(T, [&cs, h, n, T, &range_total](unsigned t) {
-            uint64_t run[3] = { 0, 0, 0 };
-            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) {
-                const r1cs_constraint<FieldT> &c = cs.constraints_[i];
-                h->row_ptr[0][i] = run[0]; run[0] += c.a_.terms.size();
-                h->row_ptr[1][i] = run[1]; run[1] += c.b_.terms.size();
-                h->row_ptr[2][i] = run[2]; run[2] += c.c_.terms.size();
-            }
-            range_total[t] = { run[0], run[1], run[2] };
+        std::vector<uint64_t> range_total(T), range_base(T);
+        uint64_t *rp = row_ptr.get();
+        on_threads(T, [&cs, rp, n, T, m, &range_total](unsigned t) {
+            uint64_t run = 0;
+            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) { rp[i] = run; run += row_of(cs.constraints_[i], m).terms.size(); }
+            range_total[t] = run;
         });
-        std::vector<std::array<uint64_t, 3>> range_base(T);
-        uint64_t run[3] = { 0, 0, 0 };
-        for (unsigned t = 0; t < T; ++t) for (int m = 0; m < 3; ++m) { range_base[t][m] = run[m]; run[m] += range_total[t][m]; }
-        FieldT *coeff[3];
-        for (int m = 0; m < 3; ++m) {
-            H->row_ptr[m][n] = H->nnz[m] = run[m];
-            H->col[m].reset(new uint32_t[run[m] ? run[m] : 1]);
-            H->row[m].reset(new uint32_t[run[m] ? run[m] : 1]);
-            H->coeff[m].reset(::operator new((run[m] ? run[m] : 1) * sizeof(FieldT)));      /* every slot is written below */
-            coeff[m] = static_cast<FieldT *>(H->coeff[m].get());
-        }
+        uint64_t nnz = 0;
+        for (unsigned t = 0; t < T; ++t) { range_base[t] = nnz; nnz += range_total[t]; }
+        rp[n] = nnz;
+        std::unique_ptr<uint32_t[]> col(new uint32_t[nnz ? nnz : 1]), row(new uint32_t[nnz ? nnz : 1]);
+        std::unique_ptr<void, raw_free> coeff_store(::operator new((nnz ? nnz : 1) * sizeof(FieldT)));      /* every slot is written below */
+        FieldT *coeff = static_cast<FieldT *>(coeff_store.get());
+        uint32_t *colp = col.get(), *rowp = row.get();
         const auto t1 = std::chrono::steady_clock::now();
-        on_threads(T, [&cs, h, n, T, &range_base, &coeff](unsigned t) {
+        on_threads(T, [&cs, rp, colp, rowp, coeff, n, T, m, &range_base](unsigned t) {
             for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) {
-                const linear_combination<FieldT> *lc[3] = { &cs.constraints_[i].a_, &cs.constraints_[i].b_, &cs.constraints_[i].c_ };
-                if (i + 12 < end) {                            /* the term blocks are separate heap objects: ask for them early */
-                    const r1cs_constraint<FieldT> &ahead = cs.constraints_[i + 12];
-                    __builtin_prefetch(ahead.a_.terms.data()); __builtin_prefetch(ahead.b_.terms.data()); __builtin_prefetch(ahead.c_.terms.data());
-                }
-                for (int m = 0; m < 3; ++m) {
-                    uint64_t k = (h->row_ptr[m][i] += range_base[t][m]);
-                    for (const auto &term : lc[m]->terms) { h->col[m][k] = (uint32_t)term.index_; h->row[m][k] = (uint32_t)i; new (&coeff[m][k]) FieldT(term.coeff_); ++k; }
-                }
+                uint64_t k = (rp[i] += range_base[t]);
+                for (const auto &term : row_of(cs.constraints_[i], m).terms) { colp[k] = (uint32_t)term.index_; rowp[k] = (uint32_t)i; new (&coeff[k]) FieldT(term.coeff_); ++k; }
             }
         });
-        if (trace) {
-            const auto t2 = std::chrono::steady_clock::now();
-            std::fprintf(stderr, "[b200] flatten: %zu rows, count pass %.2f ms, fill pass %.2f ms on %u threads\n", n,
-                         std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(), T);
-        }
-        return H;
-    }
-    static void upload(entry &e, const host_arrays &H)
-    {
-        using namespace libiop_b200;
-        for (int m = 0; m < 3; ++m) {
-            flat_matrix &F = e.M[m];
-            F.n_rows = H.n; F.nnz = H.nnz[m];
-            upload_bytes(F.row_ptr, H.row_ptr[m].get(), (H.n + 1) * sizeof(uint64_t));
-            upload_bytes(F.col, H.col[m].get(), F.nnz * sizeof(uint32_t));
-            upload_bytes(F.row, H.row[m].get(), F.nnz * sizeof(uint32_t));
-            F.coeff = device_buffer(F.nnz ? F.nnz : 1);
-            if (F.nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, static_cast<const uint64_t *>(H.coeff[m].get()), F.nnz));
-        }
-        throw_status(context(), b200_wait_uploads(context()));        /* the host arrays die with the caller's scope */
-        e.built = true;
+        const auto t2 = std::chrono::steady_clock::now();
+        flat_matrix &F = e.M[m];
+        F.n_rows = n; F.nnz = nnz;
+        upload_bytes(F.row_ptr, rp, (n + 1) * sizeof(uint64_t));
+        upload_bytes(F.col, colp, nnz * sizeof(uint32_t));
+        upload_bytes(F.row, rowp, nnz * sizeof(uint32_t));
+        F.coeff = device_buffer(nnz ? nnz : 1);
+        if (nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, reinterpret_cast<const uint64_t *>(coeff), nnz));
+        throw_status(context(), b200_wait_uploads(context()));        /* the host arrays die with this scope */
+        e.built[m] = true;
+        if (trace)
+            std::fprintf(stderr, "[b200] flatten %c: %zu rows, %llu entries, count pass %.2f ms, fill pass %.2f ms on %u threads, upload %.2f ms\n",
+                         "ABC"[m], n, (unsigned long long)nnz, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                         std::chrono::duration<double, std::milli>(t2 - t1).count(), T,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
     }
     static bool worth_it(const r1cs_constraint_system<FieldT> &cs)
     {
         return cs.constraints_.size() >= 16384 && cs.num_variables() + 1 < (std::size_t(1) << 32);
     }
-    /* the live entry of `cs` under the lock, or nullptr */
-    entry *live_entry(const r1cs_constraint_system<FieldT> *cs, std::shared_ptr<r1cs_constraint_system<FieldT>> &keep)
+    /* the live entry of `cs` (call under the lock), or nullptr */
+    entry *live_entry(const r1cs_constraint_system<FieldT> *cs)
     {
         auto it = entries_.find(cs);
         if (it == entries_.end()) return nullptr;
-        keep = it->second.alive.lock();
-        if (keep.get() != cs) { entries_.erase(it); return nullptr; }
+        const std::shared_ptr<r1cs_constraint_system<FieldT>> cur = it->second.alive.lock();
+        if (cur.get() != cs) { entries_.erase(it); return nullptr; }
         return &it->second;
     }
 
@@ -189,38 +159,24 @@ public:
         const bool same_owner = !e.alive.expired() && !e.alive.owner_before(cs) && !cs.owner_before(e.alive);
         if (!same_owner) { e = entry(); e.alive = cs; }
     }
-    /* the flattened matrices of the constraint system at `cs` (built on first use), or nullptr if that object is not a
-       registered, still-living system large enough to be worth it */
+    /* matrix m (0 = A, 1 = B, 2 = C) of the constraint system at `cs`, flattened on first use, or nullptr if that object is
+       not a registered, still-living system large enough to be worth it */
+    const flat_matrix *get_matrix(const r1cs_constraint_system<FieldT> *cs, int m)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        entry *e = live_entry(cs);
+        if (!e || !worth_it(*cs)) return nullptr;
+        if (!e->built[m]) build(*e, *cs, m);
+        return &e->M[m];
+    }
+    /* all three (an array of 3) */
     const flat_matrix *get(const r1cs_constraint_system<FieldT> *cs)
     {
         std::lock_guard<std::mutex> lock(mu_);
-        std::shared_ptr<r1cs_constraint_system<FieldT>> keep;
-        entry *e = live_entry(cs, keep);
+        entry *e = live_entry(cs);
         if (!e || !worth_it(*cs)) return nullptr;
-        if (!e->built) {
-            const std::shared_ptr<host_arrays> H = e->prep.valid() ? e->prep.get() : flatten(*cs);
-            upload(*e, *H);
-        }
+        for (int m = 0; m < 3; ++m) if (!e->built[m]) build(*e, *cs, m);
         return e->M;
-    }
-    /* Start flattening `cs` on another thread (host work only) if its matrices are going to be asked for and are not there
-       yet: the prover calls this before the witness codeword keeps the device — and this thread — busy, so that get()
-       finds the arrays ready.  The worker holds the owning pointer: the system cannot die under it. */
-    void prefetch(const r1cs_constraint_system<FieldT> *cs)
-    {
-        std::lock_guard<std::mutex> lock(mu_);
-        std::shared_ptr<r1cs_constraint_system<FieldT>> keep;
-        entry *e = live_entry(cs, keep);
-        if (!e || e->built || e->prep.valid() || !worth_it(*cs)) return;
-        if (const char *off = std::getenv("B200_FLATTEN_ASYNC")) if (off[0] == '0') return;
-        e->prep = std::async(std::launch::async, [keep]() { return flatten(*keep); });
-    }
-    /* wait for a flatten that prefetch() started and nobody consumed (error paths) */
-    void settle(const r1cs_constraint_system<FieldT> *cs)
-    {
-        std::lock_guard<std::mutex> lock(mu_);
-        auto it = entries_.find(cs);
-        if (it != entries_.end() && it->second.prep.valid()) it->second.prep.wait();
     }
 };
 

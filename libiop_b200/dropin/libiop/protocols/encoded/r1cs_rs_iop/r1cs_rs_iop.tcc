@@ -51,16 +51,35 @@ B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
 #undef B200_ABCZ_SPECIALISE
 
 namespace b200_glue {
-/* starts constraint_matrices::prefetch for the scope's constraint system and makes sure the worker is done when the scope
-   ends, however it ends */
+/* f_Az, f_Bz, f_Cz over the codeword domain, one matrix at a time: flatten M (host), then M z and its extension to L
+   (device, asynchronous) — so the device extends A z while the host flattens B, and B z while it flattens C
+   (create_Az_Bz_Cz_from_variable_assignment + compute_fprime_ABCz_over_codeword_domain, r1cs_rs_iop.tcc:449-479, 571-598,
+   without zero knowledge: nothing happens between the products and their extensions).  false = this constraint system
+   has no device-resident matrices (too small, or not registered); nothing is done then. */
 template<typename FieldT>
-struct flatten_ahead {
-    const r1cs_constraint_system<FieldT> *cs;
-    explicit flatten_ahead(const r1cs_constraint_system<FieldT> *c) : cs(c) { constraint_matrices<FieldT>::instance().prefetch(cs); }
-    ~flatten_ahead() { constraint_matrices<FieldT>::instance().settle(cs); }
-    flatten_ahead(const flatten_ahead &) = delete;
-    flatten_ahead &operator=(const flatten_ahead &) = delete;
-};
+bool extend_constraint_products(const r1cs_constraint_system<FieldT> &cs, const std::vector<FieldT> &variable_assignment,
+                                const field_subset<FieldT> &constraint_domain, const field_subset<FieldT> &codeword_domain,
+                                std::vector<FieldT> *const out[3])
+{
+    using namespace libiop_b200;
+    const std::size_t n_H = constraint_domain.num_elements(), n_L = codeword_domain.num_elements();
+    if (cs.constraints_.size() != n_H) return false;
+    for (int m = 0; m < 3; ++m) {
+        const flat_matrix *M = constraint_matrices<FieldT>::instance().get_matrix(&cs, m);
+        if (!M) { if (m) throw std::logic_error("B200 drop-in: constraint matrices went away mid-proof"); return false; }
+        const device_view d_z(variable_assignment);
+        device_buffer d_y(n_H), d_out(n_L);
+        throw_status(context(), b200_spmv_csr_dev(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), M->n_rows,
+                                                  M->row_ptr->get(), M->col->get(), M->coeff.get(), d_z.get(), d_y.get()));
+        if (!LDE_over_field_subsets_device<FieldT>(d_y, constraint_domain, codeword_domain, d_out)) {
+            device_buffer coeffs(n_H);
+            IFFT_over_field_subset_device<FieldT>(d_y, constraint_domain, coeffs);
+            FFT_over_field_subset_device<FieldT>(coeffs, n_H, codeword_domain, d_out);
+        }
+        *out[m] = make_lazy_vector<FieldT>(std::move(d_out), n_L);
+    }
+    return true;
+}
 
 /* f_w over the codeword domain WITHOUT a coefficient vector (submit_witness_oracles, r1cs_rs_iop.tcc:497-569).
    The reference interpolates \hat f_w = (witness - f_{1,v}) over the variable domain (IFFT), divides the coefficient vector by
@@ -147,8 +166,6 @@ template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(  
 {                                                                                                                          \
     this->fz_oracle_->set_primary_input(primary_input);                                                                    \
     libff::enter_block("Submit witness oracles");                                                                          \
-    /* the constraint matrices are flattened beside this thread while it forms the witness codeword */                    \
-    const b200_glue::flatten_ahead<FIELD> matrices_ahead(this->constraint_system_.get());                                  \
     if (this->params_.holographic()) this->holographic_multi_lincheck_->submit_sumcheck_masking_polynomials();             \
     else this->multi_lincheck_->submit_sumcheck_masking_polynomials();                                                     \
     libff::enter_block("Compute randomized f_w");                                                                          \
@@ -179,11 +196,15 @@ template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(  
     }                                                                                                                      \
     libff::leave_block("Compute randomized f_w");                                                                          \
     libff::enter_block("Compute A/B/Cz");                                                                                  \
+    std::vector<FIELD> *const extended[3] = { &this->fprime_Az_over_codeword_domain_, &this->fprime_Bz_over_codeword_domain_, \
+                                              &this->fprime_Cz_over_codeword_domain_ };                                    \
+    const bool pipelined = !this->params_.make_zk() && b200_glue::extend_constraint_products<FIELD>(                       \
+        *this->constraint_system_, variable_assignment, this->constraint_domain_, this->codeword_domain_, extended);       \
     std::vector<FIELD> Az, Bz, Cz;                                                                                         \
-    this->constraint_system_->create_Az_Bz_Cz_from_variable_assignment(variable_assignment, Az, Bz, Cz);                   \
+    if (!pipelined) this->constraint_system_->create_Az_Bz_Cz_from_variable_assignment(variable_assignment, Az, Bz, Cz);   \
     libff::leave_block("Compute A/B/Cz");                                                                                  \
     libff::enter_block("Compute f_{A/B/Cz} over codeword domain");                                                         \
-    this->compute_fprime_ABCz_over_codeword_domain(Az, Bz, Cz);                                                            \
+    if (!pipelined) this->compute_fprime_ABCz_over_codeword_domain(Az, Bz, Cz);                                            \
     libff::leave_block("Compute f_{A/B/Cz} over codeword domain");                                                         \
     libff::enter_block("Call IOP oracle submission routines");                                                             \
     this->IOP_.submit_oracle(this->fw_handle_, std::move(this->fw_over_codeword_domain_));                                 \

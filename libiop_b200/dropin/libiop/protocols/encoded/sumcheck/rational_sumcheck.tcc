@@ -26,10 +26,9 @@ template<> inline std::shared_ptr<std::vector<FIELD>> sumcheck_constraint_oracle
     device_buffer d_t(n), d_u(n), d_out(n);                                                                                \
     if (this->field_subset_type_ == affine_subspace_type) {                                                                \
         /* d_t = x^-1, d_u = mu' x^|H|  ->  d_u = p + mu' x^(|H|-1) */                                                     \
-        domain_element_powers<FIELD>(d_t, this->codeword_domain_, 1, FIELD::one());                                        \
-        vec_inverse<FIELD>(d_t, d_t, n);                                                                                   \
+        const device_buffer &d_xinv = subspace_element_inverses<FIELD>(this->codeword_domain_);                            \
         domain_element_powers<FIELD>(d_u, this->codeword_domain_, order_H, this->eps_inv_times_claimed_sum_);              \
-        vec_mul_add<FIELD>(d_u, d_u, &d_t, &d_p.buf(), nullptr, false, n);                                                 \
+        vec_mul_add<FIELD>(d_u, d_u, &d_xinv, &d_p.buf(), nullptr, false, n);                                              \
         vec_mul_add<FIELD>(d_t, d_u, &d_D.buf(), &d_N.buf(), nullptr, true, n);          /* D * (...) - N */               \
         vec_mul_table<FIELD>(d_out, &d_t, Z_inv, (unsigned)libff::log2(order_H), ~std::size_t(0), n);                      \
     } else {                                                                                                               \

@@ -24,12 +24,11 @@ template<> inline std::shared_ptr<std::vector<FIELD>> sumcheck_g_oracle<FIELD>::
     device_buffer d_Z(n), d_t(n), d_u(n), d_out(n);                                                                        \
     vanishing_polynomial_over_domain<FIELD>(d_Z, this->Z_, this->codeword_domain_);                                        \
     if (this->field_subset_type_ == affine_subspace_type) {                                                                \
-        /* d_t = elements of L, then their inverses; d_u = eps^-1 mu * x^|H| */                                            \
-        domain_element_powers<FIELD>(d_t, this->codeword_domain_, 1, FIELD::one());                                        \
-        throw_status(context(), b200_gf192_inv(context(), d_t.get(), d_t.get(), n));                                       \
+        /* x^-1 over L: the domain's table (kept on the device across proofs); d_u = eps^-1 mu * x^|H| */                  \
+        const device_buffer &d_xinv = subspace_element_inverses<FIELD>(this->codeword_domain_);                            \
         domain_element_powers<FIELD>(d_u, this->codeword_domain_, this->summation_domain_.num_elements(),                  \
                                      this->eps_inv_times_claimed_sum_);                                                    \
-        vec_mul_add<FIELD>(d_u, d_u, &d_t, &d_Z, &d_h.buf(), false, n);          /* mu' x^(|H|-1) + Z_H h */                     \
+        vec_mul_add<FIELD>(d_u, d_u, &d_xinv, &d_Z, &d_h.buf(), false, n);       /* mu' x^(|H|-1) + Z_H h */                     \
         vec_mul_add<FIELD>(d_out, d_f.buf(), nullptr, &d_u, nullptr, true, n);   /* f - (...) */                                 \
     } else {                                                                                                               \
         /* d_t = f - Z_H h; d_u = constant |H|^-1 mu ... folded: (f - Z_H h - c) * x^-1 */                                 \

@@ -13,6 +13,7 @@
 
 #include <cstring>
 #include <list>
+#include <mutex>
 #include <stdexcept>
 #include <utility>
 #include <vector>
@@ -175,6 +176,31 @@ void domain_elements_affine(device_buffer &out, const DomainT &domain, bool nega
     } else {
         geometric_sequence<FieldT>(out, domain.num_elements(), sign * domain.shift(), domain.generator(), offset);
     }
+}
+
+/* x^-1 for every element x of an affine subspace, in domain order (zero stays zero): a table that depends on the domain
+   alone, like the transforms' twiddle tables — sumcheck's g oracle needs it over the codeword domain in every proof
+   (sumcheck.tcc:82-99: x^(|H|-1) = x^|H| * x^-1; 4.2 ms of inversions at |L| = 2^23).  The last two domains' tables stay on
+   the device (|L| * 24 bytes each); the returned buffer is valid until two other domains have been asked for. */
+template<typename FieldT, typename DomainT>
+const device_buffer &subspace_element_inverses(const DomainT &domain)
+{
+    static_assert(sizeof(FieldT) == 24, "field elements must be 3 x u64");
+    struct entry { std::vector<FieldT> key; device_buffer inv; };
+    static std::list<entry> *cache = new std::list<entry>();           /* never destroyed: device buffers outlive no context */
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<FieldT> key(1, domain.shift());
+    key.insert(key.end(), domain.basis().begin(), domain.basis().end());
+    for (auto it = cache->begin(); it != cache->end(); ++it)
+        if (it->key == key) { cache->splice(cache->begin(), *cache, it); return cache->front().inv; }
+    const std::size_t n = domain.num_elements();
+    device_buffer inv(n);
+    domain_elements_affine<FieldT>(inv, domain, false, FieldT::zero());
+    vec_inverse<FieldT>(inv, inv, n);
+    while (cache->size() >= 2) { throw_status(context(), b200_sync(context())); cache->pop_back(); }
+    cache->push_front(entry{ std::move(key), std::move(inv) });
+    return cache->front().inv;
 }
 
 /* Z(x) for every element x of the domain, Z a vanishing polynomial of a subset H of the same kind
