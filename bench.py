@@ -54,12 +54,14 @@ def workload(log_n=LOG_N):
     """The hot-path call sequence of aurora_snark_prover (non-zk, rho=3, FRI localization 2), SURVEY.md §3.1."""
     n, m = log_n, log_n + RHO
     N = 1 << n
-    # f_1v over the variable domain, f_w, f_1v over L (f_z), p_alpha' and p_alpha_ABC over L, h
-    ffts = [(32, n), (N - 32, m), (32, m), (N, m), (N, m), (N - 1, m)]
-    # f_Az, f_Bz, f_Cz: evaluations over H straight to L (b200_gf192_lde; the reference's IFFT(H) + FFT(L), r1cs_rs_iop.tcc:449-479)
-    ldes = [(n, m)] * 3
-    # f_1v, f_w, p_alpha_ABC, p_alpha', f_1v again (f_z), sumcheck's combined f, the final FRI polynomial
-    iffts = [5, n, n, n, 5, n + 1, 4]
+    # the calls the drop-in's prover makes (bench/host_gaps.py lists them; profiles/r2_host_gaps_N20_v3.txt):
+    # f_1v over the variable domain, f_1v over L (f_z), h = the sumcheck quotient over L
+    ffts = [(32, n), (32, m), (N - 1, m)]
+    # evaluations over H / the variable domain straight to L (b200_gf192_lde; the reference's IFFT + FFT pairs): f_w, f_Az, f_Bz,
+    # f_Cz (r1cs_rs_iop.tcc:449-479, 497-569), p_alpha' and p_alpha_ABC (basic_lincheck_aux.tcc:86-144)
+    ldes = [(n, m)] * 6
+    # f_1v (twice: submit_witness_oracles and the f_z oracle), sumcheck's combined f, the final FRI polynomial
+    iffts = [5, 5, n + 1, 4]
     folds = [(m, 1)] + [(k, 2) for k in range(m - 1, 4, -2)]        # (dim of L_i, eta)
     trees = [(4, m, 2), (1, m, 2)] + [(1, k, 4) for k in range(m - 1, 4, -2)]   # (n_oracles, dim, coset)
     return ffts, ldes, iffts, folds, trees
@@ -296,7 +298,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "gf2^192 (carry-less u32 limbs) + u64 BLAKE2b", "data": "synthetic",
         "config": dict(CONFIG),
-        "value_scope": "hot-path calls of one proof (6 FFT, 3 fused LDE, 7 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
+        "value_scope": "hot-path calls of one proof as the drop-in prover makes them (6 fused LDE, 3 FFT, 4 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
                        "the whole prover is `e2e`",
         "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

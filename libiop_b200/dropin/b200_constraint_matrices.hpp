@@ -159,6 +159,12 @@ public:
         const bool same_owner = !e.alive.expired() && !e.alive.owner_before(cs) && !cs.owner_before(e.alive);
         if (!same_owner) { e = entry(); e.alive = cs; }
     }
+    /* will get_matrix() / get() serve this constraint system? */
+    bool serves(const r1cs_constraint_system<FieldT> *cs)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        return live_entry(cs) != nullptr && worth_it(*cs);
+    }
     /* matrix m (0 = A, 1 = B, 2 = C) of the constraint system at `cs`, flattened on first use, or nullptr if that object is
        not a registered, still-living system large enough to be worth it */
     const flat_matrix *get_matrix(const r1cs_constraint_system<FieldT> *cs, int m)

@@ -97,7 +97,7 @@ bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input,
                                 const std::vector<FieldT> &f_1v_coefficients, const field_subset<FieldT> &input_variable_domain,
                                 const field_subset<FieldT> &variable_domain, const field_subset<FieldT> &codeword_domain,
                                 const polynomial<FieldT> *fw_mask, std::vector<FieldT> &fw_over_codeword_domain,
-                                std::vector<FieldT> &variable_assignment)
+                                std::vector<FieldT> *variable_assignment /* null: the caller's products run on the host */)
 {
     using namespace libiop_b200;
     if (field_traits<FieldT>::kind != B200_FIELD_GF192) return false;
@@ -151,7 +151,7 @@ bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input,
     /* no synchronisation: the temporaries go back to the context's stream-ordered block cache */
 
     fw_over_codeword_domain = make_lazy_vector<FieldT>(std::move(d_L), n_L);
-    variable_assignment = make_lazy_vector<FieldT>(std::move(d_z), n_z);
+    if (variable_assignment) *variable_assignment = make_lazy_vector<FieldT>(std::move(d_z), n_z);
     return true;
 }
 } // namespace b200_glue
@@ -179,9 +179,13 @@ template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(  
     this->f_1v_coefficients_ = IFFT_over_field_subset<FIELD>(f_1v_evaluations, this->input_variable_domain_);              \
     if (this->params_.make_zk()) this->fw_mask_ = polynomial<FIELD>::random_polynomial(this->fw_mask_degree_);             \
     std::vector<FIELD> variable_assignment;                                                                                \
-    if (!b200_glue::witness_codeword_on_device<FIELD>(primary_input, auxiliary_input, this->f_1v_coefficients_,            \
-            this->input_variable_domain_, this->variable_domain_, this->codeword_domain_,                                  \
-            this->params_.make_zk() ? &this->fw_mask_ : nullptr, this->fw_over_codeword_domain_, variable_assignment)) {   \
+    /* z stays on the device only if the products with A, B, C run there (a host loop would fault it back in) */           \
+    const bool device_products = b200_glue::constraint_matrices<FIELD>::instance().serves(this->constraint_system_.get()); \
+    const bool witness_on_device = b200_glue::witness_codeword_on_device<FIELD>(primary_input, auxiliary_input,            \
+            this->f_1v_coefficients_, this->input_variable_domain_, this->variable_domain_, this->codeword_domain_,        \
+            this->params_.make_zk() ? &this->fw_mask_ : nullptr, this->fw_over_codeword_domain_,                           \
+            device_products ? &variable_assignment : nullptr);                                                             \
+    if (!witness_on_device) {                                                                                              \
         /* the reference's route: interpolate, add the mask, divide the coefficients, evaluate */                          \
         const std::vector<FIELD> f_1v_over_variable_domain = FFT_over_field_subset<FIELD>(this->f_1v_coefficients_, this->variable_domain_); \
         polynomial<FIELD> fw_prime(IFFT_over_field_subset<FIELD>(                                                          \
@@ -190,6 +194,8 @@ template<> inline void encoded_aurora_protocol<FIELD>::submit_witness_oracles(  
         if (this->params_.make_zk()) fw_prime += vanishing_polynomial<FIELD>(this->variable_domain_) * this->fw_mask_;     \
         fw_prime = polynomial_over_vanishing_polynomial(fw_prime, vanishing_polynomial<FIELD>(this->input_variable_domain_)).first; \
         this->fw_over_codeword_domain_ = FFT_over_field_subset<FIELD>(fw_prime.coefficients(), this->codeword_domain_);    \
+    }                                                                                                                      \
+    if (!witness_on_device || !device_products) {                                                                          \
         variable_assignment.assign(1, FIELD::one());                                                                       \
         variable_assignment.insert(variable_assignment.end(), primary_input.begin(), primary_input.end());                 \
         variable_assignment.insert(variable_assignment.end(), auxiliary_input.begin(), auxiliary_input.end());             \

@@ -72,6 +72,23 @@ def test_whole_provers_through_the_dropin_host_logic(sim, which, log_n, zk, nbyt
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == (nbytes, sha)
 
 
+def test_provers_do_not_read_device_resident_vectors_on_the_host(sim):
+    """Oracles the adapter produces stay on the device behind lazy host vectors; a host read is served correctly by the fault
+    handler but costs a whole-vector download.  None of the provers may take that path (the same check runs on the GPU box in
+    test_gpu_parity.py; here it catches a shadow that starts touching a lazy vector before any GPU time is spent)."""
+    before = sim.lazy_stats()
+    with quiet_stdout():
+        sim.aurora_gf192(12, make_zk=False, verify=False)
+        sim.aurora_gf192(14, make_zk=False, verify=False)
+        sim.aurora_gf192(12, make_zk=True, verify=False)
+        sim.aurora_edwards(12, verify=False)
+        sim.fractal_edwards(12, verify=False)
+        sim.ligero_gf192(12, make_zk=False, verify=False)
+    after = sim.lazy_stats()
+    assert after["gathers"] > before["gathers"]
+    assert after["faults"] == before["faults"], (before, after)
+
+
 def test_lazy_vectors_against_the_simulator():
     """tests/hostsim/lazy_vector_test.cpp: the device-resident ("lazy") host vectors of libiop_b200/host/b200_residency.hpp —
     registration by ownership, materialisation on any host access (read, write, by-value copy) through the SIGSEGV handler,
