@@ -525,7 +525,7 @@ def main():
     ap.add_argument("--reference-proofs", type=int, default=2, help="N=2^20 CPU proofs timed by the reference arm (75 s each)")
     ap.add_argument("--cpu-all-cores", action="store_true", help="reference arm: also one CPU prover per core at N=2^17")
     ap.add_argument("--config5", action="store_true", help="also prove BASELINE config 5 (N=2^22 per GPU); default at 8 GPUs")
-    ap.add_argument("--concurrency", type=int, default=8, help="prover processes sharing the GPU in the e2e_throughput section (1 = skip)")
+    ap.add_argument("--concurrency", type=int, default=1, help="prover processes sharing the GPU in the e2e_throughput section (1 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
