@@ -208,6 +208,17 @@ int b200_spmv_csr(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows
 int b200_spmv_csr_dev(b200_ctx *, int field, const b200_fp_params *fp, size_t n_rows, b200_bytes row_ptr, b200_bytes col, b200_buf coeff,
                       b200_buf x, b200_buf y_out);
 
+/* Index-driven copies of 24-byte elements between device arrays (field-agnostic), idx / map device arrays of u32:
+ *   b200_gather_dev   out[k] = table[map ? map[idx[k]] : idx[k]], k < n  — the row / column elements and the per-column factors of
+ *                     every non-zero entry in matrix_indexer::compute_oracles_over_K (r1cs_rs_iop/fractal_indexer.tcc:52-123), read
+ *                     from per-domain tables through the flattened entry list (map = field_subset::reindex_by_subset as a table)
+ *   b200_scatter_dev  out[map[c]] = x[c], c < n (map injective) — compute_p_alpha_M's placement of column c at its position in
+ *                     the summation domain (lincheck/common.tcc:22-27)
+ *   b200_fill         dst[dst_offset + i] = value, i < n — the padding entries of the index oracles (fractal_indexer.tcc:104-121) */
+int b200_gather_dev(b200_ctx *, b200_buf out, b200_buf table, b200_bytes idx, b200_bytes map, size_t n);
+int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_t n);
+int b200_fill(b200_ctx *, b200_buf dst, size_t dst_offset, const uint64_t value[3], size_t n);
+
 /* GF(2^192) scatter-accumulate over a list of matrix entries: y[dst[k]] += scale * coeff[k] * x[src[k]], k < nnz.
  * multi_lincheck_virtual_oracle::set_challenge's p_alpha_ABC (protocols/encoded/lincheck/basic_lincheck_aux.tcc:63-84): the
  * transposed product (sum_m r_m M_m)^T (1, alpha, alpha^2, ...) — one call per matrix with scale = r_m, x = the powers of alpha,

@@ -505,6 +505,34 @@ class B200:
         finally:
             self.free(ds); self.free(do)
 
+    def gather_scatter_fill(self, table, idx, map_, x_scatter, n_out, fill_value, fill_from):
+        """exercises b200_gather_dev / b200_scatter_dev / b200_fill on device arrays; returns (gathered, scattered-and-filled):
+        gathered[k] = table[map[idx[k]]] (map may be None); out = zeros(n_out), out[map[c]] = x_scatter[c], out[fill_from:] = fill_value"""
+        table = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        dt, dg = self.upload(table), self.alloc(max(len(idx), 1))
+        di = self.alloc_bytes(max(idx.nbytes, 4)); self.upload_bytes(idx.view(np.uint8), di)
+        dm = 0
+        if map_ is not None:
+            map_ = np.ascontiguousarray(map_, dtype=np.uint32)
+            dm = self.alloc_bytes(max(map_.nbytes, 4)); self.upload_bytes(map_.view(np.uint8), dm)
+        x_scatter = np.ascontiguousarray(x_scatter, dtype=np.uint64).reshape(-1, 3)
+        dx, do = self.upload(x_scatter), self.alloc(max(n_out, 1))
+        try:
+            self._chk(self.lib.b200_gather_dev(self.ctx, C.c_uint64(dg), C.c_uint64(dt), C.c_uint64(di), C.c_uint64(dm), C.c_size_t(len(idx))))
+            self._chk(self.lib.b200_fill_zero(self.ctx, C.c_uint64(do), C.c_size_t(0), C.c_size_t(n_out)))
+            if dm:
+                self._chk(self.lib.b200_scatter_dev(self.ctx, C.c_uint64(do), C.c_uint64(dx), C.c_uint64(dm), C.c_size_t(len(x_scatter))))
+            fv = np.ascontiguousarray(fill_value, dtype=np.uint64).reshape(3)
+            self._chk(self.lib.b200_fill(self.ctx, C.c_uint64(do), C.c_size_t(fill_from), fv.ctypes.data_as(_u64p), C.c_size_t(n_out - fill_from)))
+            return self.download(dg, len(idx)), self.download(do, n_out)
+        finally:
+            for b in (dt, dg, dx, do):
+                self.free(b)
+            self.free_bytes(di)
+            if dm:
+                self.free_bytes(dm)
+
     def vec_rows_dot(self, field, fp, x, y, split):
         """x, y: (rows, n, 3) -> out[a] = sum_{r<split} x[r,a]*y[r,a] - sum_{r>=split} x[r,a]*y[r,a]"""
         x = np.ascontiguousarray(x, dtype=np.uint64); y = np.ascontiguousarray(y, dtype=np.uint64)

@@ -220,10 +220,67 @@ int b200_fill_zero(b200_ctx *c, b200_buf dst, size_t dst_offset, size_t n_elems)
     return 0;
 }
 
+/* out[k] = table[map ? map[idx[k]] : idx[k]]; out[map[c]] = x[c]; dst[i] = v — 24-byte elements as three u64 words */
+__global__ void gather_dev_kernel(uint64_t *out, const uint64_t *table, const uint32_t *idx, const uint32_t *map, size_t n)
+{
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        size_t j = idx[k];
+        if (map) j = map[j];
+        const uint64_t *q = table + 3 * j;
+        uint64_t *d = out + 3 * k;
+        d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+    }
+}
+__global__ void scatter_dev_kernel(uint64_t *out, const uint64_t *x, const uint32_t *map, size_t n)
+{
+    for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t *q = x + 3 * c;
+        uint64_t *d = out + 3 * (size_t)map[c];
+        d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+    }
+}
+__global__ void fill_kernel(uint64_t *dst, uint64_t v0, uint64_t v1, uint64_t v2, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t *d = dst + 3 * i;
+        d[0] = v0; d[1] = v1; d[2] = v2;
+    }
+}
+
 __global__ void gather_kernel(uint64_t *out, const uint64_t *src, const size_t *idx, size_t k)
 {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t < k * 3) out[t] = src[idx[t / 3] * 3 + t % 3];
+}
+
+static unsigned copy_grid(size_t n) { return (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+int b200_gather_dev(b200_ctx *c, b200_buf out, b200_buf table, b200_bytes idx, b200_bytes map, size_t n)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "gather_dev", n);
+    if (!n) return 0;
+    gather_dev_kernel<<<copy_grid(n), 256, 0, c->stream>>>((uint64_t *)(uintptr_t)out, (const uint64_t *)(uintptr_t)table,
+                                                          (const uint32_t *)(uintptr_t)idx, (const uint32_t *)(uintptr_t)map, n);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+int b200_scatter_dev(b200_ctx *c, b200_buf out, b200_buf x, b200_bytes map, size_t n)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "scatter_dev", n);
+    if (!n) return 0;
+    if (!map) return set_err(c, B200_ERR_INVALID, "b200_scatter_dev needs an index map");
+    scatter_dev_kernel<<<copy_grid(n), 256, 0, c->stream>>>((uint64_t *)(uintptr_t)out, (const uint64_t *)(uintptr_t)x, (const uint32_t *)(uintptr_t)map, n);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
+int b200_fill(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t value[3], size_t n)
+{
+    B200_ENTER(c);
+    if (!n) return 0;
+    fill_kernel<<<copy_grid(n), 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst + 3 * dst_offset, value[0], value[1], value[2], n);
+    B200_LAUNCH_CHECK(c);
+    return 0;
 }
 
 int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, size_t k)

@@ -141,6 +141,21 @@ int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, siz
     for (size_t i = 0; i < k; ++i) std::memcpy(dst + 3 * i, E(src) + idx[i], 24);
     return 0;
 }
+int b200_gather_dev(b200_ctx *, b200_buf out, b200_buf table, b200_bytes idx, b200_bytes map, size_t n)
+{
+    const uint32_t *ix = reinterpret_cast<const uint32_t *>(idx), *mp = reinterpret_cast<const uint32_t *>(map);
+    for (size_t k = 0; k < n; ++k) E(out)[k] = E(table)[mp ? mp[ix[k]] : ix[k]];
+    return 0;
+}
+int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_t n)
+{
+    const uint32_t *mp = reinterpret_cast<const uint32_t *>(map);
+    if (!mp) return B200_ERR_INVALID;
+    for (size_t c = 0; c < n; ++c) E(out)[mp[c]] = E(x)[c];
+    return 0;
+}
+int b200_fill(b200_ctx *, b200_buf dst, size_t off, const uint64_t value[3], size_t n)
+{ for (size_t i = 0; i < n; ++i) std::memcpy(E(dst) + off + i, value, 24); return 0; }
 int b200_timer_start(b200_ctx *c) { c->t0 = std::chrono::steady_clock::now(); return 0; }
 int b200_timer_stop(b200_ctx *c, float *ms)
 { *ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t0).count(); return 0; }

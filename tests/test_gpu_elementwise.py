@@ -371,6 +371,27 @@ def test_copy_strided(dev, n_src, n_out, ds, so, ss, n):
     assert (dev.copy_strided(src, n_out, ds, so, ss, n) == want).all()
 
 
+@pytest.mark.parametrize("n_table,n_idx,with_map", [(1 << 10, 1 << 12, True), (1 << 10, 1 << 12, False), (37, 5, True), (16, 0, True)])
+def test_gather_scatter_fill_on_device(dev, n_table, n_idx, with_map):
+    """b200_gather_dev / b200_scatter_dev / b200_fill: the index-driven copies behind matrix_indexer::compute_oracles_over_K
+    (fractal_indexer.tcc:52-123) and compute_p_alpha_M's placement (lincheck/common.tcc:22-27); pure data movement, bit-exact"""
+    rng = np.random.default_rng(n_table * 7 + n_idx)
+    table = rand_elems(rng, n_table)
+    idx = rng.integers(0, n_table, size=n_idx, dtype=np.uint32)
+    perm = rng.permutation(n_table).astype(np.uint32)
+    x = rand_elems(rng, n_table)
+    n_out = n_table + 9
+    fill = rand_elems(rng, 1)[0]
+    got_g, got_s = dev.gather_scatter_fill(table, idx, perm if with_map else None, x, n_out, fill, n_table + 2)
+    want_g = table[perm[idx]] if with_map else table[idx]
+    assert got_g.shape == (n_idx, 3) and (got_g == want_g).all()
+    want_s = elems(n_out)
+    if with_map:
+        want_s[perm] = x
+    want_s[n_table + 2:] = fill
+    assert (got_s == want_s).all()
+
+
 @pytest.mark.parametrize("dim", [1, 5, 12])
 def test_powers_by_subset_sum_products(dev, oracle, dim):
     """alpha^i for i < 2^dim as a product of dim index-bit-affine factors (libiop_b200/host/b200_elementwise.hpp powers_of):
