@@ -21,6 +21,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -48,6 +50,8 @@ class constraint_matrices {
         std::weak_ptr<r1cs_constraint_system<FieldT>> alive;
         bool built[3] = { false, false, false };
         flat_matrix M[3];
+        bool built_t[3] = { false, false, false };
+        flat_matrix T[3];                                     /* the transposes, CSR over the columns of M */
     };
     std::map<const void *, entry> entries_;
     std::mutex mu_;
@@ -129,6 +133,39 @@ class constraint_matrices {
                          std::chrono::duration<double, std::milli>(t2 - t1).count(), T,
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
     }
+    /* The transpose of matrix m as CSR over M's columns (num_variables + 1 of them): n_rows = columns of M, `col` = the row of
+       each entry, `row` = its column, entries grouped by column in row order.  For fields without an atomic addition on the
+       device the transposed product (compute_p_alpha_M, lincheck/common.tcc:3-36) is then the same gather product as M z.
+       Counting sort on the host: histogram of the columns, prefix sums, one fill pass. */
+    static void build_transposed(entry &e, const r1cs_constraint_system<FieldT> &cs, int m)
+    {
+        using namespace libiop_b200;
+        const std::size_t n = cs.constraints_.size(), n_cols = cs.num_variables() + 1;
+        std::unique_ptr<uint64_t[]> col_ptr(new uint64_t[n_cols + 1]());
+        for (std::size_t i = 0; i < n; ++i)
+            for (const auto &term : row_of(cs.constraints_[i], m).terms) ++col_ptr[term.index_ + 1];
+        for (std::size_t c = 0; c < n_cols; ++c) col_ptr[c + 1] += col_ptr[c];
+        const uint64_t nnz = col_ptr[n_cols];
+        std::unique_ptr<uint64_t[]> cursor(new uint64_t[n_cols]);
+        std::memcpy(cursor.get(), col_ptr.get(), n_cols * sizeof(uint64_t));
+        std::unique_ptr<uint32_t[]> src(new uint32_t[nnz ? nnz : 1]), dst(new uint32_t[nnz ? nnz : 1]);
+        std::unique_ptr<void, raw_free> coeff_store(::operator new((nnz ? nnz : 1) * sizeof(FieldT)));
+        FieldT *coeff = static_cast<FieldT *>(coeff_store.get());
+        for (std::size_t i = 0; i < n; ++i)
+            for (const auto &term : row_of(cs.constraints_[i], m).terms) {
+                const uint64_t k = cursor[term.index_]++;
+                src[k] = (uint32_t)i; dst[k] = (uint32_t)term.index_; new (&coeff[k]) FieldT(term.coeff_);
+            }
+        flat_matrix &F = e.T[m];
+        F.n_rows = n_cols; F.nnz = nnz;
+        upload_bytes(F.row_ptr, col_ptr.get(), (n_cols + 1) * sizeof(uint64_t));
+        upload_bytes(F.col, src.get(), nnz * sizeof(uint32_t));
+        upload_bytes(F.row, dst.get(), nnz * sizeof(uint32_t));
+        F.coeff = device_buffer(nnz ? nnz : 1);
+        if (nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, reinterpret_cast<const uint64_t *>(coeff), nnz));
+        throw_status(context(), b200_wait_uploads(context()));
+        e.built_t[m] = true;
+    }
     static bool worth_it(const r1cs_constraint_system<FieldT> &cs)
     {
         return cs.constraints_.size() >= 16384 && cs.num_variables() + 1 < (std::size_t(1) << 32);
@@ -174,6 +211,15 @@ public:
         if (!e || !worth_it(*cs)) return nullptr;
         if (!e->built[m]) build(*e, *cs, m);
         return &e->M[m];
+    }
+    /* the transpose of matrix m (see build_transposed), or nullptr like get_matrix */
+    const flat_matrix *get_transposed(const r1cs_constraint_system<FieldT> *cs, int m)
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        entry *e = live_entry(cs);
+        if (!e || !worth_it(*cs)) return nullptr;
+        if (!e->built_t[m]) build_transposed(*e, *cs, m);
+        return &e->T[m];
     }
     /* all three (an array of 3) */
     const flat_matrix *get(const r1cs_constraint_system<FieldT> *cs)

@@ -9,7 +9,7 @@
    codeword domain (every prover-side query), the value is simply read out of the low-degree extension that
    evaluated_contents left on the device. */
 #include "b200_dropin_common.hpp"
-#include "b200_constraint_matrices.hpp"
+#include "b200_matrix_views.hpp"
 #include B200_REF_FILE(libiop/protocols/encoded/lincheck/basic_lincheck_aux.tcc)
 
 namespace libiop {
@@ -72,13 +72,6 @@ void extend_p_alpha(const std::vector<FieldT> &coefficients, const field_subset<
     FFT_over_field_subset_device<FieldT>(c.buf(), coefficients.size(), codeword_domain, out);
 }
 
-/* the constraint system behind an r1cs_sparse_matrix (a protected member: reached through a pointer to member formed in
-   a derived class), so that rows can be walked by reference instead of through get_row()'s by-value copies */
-template<typename FieldT>
-struct r1cs_matrix_peek : public r1cs_sparse_matrix<FieldT> {
-    static const r1cs_constraint_system<FieldT> &system(const r1cs_sparse_matrix<FieldT> &m) { return *(m.*(&r1cs_matrix_peek::constraint_system_)); }
-    static r1cs_sparse_matrix_type type(const r1cs_sparse_matrix<FieldT> &m) { return m.*(&r1cs_matrix_peek::matrix_type_); }
-};
 /* calls f(row index, term) for every entry of M */
 template<typename FieldT, typename Fn>
 void for_each_entry(const sparse_matrix<FieldT> &M, Fn f)

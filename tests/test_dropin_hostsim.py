@@ -51,7 +51,9 @@ def _golden_cases():
         which, log_n, zk, nbytes, sha = str(line).split(",")
         cases.append((which, int(log_n), zk == "1", int(nbytes), sha))
     for c in json.load(open(os.path.join(ROOT, "tests", "golden", "prover_fingerprints_extra.json"))):
-        if c["log_n"] <= 12 or (c["prover"] == "aurora_gf192" and c["log_n"] <= 14):   # 2^14: the low-degree-divisor division runs on the device path
+        # 2^14 = the smallest size at which the constraint matrices are served from the device (b200_constraint_matrices.hpp): the
+        # pipelined A z / B z / C z extensions (Aurora), the transposed products and the index oracles (Fractal) run their device paths
+        if c["log_n"] <= 12 or (c["prover"] in ("aurora_gf192", "aurora_edwards", "fractal_edwards") and c["log_n"] <= 14):
             cases.append((c["prover"], c["log_n"], c["zk"], c["bytes"], c["sha256"]))
     return cases
 
