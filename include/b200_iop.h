@@ -219,6 +219,14 @@ int b200_gather_dev(b200_ctx *, b200_buf out, b200_buf table, b200_bytes idx, b2
 int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_t n);
 int b200_fill(b200_ctx *, b200_buf dst, size_t dst_offset, const uint64_t value[3], size_t n);
 
+/* Transpose of a device-resident sparse matrix given as an entry list (row[k], col[k], coeff[k]), k < nnz (u32 device arrays and a
+ * device element array, as left by the flattening of an R1CS matrix): the entries regrouped by column as CSR over the columns —
+ * col_ptr_out (n_cols + 1 x u64), src_out[k'] = the row of the entry now at k', coeff_out[k'].  The order of the entries inside one
+ * column is unspecified: the only use is the sum of b200_spmv_csr_dev, which is exact and commutative in either field.  This is
+ * compute_p_alpha_M's transposed product (lincheck/common.tcc:3-36) for fields without an atomic addition on the device. */
+int b200_csr_transpose_dev(b200_ctx *, size_t n_cols, size_t nnz, b200_bytes col, b200_bytes row, b200_buf coeff,
+                           b200_bytes col_ptr_out, b200_bytes src_out, b200_buf coeff_out);
+
 /* GF(2^192) scatter-accumulate over a list of matrix entries: y[dst[k]] += scale * coeff[k] * x[src[k]], k < nnz.
  * multi_lincheck_virtual_oracle::set_challenge's p_alpha_ABC (protocols/encoded/lincheck/basic_lincheck_aux.tcc:63-84): the
  * transposed product (sum_m r_m M_m)^T (1, alpha, alpha^2, ...) — one call per matrix with scale = r_m, x = the powers of alpha,

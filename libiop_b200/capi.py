@@ -529,9 +529,28 @@ class B200:
         finally:
             for b in (dt, dg, dx, do):
                 self.free(b)
-            self.free_bytes(di)
+            self.free(di)
             if dm:
-                self.free_bytes(dm)
+                self.free(dm)
+
+    def csr_transpose(self, n_cols, col, row, coeff):
+        """b200_csr_transpose_dev on uploaded entry lists; returns (col_ptr u64[n_cols+1], src u32[nnz], coeff (nnz,3))"""
+        col = np.ascontiguousarray(col, dtype=np.uint32); row = np.ascontiguousarray(row, dtype=np.uint32)
+        coeff = np.ascontiguousarray(coeff, dtype=np.uint64).reshape(-1, 3)
+        nnz = len(col)
+        dc = self.alloc_bytes(max(col.nbytes, 4)); self.upload_bytes(col.view(np.uint8), dc)
+        dr = self.alloc_bytes(max(row.nbytes, 4)); self.upload_bytes(row.view(np.uint8), dr)
+        dv, dvo = self.upload(coeff) if nnz else self.alloc(1), self.alloc(max(nnz, 1))
+        dp, ds = self.alloc_bytes(8 * (n_cols + 1)), self.alloc_bytes(max(4 * nnz, 4))
+        try:
+            self._chk(self.lib.b200_csr_transpose_dev(self.ctx, C.c_size_t(n_cols), C.c_size_t(nnz), C.c_uint64(dc), C.c_uint64(dr), C.c_uint64(dv),
+                                                      C.c_uint64(dp), C.c_uint64(ds), C.c_uint64(dvo)))
+            col_ptr = np.frombuffer(self.download_bytes(dp, 8 * (n_cols + 1)), dtype=np.uint64)
+            src = np.frombuffer(self.download_bytes(ds, 4 * nnz), dtype=np.uint32) if nnz else np.zeros(0, dtype=np.uint32)
+            return col_ptr, src, self.download(dvo, nnz)
+        finally:
+            for b in (dc, dr, dv, dvo, dp, ds):
+                self.free(b)
 
     def vec_rows_dot(self, field, fp, x, y, split):
         """x, y: (rows, n, 3) -> out[a] = sum_{r<split} x[r,a]*y[r,a] - sum_{r>=split} x[r,a]*y[r,a]"""

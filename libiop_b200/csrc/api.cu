@@ -253,6 +253,42 @@ __global__ void gather_kernel(uint64_t *out, const uint64_t *src, const size_t *
     if (t < k * 3) out[t] = src[idx[t / 3] * 3 + t % 3];
 }
 
+/* ---- transposition of an entry list by counting sort: histogram, exclusive scan, fill through per-column cursors ---- */
+__global__ void csr_col_histogram_kernel(const uint32_t *col, size_t nnz, unsigned int *count)
+{
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nnz; k += (size_t)gridDim.x * blockDim.x) atomicAdd(&count[col[k]], 1u);
+}
+/* one CTA: col_ptr[c] = sum_{c' < c} count[c'] for c <= n, and count[c] becomes the 32-bit cursor of column c */
+__global__ void __launch_bounds__(1024) csr_scan_kernel(unsigned int *count, unsigned long long *col_ptr, size_t n)
+{
+    __shared__ unsigned long long part[1024];
+    const size_t chunk = (n + blockDim.x - 1) / blockDim.x;
+    const size_t lo = threadIdx.x * chunk < n ? threadIdx.x * chunk : n, hi = lo + chunk < n ? lo + chunk : n;
+    unsigned long long sum = 0;
+    for (size_t c = lo; c < hi; ++c) sum += count[c];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (unsigned t = 0; t < blockDim.x; ++t) { const unsigned long long v = part[t]; part[t] = run; run += v; }
+        col_ptr[n] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (size_t c = lo; c < hi; ++c) { const unsigned int v = count[c]; col_ptr[c] = run; count[c] = (unsigned int)run; run += v; }
+}
+__global__ void csr_transpose_fill_kernel(const uint32_t *col, const uint32_t *row, const uint64_t *coeff, size_t nnz, unsigned int *cursor,
+                                          uint32_t *src_out, uint64_t *coeff_out)
+{
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nnz; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t at = atomicAdd(&cursor[col[k]], 1u);
+        src_out[at] = row[k];
+        const uint64_t *q = coeff + 3 * k;
+        uint64_t *d = coeff_out + 3 * at;
+        d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+    }
+}
+
 static unsigned copy_grid(size_t n) { return (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
 int b200_gather_dev(b200_ctx *c, b200_buf out, b200_buf table, b200_bytes idx, b200_bytes map, size_t n)
 {
@@ -280,6 +316,30 @@ int b200_fill(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t value
     if (!n) return 0;
     fill_kernel<<<copy_grid(n), 256, 0, c->stream>>>((uint64_t *)(uintptr_t)dst + 3 * dst_offset, value[0], value[1], value[2], n);
     B200_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int b200_csr_transpose_dev(b200_ctx *c, size_t n_cols, size_t nnz, b200_bytes col, b200_bytes row, b200_buf coeff,
+                           b200_bytes col_ptr_out, b200_bytes src_out, b200_buf coeff_out)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "csr_transpose_dev", nnz);
+    if (nnz >= ((size_t)1 << 32) || n_cols >= ((size_t)1 << 32)) return set_err(c, B200_ERR_INVALID, "b200_csr_transpose_dev: 32-bit indices");
+    unsigned int *count = (unsigned int *)scratch_get(c, 3, (n_cols + 1) * sizeof(unsigned int));
+    if (!count) return set_err(c, B200_ERR_NOMEM, "cannot allocate the column counters");
+    B200_CUDA(c, cudaMemsetAsync(count, 0, (n_cols + 1) * sizeof(unsigned int), c->stream));
+    if (nnz) {
+        csr_col_histogram_kernel<<<copy_grid(nnz), 256, 0, c->stream>>>((const uint32_t *)(uintptr_t)col, nnz, count);
+        B200_LAUNCH_CHECK(c);
+    }
+    csr_scan_kernel<<<1, 1024, 0, c->stream>>>(count, (unsigned long long *)(uintptr_t)col_ptr_out, n_cols);
+    B200_LAUNCH_CHECK(c);
+    if (nnz) {
+        csr_transpose_fill_kernel<<<copy_grid(nnz), 256, 0, c->stream>>>((const uint32_t *)(uintptr_t)col, (const uint32_t *)(uintptr_t)row,
+                                                                        (const uint64_t *)(uintptr_t)coeff, nnz, count,
+                                                                        (uint32_t *)(uintptr_t)src_out, (uint64_t *)(uintptr_t)coeff_out);
+        B200_LAUNCH_CHECK(c);
+    }
     return 0;
 }
 

@@ -134,36 +134,23 @@ class constraint_matrices {
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
     }
     /* The transpose of matrix m as CSR over M's columns (num_variables + 1 of them): n_rows = columns of M, `col` = the row of
-       each entry, `row` = its column, entries grouped by column in row order.  For fields without an atomic addition on the
-       device the transposed product (compute_p_alpha_M, lincheck/common.tcc:3-36) is then the same gather product as M z.
-       Counting sort on the host: histogram of the columns, prefix sums, one fill pass. */
+       each entry.  For fields without an atomic addition on the device the transposed product (compute_p_alpha_M,
+       lincheck/common.tcc:3-36) is then the same gather product as M z.  Made on the device from the flattened matrix
+       (b200_csr_transpose_dev: counting sort by column; a host counting sort took 4 ms per matrix at N = 2^18). */
     static void build_transposed(entry &e, const r1cs_constraint_system<FieldT> &cs, int m)
     {
         using namespace libiop_b200;
-        const std::size_t n = cs.constraints_.size(), n_cols = cs.num_variables() + 1;
-        std::unique_ptr<uint64_t[]> col_ptr(new uint64_t[n_cols + 1]());
-        for (std::size_t i = 0; i < n; ++i)
-            for (const auto &term : row_of(cs.constraints_[i], m).terms) ++col_ptr[term.index_ + 1];
-        for (std::size_t c = 0; c < n_cols; ++c) col_ptr[c + 1] += col_ptr[c];
-        const uint64_t nnz = col_ptr[n_cols];
-        std::unique_ptr<uint64_t[]> cursor(new uint64_t[n_cols]);
-        std::memcpy(cursor.get(), col_ptr.get(), n_cols * sizeof(uint64_t));
-        std::unique_ptr<uint32_t[]> src(new uint32_t[nnz ? nnz : 1]), dst(new uint32_t[nnz ? nnz : 1]);
-        std::unique_ptr<void, raw_free> coeff_store(::operator new((nnz ? nnz : 1) * sizeof(FieldT)));
-        FieldT *coeff = static_cast<FieldT *>(coeff_store.get());
-        for (std::size_t i = 0; i < n; ++i)
-            for (const auto &term : row_of(cs.constraints_[i], m).terms) {
-                const uint64_t k = cursor[term.index_]++;
-                src[k] = (uint32_t)i; dst[k] = (uint32_t)term.index_; new (&coeff[k]) FieldT(term.coeff_);
-            }
+        if (!e.built[m]) build(e, cs, m);
+        const flat_matrix &S = e.M[m];
+        const std::size_t n_cols = cs.num_variables() + 1;
         flat_matrix &F = e.T[m];
-        F.n_rows = n_cols; F.nnz = nnz;
-        upload_bytes(F.row_ptr, col_ptr.get(), (n_cols + 1) * sizeof(uint64_t));
-        upload_bytes(F.col, src.get(), nnz * sizeof(uint32_t));
-        upload_bytes(F.row, dst.get(), nnz * sizeof(uint32_t));
-        F.coeff = device_buffer(nnz ? nnz : 1);
-        if (nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, reinterpret_cast<const uint64_t *>(coeff), nnz));
-        throw_status(context(), b200_wait_uploads(context()));
+        F.n_rows = n_cols; F.nnz = S.nnz;
+        F.row_ptr.reset(new device_bytes((n_cols + 1) * sizeof(uint64_t)));
+        F.col.reset(new device_bytes((S.nnz ? S.nnz : 1) * sizeof(uint32_t)));
+        F.row.reset();
+        F.coeff = device_buffer(S.nnz ? S.nnz : 1);
+        throw_status(context(), b200_csr_transpose_dev(context(), n_cols, S.nnz, S.col->get(), S.row->get(), S.coeff.get(),
+                                                       F.row_ptr->get(), F.col->get(), F.coeff.get()));
         e.built_t[m] = true;
     }
     static bool worth_it(const r1cs_constraint_system<FieldT> &cs)

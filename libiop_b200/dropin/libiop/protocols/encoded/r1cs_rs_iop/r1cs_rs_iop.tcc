@@ -3,7 +3,7 @@
    domain.  On the B200: Z_{1,v} over L is generated on the device from dim(L)+1 host values, f_{1,v} is LDE'd on the
    device from its |1,v| coefficients, and one fused pass forms the result; only f_w goes up and f_z comes down. */
 #include "b200_dropin_common.hpp"
-#include "b200_constraint_matrices.hpp"
+#include "b200_matrix_views.hpp"
 #include B200_REF_FILE(libiop/protocols/encoded/r1cs_rs_iop/r1cs_rs_iop.tcc)
 
 namespace libiop {
@@ -100,12 +100,12 @@ bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input,
                                 std::vector<FieldT> *variable_assignment /* null: the caller's products run on the host */)
 {
     using namespace libiop_b200;
-    if (field_traits<FieldT>::kind != B200_FIELD_GF192) return false;
-    if (variable_domain.type() != affine_subspace_type || codeword_domain.type() != affine_subspace_type ||
-        input_variable_domain.type() != affine_subspace_type) return false;
+    const field_subset_type type = variable_domain.type();
+    if (codeword_domain.type() != type || input_variable_domain.type() != type) return false;
+    if ((type == affine_subspace_type) != (field_traits<FieldT>::kind == B200_FIELD_GF192)) return false;
     const std::size_t n_V = variable_domain.num_elements(), n_L = codeword_domain.num_elements();
     const std::size_t n_z = 1 + primary_input.size() + auxiliary_input.size();
-    if (n_V < 4096 || n_z > n_V || primary_input.size() + 1 != input_variable_domain.num_elements()) return false;
+    if (n_V < 4096 || n_z > n_V || n_V >= (std::size_t(1) << 32) || primary_input.size() + 1 != input_variable_domain.num_elements()) return false;
 
     /* z on the device */
     device_buffer d_z(n_z);
@@ -115,11 +115,20 @@ bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input,
     d_z.upload_async(auxiliary_input, head.size());
     throw_status(context(), b200_wait_uploads(context()));                /* `head` dies with this scope */
 
-    /* \hat f_w over V */
+    /* \hat f_w over V: variable c sits at position c of a subspace, at reindex_by_subset(dim(in), c) of a coset */
     device_buffer d_f1v(n_V), d_fw(n_V);
     { const device_view c(f_1v_coefficients); FFT_over_field_subset_device<FieldT>(c.buf(), f_1v_coefficients.size(), variable_domain, d_f1v); }
-    vec_mul_add<FieldT>(d_fw, d_z, nullptr, &d_f1v, nullptr, false, n_z);
-    if (n_z < n_V) throw_status(context(), b200_fill_zero(context(), d_fw.get(), n_z, n_V - n_z));
+    if (type == affine_subspace_type) {
+        vec_mul_add<FieldT>(d_fw, d_z, nullptr, &d_f1v, nullptr, true, n_z);
+        if (n_z < n_V) throw_status(context(), b200_fill_zero(context(), d_fw.get(), n_z, n_V - n_z));
+    } else {
+        const b200_bytes position = reindex_table<FieldT>(variable_domain, input_variable_domain.dimension(), n_z);
+        device_buffer d_at(n_z);
+        throw_status(context(), b200_gather_dev(context(), d_at.get(), d_f1v.get(), position, 0, n_z));
+        vec_mul_add<FieldT>(d_at, d_z, nullptr, &d_at, nullptr, true, n_z);
+        throw_status(context(), b200_fill_zero(context(), d_fw.get(), 0, n_V));
+        throw_status(context(), b200_scatter_dev(context(), d_fw.get(), d_at.get(), position, n_z));
+    }
 
     /* over L */
     device_buffer d_L(n_L);
@@ -135,19 +144,33 @@ bool witness_codeword_on_device(const r1cs_primary_input<FieldT> &primary_input,
         vec_mul_add<FieldT>(d_L, d_L, nullptr, &d_Zv, &d_mask, false, n_L);
     }
 
-    /* / Z_in: the table of Z_in over L collapses along the directions Z_in kills */
+    /* / Z_in: the table of Z_in over L collapses — along the basis directions Z_in kills (subspaces), or to its period
+       |L| / deg Z_in in the position (cosets: Z_in = x^deg - c and x_i^deg = s^deg (g^deg)^i) */
     const vanishing_polynomial<FieldT> input_vp(input_variable_domain);
-    std::vector<FieldT> t = affine_function_table<FieldT>(codeword_domain, [&input_vp](const FieldT &x) { return input_vp.evaluation_at_point(x); },
-                                                          FieldT::one());
-    std::size_t lead = 0;
-    while (lead < codeword_domain.dimension() && t[1 + lead].is_zero()) ++lead;
-    t.erase(t.begin() + 1, t.begin() + 1 + lead);
-    const std::size_t q_dim = codeword_domain.dimension() - lead, n_q = std::size_t(1) << q_dim;
-    device_buffer d_q(n_q), d_qinv(n_q);
-    subspace_function_product<FieldT>(d_q, q_dim, { t });
+    std::size_t n_q = 0;
+    uint32_t shift_bits = 0;
+    device_buffer d_q, d_qinv;
+    if (type == affine_subspace_type) {
+        std::vector<FieldT> t = affine_function_table<FieldT>(codeword_domain, [&input_vp](const FieldT &x) { return input_vp.evaluation_at_point(x); },
+                                                              FieldT::one());
+        std::size_t lead = 0;
+        while (lead < codeword_domain.dimension() && t[1 + lead].is_zero()) ++lead;
+        t.erase(t.begin() + 1, t.begin() + 1 + lead);
+        const std::size_t q_dim = codeword_domain.dimension() - lead;
+        n_q = std::size_t(1) << q_dim; shift_bits = (uint32_t)lead;
+        d_q = device_buffer(n_q); d_qinv = device_buffer(n_q);
+        subspace_function_product<FieldT>(d_q, q_dim, { t });
+    } else {
+        const std::size_t deg = input_vp.degree();
+        if (deg == 0 || n_L % deg) return false;
+        n_q = n_L / deg;
+        d_q = device_buffer(n_q); d_qinv = device_buffer(n_q);
+        const FieldT a = field_pow(codeword_domain.shift(), deg);
+        geometric_sequence<FieldT>(d_q, n_q, a, field_pow(codeword_domain.generator(), deg), input_vp.evaluation_at_point(codeword_domain.shift()) - a);
+    }
     vec_inverse<FieldT>(d_qinv, d_q, n_q);
     throw_status(context(), b200_vec_mul_table(context(), field_traits<FieldT>::kind, field_traits<FieldT>::fp(), d_L.get(), d_L.get(),
-                                               d_qinv.get(), (uint32_t)lead, n_q - 1, n_L));
+                                               d_qinv.get(), shift_bits, n_q - 1, n_L));
     /* no synchronisation: the temporaries go back to the context's stream-ordered block cache */
 
     fw_over_codeword_domain = make_lazy_vector<FieldT>(std::move(d_L), n_L);

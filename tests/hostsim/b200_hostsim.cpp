@@ -156,6 +156,19 @@ int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_
 }
 int b200_fill(b200_ctx *, b200_buf dst, size_t off, const uint64_t value[3], size_t n)
 { for (size_t i = 0; i < n; ++i) std::memcpy(E(dst) + off + i, value, 24); return 0; }
+int b200_csr_transpose_dev(b200_ctx *, size_t n_cols, size_t nnz, b200_bytes col, b200_bytes row, b200_buf coeff,
+                           b200_bytes col_ptr_out, b200_bytes src_out, b200_buf coeff_out)
+{
+    const uint32_t *cl = reinterpret_cast<const uint32_t *>(col), *rw = reinterpret_cast<const uint32_t *>(row);
+    uint64_t *cp = reinterpret_cast<uint64_t *>(col_ptr_out);
+    uint32_t *src = reinterpret_cast<uint32_t *>(src_out);
+    std::vector<uint64_t> cursor(n_cols + 1, 0);
+    for (size_t k = 0; k < nnz; ++k) ++cursor[cl[k] + 1];
+    for (size_t c = 0; c < n_cols; ++c) cursor[c + 1] += cursor[c];
+    for (size_t c = 0; c <= n_cols; ++c) cp[c] = cursor[c];
+    for (size_t k = 0; k < nnz; ++k) { const uint64_t at = cursor[cl[k]]++; src[at] = rw[k]; E(coeff_out)[at] = E(coeff)[k]; }
+    return 0;
+}
 int b200_timer_start(b200_ctx *c) { c->t0 = std::chrono::steady_clock::now(); return 0; }
 int b200_timer_stop(b200_ctx *c, float *ms)
 { *ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t0).count(); return 0; }

@@ -392,6 +392,25 @@ def test_gather_scatter_fill_on_device(dev, n_table, n_idx, with_map):
     assert (got_s == want_s).all()
 
 
+@pytest.mark.parametrize("n_rows,n_cols,nnz", [(1 << 12, 1 << 12, 3 << 12), (100, 37, 1000), (5000, 70000, 20000), (8, 8, 0)])
+def test_csr_transpose_on_device(dev, n_rows, n_cols, nnz):
+    """b200_csr_transpose_dev: the entries of an (row, col, coeff) list regrouped by column (counting sort with atomic cursors).
+    The order inside a column is unspecified, so each column is compared as a multiset."""
+    rng = np.random.default_rng(n_rows + n_cols + nnz)
+    row = np.sort(rng.integers(0, n_rows, size=nnz, dtype=np.uint32))
+    col = rng.integers(0, n_cols, size=nnz, dtype=np.uint32)
+    coeff = rand_elems(rng, nnz)
+    col_ptr, src, out = dev.csr_transpose(n_cols, col, row, coeff)
+    counts = np.bincount(col, minlength=n_cols)
+    assert (col_ptr == np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)).all()
+    order = np.argsort(col, kind="stable")
+    want = np.concatenate([row[order].reshape(-1, 1).astype(np.uint64), coeff[order]], axis=1)
+    got = np.concatenate([src.reshape(-1, 1).astype(np.uint64), out], axis=1)
+    for c in np.unique(col):
+        lo, hi = int(col_ptr[c]), int(col_ptr[c + 1])
+        assert sorted(map(tuple, got[lo:hi])) == sorted(map(tuple, want[lo:hi]))
+
+
 @pytest.mark.parametrize("dim", [1, 5, 12])
 def test_powers_by_subset_sum_products(dev, oracle, dim):
     """alpha^i for i < 2^dim as a product of dim index-bit-affine factors (libiop_b200/host/b200_elementwise.hpp powers_of):
