@@ -97,6 +97,10 @@ int b200_fill_zero(b200_ctx *, b200_buf dst, size_t dst_offset, size_t n_elems);
 /* iop_protocol::get_oracle_evaluation_at_point (libiop/iop/iop.tcc:670-688): query answers */
 int b200_gather(b200_ctx *, uint64_t *dst, b200_buf src, const size_t *idx, size_t k);
 
+/* the same for many device arrays at one list of positions, one launch and one transfer: dst[s * k + j] = srcs[s][idx[j]],
+ * s < n_srcs, j < k (bcs_prover::get_transcript, bcs/bcs_prover.tcc:197-207: every oracle of a Merkle tree at every position
+ * queried in that tree; Ligero commits ~10^3 oracles per tree) */
+int b200_gather_multi(b200_ctx *, uint64_t *dst, const b200_buf *srcs, size_t n_srcs, const size_t *idx, size_t k);
 /* device timing on the context's stream (CUDA events) */
 int b200_timer_start(b200_ctx *);
 int b200_timer_stop(b200_ctx *, float *ms);          /* synchronises */

@@ -178,6 +178,15 @@ class B200:
         self.sync()
         return buf
 
+    def gather_multi(self, bufs, idx):
+        """values of several device buffers at one list of positions: (len(bufs), len(idx), 3)"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.zeros((len(bufs), len(idx), 3), dtype=np.uint64)
+        arr = (C.c_uint64 * max(len(bufs), 1))(*bufs)
+        self._chk(self.lib.b200_gather_multi(self.ctx, out.ctypes.data_as(_u64p), arr, C.c_size_t(len(bufs)),
+                                             idx.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(len(idx))))
+        return out
+
     def gather(self, buf, idx):
         idx = np.ascontiguousarray(idx, dtype=np.uint64)
         out = np.zeros((len(idx), 3), dtype=np.uint64)

@@ -357,6 +357,36 @@ int b200_gather(b200_ctx *c, uint64_t *dst, b200_buf src, const size_t *idx, siz
     B200_LAUNCH_CHECK(c);
     B200_CUDA(c, cudaMemcpyAsync(dst, dout, k * 24, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += k * sizeof(size_t); c->d2h_bytes += k * 24;
+    return 0;
+}
+
+__global__ void gather_multi_kernel(uint64_t *out, const uint64_t *const *srcs, const size_t *idx, size_t n_srcs, size_t k)
+{
+    const size_t total = n_srcs * k * 3;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = t / 3, s = e / k, j = e % k;
+        out[t] = srcs[s][idx[j] * 3 + t % 3];
+    }
+}
+int b200_gather_multi(b200_ctx *c, uint64_t *dst, const b200_buf *srcs, size_t n_srcs, const size_t *idx, size_t k)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "gather_multi", n_srcs * k);
+    if (!k || !n_srcs) return 0;
+    const size_t b_src = n_srcs * sizeof(uint64_t), b_idx = k * sizeof(size_t), b_out = n_srcs * k * 24;
+    char *dev = (char *)scratch_get(c, 3, b_src + b_idx + b_out);
+    if (!dev) return set_err(c, B200_ERR_NOMEM, "cannot allocate gather buffer");
+    const uint64_t **dsrc = (const uint64_t **)dev;
+    size_t *didx = (size_t *)(dev + b_src);
+    uint64_t *dout = (uint64_t *)(dev + b_src + b_idx);
+    B200_CUDA(c, cudaMemcpyAsync(dsrc, srcs, b_src, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(c, cudaMemcpyAsync(didx, idx, b_idx, cudaMemcpyHostToDevice, c->stream));
+    gather_multi_kernel<<<copy_grid(n_srcs * k * 3), 256, 0, c->stream>>>(dout, dsrc, didx, n_srcs, k);
+    B200_LAUNCH_CHECK(c);
+    B200_CUDA(c, cudaMemcpyAsync(dst, dout, b_out, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += b_src + b_idx; c->d2h_bytes += b_out;
     return 0;
 }
 

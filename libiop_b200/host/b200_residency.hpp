@@ -240,6 +240,7 @@ public:
     std::size_t faults() const { return faults_; }
     std::size_t fault_bytes() const { return fault_bytes_; }
     std::size_t gathers() const { return gathers_; }
+    void count_gather() { std::lock_guard<std::mutex> lock(mu_); ++gathers_; }       /* a fetch made by the caller itself (b200_gather_multi) */
     std::size_t resident_bytes() const { return bytes_; }
 };
 

@@ -169,6 +169,13 @@ int b200_csr_transpose_dev(b200_ctx *, size_t n_cols, size_t nnz, b200_bytes col
     for (size_t k = 0; k < nnz; ++k) { const uint64_t at = cursor[cl[k]]++; src[at] = rw[k]; E(coeff_out)[at] = E(coeff)[k]; }
     return 0;
 }
+int b200_gather_multi(b200_ctx *c, uint64_t *dst, const b200_buf *srcs, size_t n_srcs, const size_t *idx, size_t k)
+{
+    c->d2h += n_srcs * k * 24;
+    for (size_t s = 0; s < n_srcs; ++s)
+        for (size_t j = 0; j < k; ++j) std::memcpy(dst + 3 * (s * k + j), E(srcs[s]) + idx[j], 24);
+    return 0;
+}
 int b200_timer_start(b200_ctx *c) { c->t0 = std::chrono::steady_clock::now(); return 0; }
 int b200_timer_stop(b200_ctx *c, float *ms)
 { *ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t0).count(); return 0; }

@@ -392,6 +392,23 @@ def test_gather_scatter_fill_on_device(dev, n_table, n_idx, with_map):
     assert (got_s == want_s).all()
 
 
+@pytest.mark.parametrize("n_bufs,n,k", [(1, 100, 7), (37, 1 << 12, 211), (1100, 256, 64), (3, 50, 0)])
+def test_gather_multi(dev, n_bufs, n, k):
+    """b200_gather_multi: every oracle of a Merkle tree at every queried position with one launch (bcs_prover.tcc:197-207)"""
+    rng = np.random.default_rng(n_bufs * 1000 + k)
+    data = [rand_elems(rng, n) for _ in range(n_bufs)]
+    bufs = [dev.upload(d) for d in data]
+    idx = rng.integers(0, n, size=k)
+    try:
+        got = dev.gather_multi(bufs, idx)
+    finally:
+        for b in bufs:
+            dev.free(b)
+    assert got.shape == (n_bufs, k, 3)
+    for s in range(n_bufs):
+        assert (got[s] == data[s][idx]).all()
+
+
 @pytest.mark.parametrize("n_rows,n_cols,nnz", [(1 << 12, 1 << 12, 3 << 12), (100, 37, 1000), (5000, 70000, 20000), (8, 8, 0)])
 def test_csr_transpose_on_device(dev, n_rows, n_cols, nnz):
     """b200_csr_transpose_dev: the entries of an (row, col, coeff) list regrouped by column (counting sort with atomic cursors).
