@@ -54,23 +54,27 @@ def workload(log_n=LOG_N):
     """The hot-path call sequence of aurora_snark_prover (non-zk, rho=3, FRI localization 2), SURVEY.md §3.1."""
     n, m = log_n, log_n + RHO
     N = 1 << n
-    # the calls the drop-in's prover makes (bench/host_gaps.py lists them; profiles/r2_host_gaps_N20_v3.txt):
-    # f_1v over the variable domain, f_1v over L (f_z), h = the sumcheck quotient over L
-    ffts = [(32, n), (32, m), (N - 1, m)]
+    # the calls the drop-in's prover makes (bench/host_gaps.py lists them; profiles/r2_host_gaps_N20_v4.txt):
+    # f_1v over the variable domain, f_1v over L (f_z)
+    ffts = [(32, n), (32, m)]
     # evaluations over H / the variable domain straight to L (b200_gf192_lde; the reference's IFFT + FFT pairs): f_w, f_Az, f_Bz,
     # f_Cz (r1cs_rs_iop.tcc:449-479, 497-569), p_alpha' and p_alpha_ABC (basic_lincheck_aux.tcc:86-144)
     ldes = [(n, m)] * 6
-    # f_1v (twice: submit_witness_oracles and the f_z oracle), sumcheck's combined f, the final FRI polynomial
-    iffts = [5, 5, n + 1, 4]
+    # f_1v (twice: submit_witness_oracles and the f_z oracle), the final FRI polynomial
+    iffts = [5, 5, 4]
+    # the sumcheck quotient h over L from f on two cosets of H (sumcheck.tcc:344-388: the reference's IFFT(2^21), division by Z_H,
+    # FFT(2^23)): two interpolation halves, one evaluation half (b200_gf192_lde_interpolate / _evaluate)
+    quotients = [(n, m)]
     folds = [(m, 1)] + [(k, 2) for k in range(m - 1, 4, -2)]        # (dim of L_i, eta)
     trees = [(4, m, 2), (1, m, 2)] + [(1, k, 4) for k in range(m - 1, 4, -2)]   # (n_oracles, dim, coset)
-    return ffts, ldes, iffts, folds, trees
+    return ffts, ldes, iffts, folds, trees, quotients
 
 
-def algorithmic_bytes(ffts, ldes, iffts, folds, trees):
+def algorithmic_bytes(ffts, ldes, iffts, folds, trees, quotients=()):
     """FFT / LDE 24*(n_in + 2^m); IFFT 48*2^k; fold 24*|L_i|*(1+2^-eta); Merkle 24*n_or*|L| + 32*(2*leaves-1)."""
     b = sum(24 * (nc + (1 << m)) for nc, m in ffts) + sum(24 * ((1 << d) + (1 << m)) for d, m in ldes)
     b += sum(48 * (1 << k) for k in iffts)
+    b += sum(2 * 48 * (1 << d) + 24 * ((1 << d) + (1 << m)) for d, m in quotients)
     b += sum(24 * (1 << k) * (1 + 2.0 ** -eta) for k, eta in folds)
     b += sum(24 * no * (1 << k) + 32 * (2 * ((1 << k) // cs) - 1) for no, k, cs in trees)
     return b
@@ -168,7 +172,7 @@ def run_gpu(args):
         dist = dist_mod
 
     dev = L.B200(local_rank)
-    ffts, ldes, iffts, folds, trees = workload()
+    ffts, ldes, iffts, folds, trees, quotients = workload()
     rng = np.random.default_rng(1234 + rank)           # independent proof instance per GPU
     n_l = 1 << M
 
@@ -183,7 +187,10 @@ def run_gpu(args):
 
     # ---- device-resident state: 5 full-size oracles + inputs ----
     dom_L = L.Domain.standard(M)
-    dom_of = {k: L.Domain.standard(k) for k in set([n for _, n in ffts] + iffts)}
+    dom_of = {k: L.Domain.standard(k) for k in set([n for _, n in ffts] + iffts + [d for d, _ in ldes])}
+    # the two cosets of span(basis[0..d)) the first 2^(d+1) positions of L lie on (shift of L, shift + basis[d])
+    coset_of = {d: (L.Domain.standard(d, shift_int=1 << M), L.Domain.standard(d, shift_int=(1 << M) | (1 << d))) for d, _ in quotients}
+    half_a, half_b = dev.alloc(1 << LOG_N), dev.alloc(1 << LOG_N)
     # FRI domains L_i have non-standard bases (fri_ldt.tcc:310-338); the fold cost does not depend on the basis values
     fold_doms = {k: L.Domain.affine(rng.integers(0, 2**64, size=(k, 3), dtype=np.uint64),
                                     rng.integers(0, 2**64, size=3, dtype=np.uint64)) for k, _ in folds}
@@ -208,6 +215,10 @@ def run_gpu(args):
             dev.gf192_lde_dev(dom_of[d], dom_L, evals_in, oracles[oi % 5]); oi += 1
         for k in iffts:
             dev.gf192_ifft_dev(dom_of[k], evals_in, small_out)
+        for d, m in quotients:
+            dev.gf192_lde_interpolate_dev(coset_of[d][0], evals_in, half_a)
+            dev.gf192_lde_interpolate_dev(coset_of[d][1], evals_in, half_b)
+            dev.gf192_lde_evaluate_dev(dom_L, d, half_a, oracles[oi % 5]); oi += 1
         cur = oracles[4]
         for k, eta in folds:
             dev.fri_fold_dev(1, None, fold_doms[k], eta, x_chal, cur, fri_bufs[k - eta])
@@ -298,7 +309,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "gf2^192 (carry-less u32 limbs) + u64 BLAKE2b", "data": "synthetic",
         "config": dict(CONFIG),
-        "value_scope": "hot-path calls of one proof as the drop-in prover makes them (6 fused LDE, 3 FFT, 4 IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
+        "value_scope": "hot-path calls of one proof as the drop-in prover makes them (6 fused LDE, the sumcheck quotient as 2 interpolation + 1 evaluation halves, 2 short FFT, 3 short IFFT, 10 FRI folds, 11 Merkle trees), oracles resident in HBM; "
                        "the whole prover is `e2e`",
         "roofline": {"bound": "hbm", "kernel": "additive_tile_pass<0>: butterfly tile pass, 8 stages over the 2^23-point oracle (8 cosets)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -314,13 +325,13 @@ def run_gpu(args):
                      "note": "integer-pipe bound, not HBM bound: ~850 instructions (292 IMAD.WIDE at quarter rate + 512 LOP3) per GF(2^192) "
                              "multiplication-butterfly, 100 multiplications per 24-byte coefficient; traffic below the algorithmic bytes = part of "
                              "the array is still in the 126 MB L2 from the previous pass; DESIGN.md 3.1-3.2, profiles/r2_variants.md"},
-        "algorithmic_bytes_per_step": algorithmic_bytes(ffts, ldes, iffts, folds, trees),
+        "algorithmic_bytes_per_step": algorithmic_bytes(ffts, ldes, iffts, folds, trees, quotients),
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary() if rank == 0 else None,
         "host_cores_of_rank": cores,
     }
     # free the synthetic state before the whole provers run
-    for b in oracles + [coeff_in, evals_in, small_out] + list(fri_bufs.values()):
+    for b in oracles + [coeff_in, evals_in, small_out, half_a, half_b] + list(fri_bufs.values()):
         dev.free(b)
     dev.sync()
 

@@ -124,6 +124,15 @@ int b200_gf192_ifft_batch(b200_ctx *, const b200_domain *H, b200_buf evals, size
  * H->basis (B200_ERR_INVALID otherwise: use the two calls).  Row r of a batch reads evals + r * 2^H->dim, writes out + r * 2^L->dim. */
 int b200_gf192_lde(b200_ctx *, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf evals_out);
 int b200_gf192_lde_batch(b200_ctx *, const b200_domain *H, const b200_domain *L, b200_buf evals, size_t batch, b200_buf evals_out);
+/* The two halves of the fused extension as separate calls.  `interpolate`: evaluations over H -> the 2^H->dim coefficients of
+ * the polynomial in the basis-dependent form the reference holds between additive_IFFT's inverse butterflies and its bit
+ * reversal (fft.tcc:139-170); `evaluate`: such coefficients w.r.t. L->basis[0 .. coeff_dim) -> evaluations over L.  The form is
+ * LINEAR in the polynomial and splits along cosets: for H' = H + L->basis[dim H], a polynomial f of degree < 2|H| satisfies
+ * f = A + (Z_H / Z_H(basis[dim H])) * B with coeffs(B) = interpolate_H(f|H) + interpolate_{H'}(f|H'), so the quotient of the
+ * sumcheck (sumcheck.tcc:344-388: IFFT, division by Z_H, FFT) is two interpolations, a sum, one scaling and one evaluation.
+ * Neither half runs in place. */
+int b200_gf192_lde_interpolate(b200_ctx *, const b200_domain *H, b200_buf evals, b200_buf coeffs_out);
+int b200_gf192_lde_evaluate(b200_ctx *, const b200_domain *L, uint32_t coeff_dim, b200_buf coeffs, b200_buf evals_out);
 /* element-wise helpers (gf192::operator*=, inverse: gf192.cpp:72-184, 245-288) */
 int b200_gf192_mul(b200_ctx *, b200_buf out, b200_buf a, b200_buf b, size_t n);
 int b200_gf192_inv(b200_ctx *, b200_buf out, b200_buf a, size_t n);

@@ -214,6 +214,34 @@ class B200:
     def gf192_lde_dev(self, dom_h, dom_l, evals, out, batch=1):
         self._chk(self.lib.b200_gf192_lde_batch(self.ctx, C.byref(dom_h.c), C.byref(dom_l.c), C.c_uint64(evals), C.c_size_t(batch), C.c_uint64(out)))
 
+    def gf192_lde_interpolate_dev(self, dom_h, evals, coeffs_out):
+        self._chk(self.lib.b200_gf192_lde_interpolate(self.ctx, C.byref(dom_h.c), C.c_uint64(evals), C.c_uint64(coeffs_out)))
+
+    def gf192_lde_evaluate_dev(self, dom_l, coeff_dim, coeffs, out):
+        self._chk(self.lib.b200_gf192_lde_evaluate(self.ctx, C.byref(dom_l.c), C.c_uint32(coeff_dim), C.c_uint64(coeffs), C.c_uint64(out)))
+
+    def gf192_lde_halves(self, dom_h_list, evals_list, dom_l, scale=None):
+        """evaluate_L( scale * sum_i interpolate_{H_i}(evals_i) ) through b200_gf192_lde_interpolate / _evaluate (the coefficient
+        form in between is opaque but linear); all H_i have L's first dim(H) basis vectors.  Returns 2^dim_L evaluations."""
+        d, nl = dom_h_list[0].dim, 1 << dom_l.dim
+        acc = None
+        for dom, ev in zip(dom_h_list, evals_list):
+            a, x = self.upload(ev), self.alloc(1 << d)
+            try:
+                self._chk(self.lib.b200_gf192_lde_interpolate(self.ctx, C.byref(dom.c), C.c_uint64(a), C.c_uint64(x)))
+                part = self.download(x, 1 << d)
+            finally:
+                self.free(a); self.free(x)
+            acc = part if acc is None else acc ^ part
+        if scale is not None:
+            acc = self.gf192_mul(acc, np.tile(np.asarray(scale, dtype=np.uint64).reshape(1, 3), (1 << d, 1)))
+        b, o = self.upload(acc), self.alloc(nl)
+        try:
+            self._chk(self.lib.b200_gf192_lde_evaluate(self.ctx, C.byref(dom_l.c), C.c_uint32(d), C.c_uint64(b), C.c_uint64(o)))
+            return self.download(o, nl)
+        finally:
+            self.free(b); self.free(o)
+
     def gf192_lde(self, dom_h, dom_l, rows):
         """fused IFFT over H + FFT over L of every row: rows (batch, 2^dim_H, 3) -> (batch, 2^dim_L, 3)"""
         rows = np.ascontiguousarray(rows, dtype=np.uint64)

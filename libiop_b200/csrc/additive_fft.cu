@@ -860,38 +860,15 @@ int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf ou
    butterfly stages per coset of span(basis[0..d)) in L with that coset's recursed shifts.  90 * 2^d instead of 130 * 2^d
    multiplications for d = 20, m = 23, no twist tables, and — no bit-reversed gather to coalesce — 12 stages per
    contiguous tile pass: 2 + 2 launches instead of 69.  Same batch convention as additive_fft. */
-int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf out, size_t batch)
+/* The two halves of the extension as separate steps, X = the basis-dependent intermediate coefficients (2^d per row; what the
+   reference holds after additive_IFFT's inverse butterflies, fft.tcc:139-168, before its bit reversal).  X is linear in the
+   polynomial, so callers may combine several interpolations before one evaluation (the sumcheck quotient). */
+static int lde_inverse_half(b200_ctx *c, const std::shared_ptr<AdditivePlan> &pl, const b200_domain *H, const gf192 *evals, gf192 *X, uint32_t B)
 {
-    if (!H || !L || H->kind != B200_DOMAIN_AFFINE_SUBSPACE || L->kind != B200_DOMAIN_AFFINE_SUBSPACE)
-        return set_err(c, B200_ERR_INVALID, "the fused extension needs two affine subspace domains");
-    const uint32_t d = H->dim, m = L->dim;
-    if (m > 31 || d > m) return set_err(c, B200_ERR_INVALID, "extension from dimension %u to %u is not possible", d, m);
-    if (d && memcmp(H->basis, L->basis, (size_t)d * sizeof(gf192)) != 0)
-        return set_err(c, B200_ERR_INVALID, "the codeword domain does not extend the basis of the interpolation domain");
-    if (batch == 0) return 0;
-    if (batch > ((size_t)1 << 20) || (batch << m) > ((size_t)1 << 34))
-        return set_err(c, B200_ERR_INVALID, "batch of %zu extensions to 2^%u points is too large", batch, m);
-    const size_t nd = (size_t)1 << d, n = (size_t)1 << m;
-    gf192 *o = (gf192 *)out;
-    const uint32_t B = (uint32_t)batch;
-    if (d == 0) {                                    /* constant polynomials */
-        for (size_t r = 0; r < batch; ++r) {
-            fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(o + r * n, (const gf192 *)evals + r, n);
-            B200_LAUNCH_CHECK(c);
-        }
-        return 0;
-    }
-    std::shared_ptr<AdditivePlan> pl;
-    int rc = get_plan(c, (const gf192 *)H->basis, d, false, &pl, /*need_twists=*/false);
+    const uint32_t d = H->dim;
+    gf192 *taus_h = nullptr;
+    int rc = upload_taus(c, *pl, H, d, d, &taus_h);
     if (rc) return rc;
-    gf192 *taus_h = nullptr, *taus_l = nullptr;
-    rc = upload_taus(c, *pl, H, d, d, &taus_h);
-    if (rc) return rc;
-    rc = upload_taus(c, *pl, L, d, m, &taus_l);
-    if (rc) return rc;
-    gf192 *X = (gf192 *)scratch_get(c, 0, batch * nd * sizeof(gf192));
-    if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate extension work array");
-
     PassParams P; memset(&P, 0, sizeof P);
     P.sums = pl->sums;
     const uint32_t tb = std::min(kTileBits, d);
@@ -899,7 +876,7 @@ int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_b
     P.taus = taus_h; P.n_extra = 0; P.src_coset_stride_log = (B > 1) ? d : 32; P.src_coset_shr = 0;
     std::vector<uint32_t> steps;
     for (int jj = (int)d - 1; jj >= (int)tb; --jj) steps.push_back((OP_BF << 8) | (uint32_t)jj);
-    const gf192 *cur = (const gf192 *)evals;
+    const gf192 *cur = evals;
     for (const Pass &p : schedule(steps, d)) {
         P.src = cur; P.dst = X;
         rc = launch_pass<true>(c, p, P, d, B);
@@ -913,6 +890,17 @@ int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_b
         rc = launch_pass<true>(c, p, P, d, B);
         if (rc) return rc;
     }
+    return 0;
+}
+static int lde_forward_half(b200_ctx *c, const std::shared_ptr<AdditivePlan> &pl, uint32_t d, const b200_domain *L, const gf192 *X, gf192 *o, uint32_t B)
+{
+    const uint32_t m = L->dim;
+    gf192 *taus_l = nullptr;
+    int rc = upload_taus(c, *pl, L, d, m, &taus_l);
+    if (rc) return rc;
+    PassParams P; memset(&P, 0, sizeof P);
+    P.sums = pl->sums;
+    const uint32_t tb = std::min(kTileBits, d);
     /* butterflies per coset of L (fft.tcc:101-120): X -> out */
     P.taus = taus_l; P.n_extra = m - d;
     const uint32_t n_cosets = B << (m - d);
@@ -930,7 +918,7 @@ int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_b
         rc = launch_pass<false>(c, p, P, d, n_cosets);
         if (rc) return rc;
     }
-    steps.clear();
+    std::vector<uint32_t> steps;
     for (uint32_t jj = tb; jj < d; ++jj) steps.push_back((OP_BF << 8) | jj);
     for (const Pass &p : schedule(steps, d)) {
         P.src = o; P.dst = o; P.src_coset_stride_log = d; P.src_coset_shr = 0;
@@ -938,6 +926,79 @@ int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_b
         if (rc) return rc;
     }
     return 0;
+}
+static int lde_check(b200_ctx *c, const b200_domain *L, uint32_t d, size_t batch)
+{
+    if (!L || L->kind != B200_DOMAIN_AFFINE_SUBSPACE)
+        return set_err(c, B200_ERR_INVALID, "the fused extension needs affine subspace domains");
+    const uint32_t m = L->dim;
+    if (m > 31 || d > m) return set_err(c, B200_ERR_INVALID, "extension from dimension %u to %u is not possible", d, m);
+    if (batch > ((size_t)1 << 20) || (batch << m) > ((size_t)1 << 34))
+        return set_err(c, B200_ERR_INVALID, "batch of %zu extensions to 2^%u points is too large", batch, m);
+    return 0;
+}
+
+int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf out, size_t batch)
+{
+    if (!H || H->kind != B200_DOMAIN_AFFINE_SUBSPACE) return set_err(c, B200_ERR_INVALID, "the fused extension needs two affine subspace domains");
+    const uint32_t d = H->dim;
+    int rc = lde_check(c, L, d, batch);
+    if (rc) return rc;
+    const uint32_t m = L->dim;
+    if (d && memcmp(H->basis, L->basis, (size_t)d * sizeof(gf192)) != 0)
+        return set_err(c, B200_ERR_INVALID, "the codeword domain does not extend the basis of the interpolation domain");
+    if (batch == 0) return 0;
+    const size_t nd = (size_t)1 << d, n = (size_t)1 << m;
+    gf192 *o = (gf192 *)out;
+    if (d == 0) {                                    /* constant polynomials */
+        for (size_t r = 0; r < batch; ++r) {
+            fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(o + r * n, (const gf192 *)evals + r, n);
+            B200_LAUNCH_CHECK(c);
+        }
+        return 0;
+    }
+    std::shared_ptr<AdditivePlan> pl;
+    rc = get_plan(c, (const gf192 *)H->basis, d, false, &pl, /*need_twists=*/false);
+    if (rc) return rc;
+    gf192 *X = (gf192 *)scratch_get(c, 0, batch * nd * sizeof(gf192));
+    if (!X) return set_err(c, B200_ERR_NOMEM, "cannot allocate extension work array");
+    rc = lde_inverse_half(c, pl, H, (const gf192 *)evals, X, (uint32_t)batch);
+    if (rc) return rc;
+    return lde_forward_half(c, pl, d, L, X, o, (uint32_t)batch);
+}
+/* interpolation half alone: evaluations over H -> intermediate coefficients (2^H->dim per row) */
+int additive_lde_interpolate(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out, size_t batch)
+{
+    if (!H || H->kind != B200_DOMAIN_AFFINE_SUBSPACE) return set_err(c, B200_ERR_INVALID, "the fused extension needs affine subspace domains");
+    const uint32_t d = H->dim;
+    if (d > 31 || batch > ((size_t)1 << 20) || (batch << d) > ((size_t)1 << 34)) return set_err(c, B200_ERR_INVALID, "interpolation of %zu rows of 2^%u is too large", batch, d);
+    if (batch == 0) return 0;
+    if (d == 0) { B200_CUDA(c, cudaMemcpyAsync((void *)coeffs_out, (const void *)evals, batch * sizeof(gf192), cudaMemcpyDeviceToDevice, c->stream)); return 0; }
+    if (evals == coeffs_out) return set_err(c, B200_ERR_INVALID, "the interpolation half does not run in place");
+    std::shared_ptr<AdditivePlan> pl;
+    int rc = get_plan(c, (const gf192 *)H->basis, d, false, &pl, /*need_twists=*/false);
+    if (rc) return rc;
+    return lde_inverse_half(c, pl, H, (const gf192 *)evals, (gf192 *)coeffs_out, (uint32_t)batch);
+}
+/* evaluation half alone: intermediate coefficients w.r.t. L's first d basis vectors -> evaluations over L */
+int additive_lde_evaluate(b200_ctx *c, const b200_domain *L, uint32_t d, b200_buf coeffs, b200_buf out, size_t batch)
+{
+    int rc = lde_check(c, L, d, batch);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    const size_t n = (size_t)1 << L->dim;
+    if (d == 0) {
+        for (size_t r = 0; r < batch; ++r) {
+            fill_kernel<<<std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>((gf192 *)out + r * n, (const gf192 *)coeffs + r, n);
+            B200_LAUNCH_CHECK(c);
+        }
+        return 0;
+    }
+    if (coeffs == out) return set_err(c, B200_ERR_INVALID, "the evaluation half does not run in place");
+    std::shared_ptr<AdditivePlan> pl;
+    rc = get_plan(c, (const gf192 *)L->basis, d, false, &pl, /*need_twists=*/false);
+    if (rc) return rc;
+    return lde_forward_half(c, pl, d, L, (const gf192 *)coeffs, (gf192 *)out, (uint32_t)batch);
 }
 
 /* ---------------------------------------------------------------------------------------------- */

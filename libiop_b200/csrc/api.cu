@@ -471,6 +471,18 @@ int b200_gf192_lde_batch(b200_ctx *c, const b200_domain *H, const b200_domain *L
     B200_TRACE_SCOPE(c, "gf192_lde_batch", batch << (L ? L->dim : 0));
     return additive_lde(c, H, L, evals, evals_out, batch);
 }
+int b200_gf192_lde_interpolate(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "gf192_lde_interpolate", (size_t)1 << (H ? H->dim : 0));
+    return additive_lde_interpolate(c, H, evals, coeffs_out, 1);
+}
+int b200_gf192_lde_evaluate(b200_ctx *c, const b200_domain *L, uint32_t coeff_dim, b200_buf coeffs, b200_buf evals_out)
+{
+    B200_ENTER(c);
+    B200_TRACE_SCOPE(c, "gf192_lde_evaluate", (size_t)1 << (L ? L->dim : 0));
+    return additive_lde_evaluate(c, L, coeff_dim, coeffs, evals_out, 1);
+}
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { B200_ENTER(c); return gf192_mul_vec(c, out, a, b, n); }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
 {

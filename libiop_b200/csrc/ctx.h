@@ -153,6 +153,8 @@ inline uint32_t ceil_log2(size_t n)
 int additive_fft(b200_ctx *c, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out, size_t batch);
 int additive_ifft(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out, size_t batch);
 int additive_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf out, size_t batch);
+int additive_lde_interpolate(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf coeffs_out, size_t batch);
+int additive_lde_evaluate(b200_ctx *c, const b200_domain *L, uint32_t d, b200_buf coeffs, b200_buf out, size_t batch);
 int gf192_mul_vec(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n);
 int gf192_inv_vec(b200_ctx *c, b200_buf out, b200_buf a, size_t n);
 int fp_ntt(b200_ctx *c, const b200_fp_params *P, const b200_domain *L, b200_buf coeffs, size_t n_coeffs, b200_buf out);

@@ -232,6 +232,20 @@ int b200_gf192_lde_batch(b200_ctx *c, const b200_domain *H, const b200_domain *L
 }
 int b200_gf192_lde(b200_ctx *c, const b200_domain *H, const b200_domain *L, b200_buf evals, b200_buf out)
 { return b200_gf192_lde_batch(c, H, L, evals, 1, out); }
+/* The halves of the extension: the device's intermediate coefficient form is opaque but LINEAR in the polynomial; the
+   simulator uses the monomial coefficients for it (the one property callers rely on holds for any linear form). */
+int b200_gf192_lde_interpolate(b200_ctx *c, const b200_domain *H, b200_buf evals, b200_buf out)
+{
+    if (evals == out) return fail(c, B200_ERR_INVALID, "the interpolation half does not run in place");
+    return b200_gf192_ifft_batch(c, H, evals, 1, out);
+}
+int b200_gf192_lde_evaluate(b200_ctx *c, const b200_domain *L, uint32_t coeff_dim, b200_buf coeffs, b200_buf out)
+{
+    if (check_affine(c, L, "fused extension")) return B200_ERR_INVALID;
+    if (coeff_dim > L->dim) return fail(c, B200_ERR_INVALID, "extension from dimension %u to %u is not possible", coeff_dim, L->dim);
+    if (coeffs == out) return fail(c, B200_ERR_INVALID, "the evaluation half does not run in place");
+    return b200_gf192_fft_batch(c, L, coeffs, (size_t)1 << coeff_dim, 1, out);
+}
 int b200_gf192_mul(b200_ctx *c, b200_buf out, b200_buf a, b200_buf b, size_t n) { ++c->launches; orc_gf192_mul_vec(E(out), E(a), E(b), n); return 0; }
 int b200_gf192_inv(b200_ctx *c, b200_buf out, b200_buf a, size_t n)
 {

@@ -187,6 +187,46 @@ def test_fused_lde_equals_ifft_then_fft(dev, oracle, d, m, batch, shift_h):
         assert (got[r] == oracle.additive_fft(coeffs, m, basis_l, sl)).all(), r
 
 
+@pytest.mark.parametrize("d,m", [(6, 9), (10, 13), (13, 15)])
+def test_lde_halves_and_the_quotient_by_the_vanishing_polynomial(dev, oracle, d, m):
+    """b200_gf192_lde_interpolate / _evaluate: (1) the two halves compose to the fused extension, i.e. to the oracle's
+    additive_IFFT over H then additive_FFT over L; (2) the form in between is linear and shift-independent, which gives the
+    sumcheck quotient h = floor(f / Z_H) (sumcheck.tcc:344-388) from f's values on two cosets of H:
+        h|L = evaluate_L( (interpolate_{C_0}(f|C_0) + interpolate_{C_1}(f|C_1)) / (Z_H(b) - Z_H(0)) ),  C_1 = C_0 + b.
+    Checked against the oracle: f = g + Z_H * h for random g (deg < |H|), h (deg < |H|), Z_H expanded by multiplication."""
+    import libiop_b200 as L
+    rng = np.random.default_rng(17 * d + m)
+    basis_l = standard_basis(m)
+    sl = el(1 << m)
+    dom_l = L.Domain.affine(basis_l, sl)
+    nh = 1 << d
+    # (1) composition
+    sh = rand_elems(rng, 1)[0]
+    ev = rand_elems(rng, nh)
+    got = dev.gf192_lde_halves([L.Domain.affine(basis_l[:d], sh)], [ev], dom_l)
+    assert (got == oracle.additive_fft(oracle.additive_ifft(ev, d, basis_l[:d], sh), m, basis_l, sl)).all()
+    # (2) quotient: Z_H = prod_{a in H} (x - a), H = span(basis[0..d)) unshifted, as monomial coefficients by repeated products
+    g, h = rand_elems(rng, nh), rand_elems(rng, nh)
+    dom2 = (d + 1, basis_l[:d + 1], sl)                                   # the first 2|H| positions of L
+    h_on_2h = oracle.additive_fft(h, *dom2)
+    g_on_2h = oracle.additive_fft(g, *dom2)
+    pts = oracle.additive_fft(np.array([[0, 0, 0], [1, 0, 0]], dtype=np.uint64), *dom2)          # the polynomial x: the points themselves
+    H_elems = oracle.additive_fft(np.array([[0, 0, 0], [1, 0, 0]], dtype=np.uint64), d, basis_l[:d], el(0))
+    Z = np.tile(el(1).reshape(1, 3), (2 * nh, 1))
+    for a in H_elems:
+        Z = oracle.gf192_mul(Z, pts ^ a.reshape(1, 3))
+    f_on_2h = g_on_2h ^ oracle.gf192_mul(Z, h_on_2h)
+    # w = Z_H(b) - Z_H(0) with b = basis[d]; Z_H(0) = 0 for the unshifted H
+    w = np.tile(el(1).reshape(1, 3), (1, 1))
+    for a in H_elems:
+        w = oracle.gf192_mul(w, (basis_l[d] ^ a).reshape(1, 3))
+    w_inv = dev.gf192_inv(w)[0]
+    c0 = L.Domain.affine(basis_l[:d], sl)
+    c1 = L.Domain.affine(basis_l[:d], sl ^ basis_l[d])
+    got_h = dev.gf192_lde_halves([c0, c1], [f_on_2h[:nh], f_on_2h[nh:]], dom_l, scale=w_inv)
+    assert (got_h == oracle.additive_fft(h, m, basis_l, sl)).all()
+
+
 def test_fused_lde_rejects_unrelated_bases(dev):
     import libiop_b200 as L
     rng = np.random.default_rng(9)
