@@ -81,7 +81,7 @@ int crypto_generichash_blake2b(unsigned char *out, size_t outlen, const unsigned
 /* ---- randombytes_buf ---------------------------------------------------------------------------------------------
  * All of the reference's prover randomness comes through this symbol: the zero-knowledge masking polynomials
  * (gf192::random_element), Ligero's blinding rows and the Merkle leaf salts (merkle_tree.tcc:37-72).
- *   default        : a ChaCha20 keystream keyed with 32 bytes from getrandom(2) (re-keyed after fork) — unpredictable.
+ *   default        : a ChaCha20 keystream keyed from getrandom(2) (fast key erasure, re-keyed after fork) — unpredictable.
  *   deterministic  : the seeded xorshift64 stream of the parity harness (same stream as oracle/ref_shim/sodium_impl.c, so
  *                    the CPU reference and the drop-in draw identical instances and salts).  NOT zero-knowledge: only
  *                    b200_shim_randombytes_deterministic() switches it on, and the prover harness (prover_api.cpp) leaves
@@ -105,31 +105,59 @@ int b200_shim_randombytes_is_deterministic(void) { return shim_deterministic; }
 /* historical name used by the harnesses: same as ..._deterministic */
 void b200_shim_randombytes_seed(uint64_t seed) { b200_shim_randombytes_deterministic(seed); }
 
-/* ChaCha20 block function (RFC 8439 2.3) */
+/* ChaCha20 (RFC 8439 2.3), eight consecutive blocks at a time: the lane loops below are plain C that the compiler turns into
+   8 x 32-bit vector code (the avx2 clone is picked at run time; the generic one is the same source). */
+#include <pthread.h>
+#define CC_LANES 8
+typedef uint32_t cc_v8 __attribute__((vector_size(32)));        /* one state word of eight blocks (GCC vector extension) */
 #define CC_ROTL(v, n) (((v) << (n)) | ((v) >> (32 - (n))))
-#define CC_QR(a, b, c, d) a += b; d ^= a; d = CC_ROTL(d, 16); c += d; b ^= c; b = CC_ROTL(b, 12); \
-                          a += b; d ^= a; d = CC_ROTL(d, 8);  c += d; b ^= c; b = CC_ROTL(b, 7)
-static void chacha20_block(const uint32_t in[16], uint8_t out[64])
+#define CC_QR(a, b, c, d) x[a] += x[b]; x[d] ^= x[a]; x[d] = CC_ROTL(x[d], 16); x[c] += x[d]; x[b] ^= x[c]; x[b] = CC_ROTL(x[b], 12); \
+                          x[a] += x[b]; x[d] ^= x[a]; x[d] = CC_ROTL(x[d], 8);  x[c] += x[d]; x[b] ^= x[c]; x[b] = CC_ROTL(x[b], 7);
+#define CC_BLOCKS8_BODY                                                                     \
+    cc_v8 x[16], s[16];                                                                     \
+    for (int i = 0; i < 16; ++i) s[i] = (cc_v8){ in[i], in[i], in[i], in[i], in[i], in[i], in[i], in[i] }; \
+    s[12] += (cc_v8){ 0, 1, 2, 3, 4, 5, 6, 7 };                                             \
+    for (int i = 0; i < 16; ++i) x[i] = s[i];                                               \
+    for (int r = 0; r < 10; ++r) {                                                          \
+        CC_QR(0, 4, 8, 12) CC_QR(1, 5, 9, 13) CC_QR(2, 6, 10, 14) CC_QR(3, 7, 11, 15)       \
+        CC_QR(0, 5, 10, 15) CC_QR(1, 6, 11, 12) CC_QR(2, 7, 8, 13) CC_QR(3, 4, 9, 14)       \
+    }                                                                                       \
+    for (int i = 0; i < 16; ++i) {                                                          \
+        x[i] += s[i];                                                                       \
+        for (int l = 0; l < CC_LANES; ++l) { const uint32_t v = x[i][l]; memcpy(out + 64 * l + 4 * i, &v, 4); }   /* little-endian host */ \
+    }
+static void chacha20_blocks8_generic(const uint32_t in[16], uint8_t *out) { CC_BLOCKS8_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static void chacha20_blocks8_avx2(const uint32_t in[16], uint8_t *out) { CC_BLOCKS8_BODY }
+#endif
+static void chacha20_blocks8(const uint32_t in[16], uint8_t *out)
 {
-    uint32_t x[16];
-    for (int i = 0; i < 16; ++i) x[i] = in[i];
-    for (int r = 0; r < 10; ++r) {
-        CC_QR(x[0], x[4], x[8], x[12]); CC_QR(x[1], x[5], x[9], x[13]); CC_QR(x[2], x[6], x[10], x[14]); CC_QR(x[3], x[7], x[11], x[15]);
-        CC_QR(x[0], x[5], x[10], x[15]); CC_QR(x[1], x[6], x[11], x[12]); CC_QR(x[2], x[7], x[8], x[13]); CC_QR(x[3], x[4], x[9], x[14]);
-    }
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t v = x[i] + in[i];
-        out[4 * i] = (uint8_t)v; out[4 * i + 1] = (uint8_t)(v >> 8); out[4 * i + 2] = (uint8_t)(v >> 16); out[4 * i + 3] = (uint8_t)(v >> 24);
-    }
+#if defined(__x86_64__) && defined(__GNUC__)
+    static int has_avx2 = -1;
+    if (has_avx2 < 0) has_avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+    if (has_avx2) { chacha20_blocks8_avx2(in, out); return; }
+#endif
+    chacha20_blocks8_generic(in, out);
 }
 
+/* Fast-key-erasure generator over a keystream pool: a refill produces CC_POOL bytes under the current key, the first 32 of
+   which become the next key (so earlier output cannot be recomputed from a later state); requests are served from the rest
+   and every byte handed out is wiped from the pool.  Small requests — one field element is 24 bytes, a zero-knowledge proof
+   draws ~3 * 10^6 of them — cost a memcpy instead of two block functions each; large ones (Merkle salts: 2^20-byte batches)
+   run at the vector code's rate.  The state is re-keyed from getrandom(2) in a forked child (pthread_atfork) and guarded by a
+   mutex (libsodium's randombytes_buf is thread-safe too). */
+#define CC_POOL 4096
 static uint32_t cc_state[16];
-static pid_t cc_pid = 0;
+static uint8_t cc_pool[CC_POOL];
+static size_t cc_pool_pos = CC_POOL;
 static int cc_keyed = 0;
+static pthread_mutex_t cc_mu = PTHREAD_MUTEX_INITIALIZER;
 
+static void cc_forget(void) { cc_keyed = 0; cc_pool_pos = CC_POOL; pthread_mutex_init(&cc_mu, NULL); }
 static void secure_key(void)
 {
-    uint8_t key[48];
+    static int atfork_set = 0;
+    uint8_t key[44];
     size_t got = 0;
     while (got < sizeof key) {
         const ssize_t r = getrandom(key + got, sizeof key - got, 0);
@@ -140,26 +168,41 @@ static void secure_key(void)
     memcpy(&cc_state[4], key, 32);
     cc_state[12] = 0; memcpy(&cc_state[13], key + 32, 12);
     memset(key, 0, sizeof key);
-    cc_pid = getpid();
+    cc_pool_pos = CC_POOL;
+    if (!atfork_set) { pthread_atfork(NULL, NULL, cc_forget); atfork_set = 1; }
     cc_keyed = 1;
 }
-
+static void cc_refill(void)
+{
+    cc_state[12] = 0;
+    for (size_t off = 0; off < CC_POOL; off += 64 * CC_LANES) { chacha20_blocks8(cc_state, cc_pool + off); cc_state[12] += CC_LANES; }
+    memcpy(&cc_state[4], cc_pool, 32);
+    memset(cc_pool, 0, 32);
+    cc_pool_pos = 32;
+}
 static void secure_bytes(unsigned char *p, size_t size)
 {
-    if (!cc_keyed || cc_pid != getpid()) secure_key();
-    uint8_t block[64];
+    pthread_mutex_lock(&cc_mu);
+    if (!cc_keyed) secure_key();
     while (size) {
-        chacha20_block(cc_state, block);
-        if (++cc_state[12] == 0) secure_key();                  /* 256 GiB per key */
-        const size_t k = size < 64 ? size : 64;
-        memcpy(p, block, k);
-        p += k; size -= k;
+        if (cc_pool_pos == CC_POOL) cc_refill();
+        const size_t avail = CC_POOL - cc_pool_pos, k = size < avail ? size : avail;
+        memcpy(p, cc_pool + cc_pool_pos, k);
+        memset(cc_pool + cc_pool_pos, 0, k);
+        cc_pool_pos += k; p += k; size -= k;
     }
-    /* fast key erasure: the next 32 keystream bytes replace the key, so earlier output cannot be recomputed from a later state */
-    chacha20_block(cc_state, block);
-    memcpy(&cc_state[4], block, 32);
-    cc_state[12] = 0;
-    memset(block, 0, sizeof block);
+    pthread_mutex_unlock(&cc_mu);
+}
+
+/* keystream of ChaCha20 for (key, counter, nonce) through the 8-block core, for known-answer tests (RFC 8439 2.3.2 / 2.4.2):
+   n_blocks <= 8 blocks of 64 bytes starting at `counter` */
+void b200_shim_chacha20_keystream(const uint8_t key[32], uint32_t counter, const uint8_t nonce[12], uint8_t *out, size_t n_blocks)
+{
+    uint32_t st[16] = { 0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u };
+    uint8_t all[64 * CC_LANES];
+    memcpy(&st[4], key, 32); st[12] = counter; memcpy(&st[13], nonce, 12);
+    chacha20_blocks8(st, all);
+    memcpy(out, all, 64 * (n_blocks < CC_LANES ? n_blocks : CC_LANES));
 }
 
 void randombytes_buf(void *buf, size_t size)

@@ -49,6 +49,36 @@ def test_shim_randombytes_stream_is_the_seeded_xorshift(shim):
     assert bytes(buf)[:37] == stream(12345, 37)
 
 
+def test_shim_chacha20_core_matches_rfc8439(shim):
+    """the 8-block vector core of the default randombytes_buf against RFC 8439: the block function test vector (2.3.2: key
+    00..1f, nonce 00:00:00:09:00:00:00:4a:00:00:00:00, counter 1) and the counter-mode continuation (lanes 1..7 = counters 2..8,
+    checked against a scalar restatement of the block function)."""
+    def block(key, counter, nonce):
+        import struct
+        def rotl(v, n): return ((v << n) | (v >> (32 - n))) & 0xffffffff
+        st = [0x61707865, 0x3320646e, 0x79622d32, 0x6b206574] + list(struct.unpack("<8I", key)) + [counter] + list(struct.unpack("<3I", nonce))
+        x = st[:]
+        def qr(a, b, c, d):
+            x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = rotl(x[d] ^ x[a], 16)
+            x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = rotl(x[b] ^ x[c], 12)
+            x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = rotl(x[d] ^ x[a], 8)
+            x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = rotl(x[b] ^ x[c], 7)
+        for _ in range(10):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        return struct.pack("<16I", *[(a + b) & 0xffffffff for a, b in zip(x, st)])
+    key = bytes(range(32))
+    nonce = bytes.fromhex("000000090000004a00000000")
+    want0 = bytes.fromhex("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+                          "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+    assert block(key, 1, nonce) == want0                    # the restatement itself against the RFC vector
+    out = C.create_string_buffer(512)
+    shim.b200_shim_chacha20_keystream(key, C.c_uint32(1), nonce, out, C.c_size_t(8))
+    assert out.raw[:64] == want0
+    for lane in range(1, 8):
+        assert out.raw[64 * lane:64 * lane + 64] == block(key, 1 + lane, nonce), lane
+
+
 def test_shim_randombytes_is_unpredictable_unless_the_parity_switch_is_thrown(shim):
     """the default randombytes_buf must not be the seeded stream — zk masks and Merkle salts come from it.
     Default = ChaCha20 keyed from getrandom(2); the xorshift stream only after b200_shim_randombytes_deterministic/seed."""
