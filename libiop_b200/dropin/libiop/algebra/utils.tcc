@@ -1,6 +1,6 @@
 /* Shadow of libiop/algebra/utils.tcc for the drop-in build.
    batch_inverse_and_mul (utils.tcc:38-103) — Montgomery's batch inversion, a loop-carried chain of 3n multiplications on
-   the host — runs on the device for long vectors (b200_gf192_inv / b200_fp_inv: one inversion per run of 8 / 16 elements,
+   the host — runs on the device for long vectors (b200_gf192_inv / b200_fp_inv: one inversion per run of 32 / 16 elements,
    runs in parallel), followed by the scalar multiplication.  A zero element yields zero, which is what the reference's
    has_zeroes path returns (utils.tcc:73-103); without zeroes both give the unique inverses. */
 #include "b200_ref_traits.hpp"

@@ -1,10 +1,13 @@
 /* Shadow of libiop/relations/r1cs.tcc for the drop-in build.
    r1cs_constraint_system::create_Az_Bz_Cz_from_variable_assignment (r1cs.tcc:236-266): the three sparse matrix-vector
-   products A z, B z, C z.  The constraints are flattened once into CSR arrays (one pass over the terms, no arithmetic) and
-   each product is one b200_spmv_csr call; z goes up once, Az / Bz / Cz come down.
-   Crossover (measured, Aurora N = 2^20 on the B200 box): flattening costs about as much as the reference's own pass over
-   the terms, so with the one-term rows of generate_r1cs_example the device route is slower (whole prover 0.74 -> 0.78 s);
-   it is taken from three terms per row on average, where the multiplications dominate.  Small systems keep the host loop. */
+   products A z, B z, C z.
+   A constraint system registered by r1cs_sparse_matrix's constructor (every system the provers hand to a protocol) has its
+   matrices flattened and kept on the device (b200_constraint_matrices.hpp, shared with the lincheck's transposed products):
+   each product is one b200_spmv_csr_dev call on a device-resident z and the results stay on the device for the extension.
+   (The Aurora prover does not even come here without zero knowledge: r1cs_rs_iop.tcc's shadow interleaves the flattening of
+   one matrix with the product and extension of the previous one.)
+   Systems nobody registered: b200_spmv_csr with host arrays from three terms per row on average — flattening costs about as
+   much as the reference's own pass over the terms, so below that the host loop stays; small systems always keep it. */
 #include "b200_dropin_common.hpp"
 #include "b200_constraint_matrices.hpp"
 #include B200_REF_FILE(libiop/relations/r1cs.tcc)
