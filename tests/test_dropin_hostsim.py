@@ -74,6 +74,49 @@ def test_whole_provers_through_the_dropin_host_logic(sim, which, log_n, zk, nbyt
     assert (len(dump), hashlib.sha256(dump).hexdigest()) == (nbytes, sha)
 
 
+AURORA_VARIATIONS = [  # (field, log_n, k_inputs, zk, rs_extra, fri_loc): shapes the golden fingerprints do not cover
+    ("gf192", 12, 0, False, 3, 2), ("gf192", 12, 1, False, 3, 2), ("gf192", 12, 7, True, 3, 2), ("gf192", 12, 31, False, 2, 1),
+    ("gf192", 12, 3, True, 2, 3), ("gf192", 13, 15, False, 3, 3), ("gf192", 12, 255, False, 3, 2),
+    ("edwards", 12, 0, False, 3, 2), ("edwards", 12, 3, False, 3, 2), ("edwards", 12, 31, False, 2, 1), ("edwards", 13, 7, False, 3, 3)]
+
+
+@pytest.mark.parametrize("field,log_n,k_inputs,zk,rs_extra,fri_loc", AURORA_VARIATIONS)
+def test_aurora_parameter_variations_against_the_cpu_reference(sim, field, log_n, k_inputs, zk, rs_extra, fri_loc):
+    """The evaluation-domain forms of the prover's coefficient chains (witness codeword, sumcheck quotient, lincheck
+    polynomials: DESIGN.md 3.8b) at other input counts, rates and FRI localizations than the committed fingerprints: the
+    unmodified CPU reference compiled here (oracle/_ref) and the drop-in over the simulator must emit the same bytes."""
+    from oracle_lib import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libiopref.so not built (needs the reference checkout)")
+    ref = Reference()
+    with quiet_stdout():
+        if field == "gf192":
+            want = ref.aurora_gf192(log_n, k_inputs=k_inputs, make_zk=zk, rs_extra=rs_extra, fri_loc=fri_loc)
+            got = sim.aurora_gf192(log_n, k_inputs=k_inputs, make_zk=zk, rs_extra=rs_extra, fri_loc=fri_loc)
+        else:
+            want = ref.aurora_edwards(log_n, k_inputs=k_inputs, rs_extra=rs_extra, fri_loc=fri_loc)
+            got = sim.aurora_edwards(log_n, k_inputs=k_inputs, rs_extra=rs_extra, fri_loc=fri_loc)
+    assert got[2] == 1, "the reference verifier rejected the proof"
+    assert bytes(got[1]) == bytes(want[1])
+
+
+def test_device_matrix_paths_at_other_parameters_against_the_cpu_reference(sim):
+    """N = 2^14 is the smallest size at which the constraint matrices are served from the device (pipelined A z / B z / C z
+    extensions, transposed products, index oracles): Aurora with 3 inputs at rate 1/4, localization 3, and Fractal at rate 1/4,
+    localization 1 — neither among the committed fingerprints — against the unmodified CPU reference compiled here."""
+    from oracle_lib import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libiopref.so not built (needs the reference checkout)")
+    ref = Reference()
+    with quiet_stdout():
+        want_a = ref.aurora_gf192(14, k_inputs=3, make_zk=False, rs_extra=2, fri_loc=3)
+        got_a = sim.aurora_gf192(14, k_inputs=3, make_zk=False, rs_extra=2, fri_loc=3)
+        want_f = ref.fractal_edwards(14, rs_extra=2, fri_loc=1)
+        got_f = sim.fractal_edwards(14, rs_extra=2, fri_loc=1)
+    assert got_a[2] == 1 and bytes(got_a[1]) == bytes(want_a[1])
+    assert got_f[2] == 1 and bytes(got_f[1]) == bytes(want_f[1])
+
+
 def test_provers_do_not_read_device_resident_vectors_on_the_host(sim):
     """Oracles the adapter produces stay on the device behind lazy host vectors; a host read is served correctly by the fault
     handler but costs a whole-vector download.  None of the provers may take that path (the same check runs on the GPU box in
