@@ -27,6 +27,7 @@
 #include "ctx.h"
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <type_traits>
 
 #include "gf192.cuh"
 
@@ -107,6 +108,32 @@ struct Tile {
     }
 };
 
+/* the array's own layout (24-byte elements): what a bulk copy delivers.  64-bit accesses at a 24-byte stride are
+   conflict-free (16 lanes x 8 bytes cover the 32 banks once). */
+struct TileAoS {
+    uint64_t *p;
+    __device__ __forceinline__ gf192 ld(uint32_t L) const
+    {
+        const uint64_t a = p[3 * L], b = p[3 * L + 1], c = p[3 * L + 2];
+        gf192 r;
+        r.w[0] = (uint32_t)a; r.w[1] = (uint32_t)(a >> 32);
+        r.w[2] = (uint32_t)b; r.w[3] = (uint32_t)(b >> 32);
+        r.w[4] = (uint32_t)c; r.w[5] = (uint32_t)(c >> 32);
+        return r;
+    }
+    __device__ __forceinline__ void st(uint32_t L, const gf192 &x) const
+    {
+        p[3 * L] = (uint64_t)x.w[0] | ((uint64_t)x.w[1] << 32);
+        p[3 * L + 1] = (uint64_t)x.w[2] | ((uint64_t)x.w[3] << 32);
+        p[3 * L + 2] = (uint64_t)x.w[4] | ((uint64_t)x.w[5] << 32);
+    }
+    __device__ __forceinline__ void xor_into(uint32_t Ldst, uint32_t Lsrc) const
+    {
+        p[3 * Ldst] ^= p[3 * Lsrc]; p[3 * Ldst + 1] ^= p[3 * Lsrc + 1]; p[3 * Ldst + 2] ^= p[3 * Lsrc + 2];
+    }
+};
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+
 __device__ __forceinline__ gf192 ldg_elem(const gf192 *p)
 {
     const uint64_t *q = reinterpret_cast<const uint64_t *>(p);
@@ -127,18 +154,24 @@ __device__ __forceinline__ uint32_t insert_zero(uint32_t k, uint32_t pos)
 /* NT threads per CTA, at least MB resident CTAs per SM.  Two instantiations per direction: 256 x 2 for grids that fill the
    machine (two 96 KiB tiles per SM) and 512 x 1 for small transforms whose whole pass is a handful of CTAs (a 2^11-point
    Ligero row is ONE tile: the chain of ~70 dependent steps then runs twice as fast on 16 warps). */
-template <bool INV, int NT, int MB>
+/* TMA = true: the tile is one contiguous run of the array on both sides (P.lo = P.c = P.ctop = P.cb = 0, no bit reversal: the
+   12-stage passes of the fused extension and of its halves).  One thread stages it with cp.async.bulk (TMA bulk copy,
+   UBLKCP in SASS) completing on an mbarrier, the tile keeps the array's AoS layout in shared memory, and it is written back
+   with cp.async.bulk.global.shared.  Measured against the 128-bit staging: profiles/r2_variants.md 1. */
+template <bool INV, int NT, int MB, bool TMA = false>
 __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
 {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
 
     const uint32_t mainb = P.hi - P.lo;
     const uint32_t tbw = mainb + P.c + P.ctop;              /* index bits of one coset inside the tile */
     const uint32_t tb = tbw + P.cb;
     const uint32_t T = 1u << tb;
     const uint32_t wmask = (1u << tbw) - 1u;
-    Tile t;
-    t.p0 = smem; t.p1 = smem + T + B200_SMEM_PAD; t.p2 = smem + 2 * (T + B200_SMEM_PAD);
+    typename std::conditional<TMA, TileAoS, Tile>::type t;
+    if constexpr (TMA) { t.p = smem; }
+    else { t.p0 = smem; t.p1 = smem + T + B200_SMEM_PAD; t.p2 = smem + 2 * (T + B200_SMEM_PAD); }
     gf192 *tau_s = reinterpret_cast<gf192 *>(smem + 3 * (T + B200_SMEM_PAD));   /* [2^cb][d] */
 
     const uint32_t d = P.d;
@@ -148,6 +181,22 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
     const uint32_t midbits = P.lo - P.c;
     const uint32_t mid = tile & ((1u << midbits) - 1u);
     const uint32_t top = tile >> midbits;
+
+    const uint32_t tile_bytes = T * (uint32_t)sizeof(gf192);
+    if constexpr (TMA) {
+        /* contiguous tile: element tile * T of the coset's source row */
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const size_t cofs = P.src_coset_stride_log >= 32 ? 0 : ((size_t)(coset_base >> P.src_coset_shr) << P.src_coset_stride_log);
+            const char *g = reinterpret_cast<const char *>(P.src + cofs + (size_t)tile * T);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(tile_bytes) : "memory");
+            const uint32_t chunk = tile_bytes > 24576u ? 24576u : tile_bytes;
+            for (uint32_t ofs = 0; ofs < tile_bytes; ofs += chunk)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(reinterpret_cast<char *>(smem) + ofs)), "l"(g + ofs), "r"(chunk), "r"(smem_u32(&mbar)) : "memory");
+        }
+    }
 
     /* recursed shift of each coset for every depth: F2-linear in the shift, so
        tau(shift + sum_k q_k basis[d+k]) = tau(shift) + sum_k q_k tau(basis[d+k]) */
@@ -170,6 +219,13 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
         return w | (mid << P.c) | (u << P.lo) | (top << P.hi) | (P.ctop ? (tbv << (d - P.ctop)) : 0u);
     };
 
+    if constexpr (TMA) {
+        __syncthreads();                                   /* the barrier's initialisation is visible to every waiter */
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    } else {
 #if B200_TILE_VEC128
     /* 128-bit variant: a thread moves two consecutive elements (48 bytes) with three 16-byte loads and three 16-byte
        shared-memory stores.  Index bit 0 of the tile is index bit 0 of the array in every tile shape, so elements L and L+1
@@ -192,6 +248,7 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
         const uint32_t a = (P.bitrev == 1) ? (__brev(i) >> (32 - d)) : i;
         const size_t cofs = shared_src ? 0 : ((size_t)((coset_base + (L >> tbw)) >> P.src_coset_shr) << P.src_coset_stride_log);
         t.st(L, ldg_elem(P.src + cofs + a));
+    }
     }
 
     for (uint32_t o = 0; o < P.n_ops; ++o) {
@@ -272,6 +329,20 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
             }
         }
     }
+    if constexpr (TMA) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* generic-proxy writes visible to the async proxy */
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            char *g = reinterpret_cast<char *>(P.dst + ((size_t)coset_base << d) + (size_t)tile * T);
+            const uint32_t chunk = tile_bytes > 24576u ? 24576u : tile_bytes;
+            for (uint32_t ofs = 0; ofs < tile_bytes; ofs += chunk)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(g + ofs), "r"(smem_u32(reinterpret_cast<char *>(smem) + ofs)), "r"(chunk) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    } else {
     __syncthreads();
 
     uint64_t *out = reinterpret_cast<uint64_t *>(P.dst);
@@ -295,6 +366,7 @@ __global__ void __launch_bounds__(NT, MB) additive_tile_pass(const PassParams P)
         const uint32_t a = (P.bitrev == 2) ? (__brev(i) >> (32 - d)) : i;
         uint64_t *q = out + (((size_t)(coset_base + (L >> tbw)) << d) + a) * 3;
         q[0] = t.p0[L]; q[1] = t.p1[L]; q[2] = t.p2[L];
+    }
     }
 }
 
@@ -608,6 +680,11 @@ static std::vector<Pass> schedule(const std::vector<uint32_t> &steps, uint32_t d
     return passes;
 }
 
+static bool tile_tma_enabled()
+{
+    static const bool on = !(getenv("B200_TILE_TMA") && getenv("B200_TILE_TMA")[0] == '0');     /* ablation switch */
+    return on;
+}
 static bool cluster_disabled()
 {
     static const bool off = getenv("B200_NO_CLUSTER") != nullptr;     /* ablation switch */
@@ -629,6 +706,8 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
         B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        B200_CUDA(c, cudaFuncSetAttribute(additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[INV] = true;
     }
     const uint64_t nblocks = ((uint64_t)1 << (d - tbw)) * (n_cosets >> p.cb);
@@ -662,7 +741,12 @@ static int launch_pass(b200_ctx *c, const Pass &p, PassParams P, uint32_t d, uin
         B200_LAUNCH_CHECK(c);
         return 0;
     }
+    /* contiguous tile on both sides -> TMA bulk staging (16-byte aligned runs of a multiple of 16 bytes) */
+    const bool contiguous = p.lo == 0 && p.c == 0 && p.ctop == 0 && p.cb == 0 && p.bitrev == 0 && tb >= 1 &&
+                            ((reinterpret_cast<uintptr_t>(P.src) | reinterpret_cast<uintptr_t>(P.dst)) & 15u) == 0;
     if (few_ctas) additive_tile_pass<INV, 512, 1><<<(unsigned)nblocks, 512, smem, c->stream>>>(P);
+    else if (contiguous && tile_tma_enabled())
+        additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS, true><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     else additive_tile_pass<INV, B200_TILE_THREADS, B200_TILE_MINBLOCKS><<<(unsigned)nblocks, B200_TILE_THREADS, smem, c->stream>>>(P);
     B200_LAUNCH_CHECK(c);
     return 0;
