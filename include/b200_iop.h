@@ -232,6 +232,11 @@ int b200_gather_dev(b200_ctx *, b200_buf out, b200_buf table, b200_bytes idx, b2
 int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_t n);
 int b200_fill(b200_ctx *, b200_buf dst, size_t dst_offset, const uint64_t value[3], size_t n);
 
+/* row_out[k] = i for k in [row_ptr[i], row_ptr[i+1]), i < n_rows: the explicit row index of every entry of a CSR matrix whose
+ * row pointers (n_rows + 1 x u64) are on the device — what the entry-list consumers above and below address entries by, made
+ * on the device instead of being written and uploaded by the host (4 bytes per entry each way). */
+int b200_csr_row_indices_dev(b200_ctx *, size_t n_rows, b200_bytes row_ptr, b200_bytes row_out);
+
 /* Transpose of a device-resident sparse matrix given as an entry list (row[k], col[k], coeff[k]), k < nnz (u32 device arrays and a
  * device element array, as left by the flattening of an R1CS matrix): the entries regrouped by column as CSR over the columns —
  * col_ptr_out (n_cols + 1 x u64), src_out[k'] = the row of the entry now at k', coeff_out[k'].  The order of the entries inside one

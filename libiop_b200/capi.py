@@ -570,6 +570,18 @@ class B200:
             if dm:
                 self.free(dm)
 
+    def csr_row_indices(self, row_ptr):
+        """b200_csr_row_indices_dev: the explicit row of every entry from uploaded row pointers (u64, n_rows + 1)"""
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        n_rows, nnz = len(row_ptr) - 1, int(row_ptr[-1])
+        dp = self.alloc_bytes(row_ptr.nbytes); self.upload_bytes(row_ptr.view(np.uint8), dp)
+        do = self.alloc_bytes(max(4 * nnz, 4))
+        try:
+            self._chk(self.lib.b200_csr_row_indices_dev(self.ctx, C.c_size_t(n_rows), C.c_uint64(dp), C.c_uint64(do)))
+            return np.frombuffer(self.download_bytes(do, 4 * nnz), dtype=np.uint32) if nnz else np.zeros(0, dtype=np.uint32)
+        finally:
+            self.free(dp); self.free(do)
+
     def csr_transpose(self, n_cols, col, row, coeff):
         """b200_csr_transpose_dev on uploaded entry lists; returns (col_ptr u64[n_cols+1], src u32[nnz], coeff (nnz,3))"""
         col = np.ascontiguousarray(col, dtype=np.uint32); row = np.ascontiguousarray(row, dtype=np.uint32)

@@ -319,6 +319,20 @@ int b200_fill(b200_ctx *c, b200_buf dst, size_t dst_offset, const uint64_t value
     return 0;
 }
 
+__global__ void csr_row_indices_kernel(const unsigned long long *row_ptr, uint32_t *row_out, size_t n_rows)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_rows; i += (size_t)gridDim.x * blockDim.x)
+        for (unsigned long long k = row_ptr[i], e = row_ptr[i + 1]; k < e; ++k) row_out[k] = (uint32_t)i;
+}
+int b200_csr_row_indices_dev(b200_ctx *c, size_t n_rows, b200_bytes row_ptr, b200_bytes row_out)
+{
+    B200_ENTER(c);
+    if (!n_rows) return 0;
+    if (n_rows >= ((size_t)1 << 32)) return set_err(c, B200_ERR_INVALID, "b200_csr_row_indices_dev: 32-bit row indices");
+    csr_row_indices_kernel<<<copy_grid(n_rows), 256, 0, c->stream>>>((const unsigned long long *)(uintptr_t)row_ptr, (uint32_t *)(uintptr_t)row_out, n_rows);
+    B200_LAUNCH_CHECK(c);
+    return 0;
+}
 int b200_csr_transpose_dev(b200_ctx *c, size_t n_cols, size_t nnz, b200_bytes col, b200_bytes row, b200_buf coeff,
                            b200_bytes col_ptr_out, b200_bytes src_out, b200_buf coeff_out)
 {

@@ -46,12 +46,22 @@ struct flat_matrix {
 
 template<typename FieldT>
 class constraint_matrices {
+    /* One pass over the constraint array — 72 bytes per constraint, the only time it is read — leaves, per matrix, the row
+       pointers and the address of each row's term block; the per-matrix fill passes then read 16 bytes per row instead of the
+       constraint again (the flatten is bound by host memory traffic, and N ranks share the host's bandwidth). */
+    struct row_index {
+        std::size_t n = 0;
+        uint64_t nnz[3] = { 0, 0, 0 };
+        std::unique_ptr<uint64_t[]> row_ptr[3];                                  /* n + 1 each */
+        std::unique_ptr<const linear_term<FieldT> *[]> terms[3];                 /* n each */
+    };
     struct entry {
         std::weak_ptr<r1cs_constraint_system<FieldT>> alive;
         bool built[3] = { false, false, false };
         flat_matrix M[3];
         bool built_t[3] = { false, false, false };
         flat_matrix T[3];                                     /* the transposes, CSR over the columns of M */
+        std::shared_ptr<row_index> rows;                      /* where every row's terms lie, for all three matrices (first use) */
     };
     std::map<const void *, entry> entries_;
     std::mutex mu_;
@@ -82,39 +92,61 @@ class constraint_matrices {
     static const linear_combination<FieldT> &row_of(const r1cs_constraint<FieldT> &c, int m) { return m == 0 ? c.a_ : m == 1 ? c.b_ : c.c_; }
     struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
 
-    /* Matrix m of `cs` (0 = A, 1 = B, 2 = C) flattened and uploaded.  Two passes over the constraints, row ranges split
-       over a few threads: the first reads the rows' term counts and lays down the row pointers relative to the range's
-       start; the second — after the ranges' totals are prefix-summed and arrays of the exact size allocated (page-locked:
-       the uploads are DMA in place) — rebases them and copies indices and coefficients.  The work is bound by memory
+    /* Matrix m of `cs` (0 = A, 1 = B, 2 = C) flattened and uploaded.  The first matrix asked for pays the pass over the
+       constraint array (index_rows: row pointers and term-block addresses of all three matrices, row ranges split over a few
+       threads, range totals prefix-summed); every matrix then has its column indices and coefficients copied into arrays of
+       the exact size (page-locked: the uploads are DMA in place).  The work is bound by memory
        traffic (one heap block per linear combination).  One matrix at a time so that the caller can start the device on
        A z while B is being flattened (r1cs_rs_iop.tcc shadow); profiles/r2_host_gaps_N20_v*.txt. */
+    static std::shared_ptr<row_index> index_rows(const r1cs_constraint_system<FieldT> &cs)
+    {
+        std::shared_ptr<row_index> R = std::make_shared<row_index>();
+        const std::size_t n = cs.constraints_.size();
+        R->n = n;
+        for (int m = 0; m < 3; ++m) { R->row_ptr[m].reset(new uint64_t[n + 1]); R->terms[m].reset(new const linear_term<FieldT> *[n ? n : 1]); }
+        const unsigned T = fill_threads(n);
+        std::vector<std::array<uint64_t, 3>> range_total(T);
+        row_index *r = R.get();
+        on_threads(T, [&cs, r, n, T, &range_total](unsigned t) {
+            uint64_t run[3] = { 0, 0, 0 };
+            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i)
+                for (int m = 0; m < 3; ++m) {
+                    const std::vector<linear_term<FieldT>> &terms = row_of(cs.constraints_[i], m).terms;
+                    r->row_ptr[m][i] = run[m]; r->terms[m][i] = terms.data(); run[m] += terms.size();
+                }
+            range_total[t] = { run[0], run[1], run[2] };
+        });
+        uint64_t base[3] = { 0, 0, 0 };
+        std::vector<std::array<uint64_t, 3>> range_base(T);
+        for (unsigned t = 0; t < T; ++t) for (int m = 0; m < 3; ++m) { range_base[t][m] = base[m]; base[m] += range_total[t][m]; }
+        on_threads(T, [r, n, T, &range_base](unsigned t) {                        /* rebase: relative -> absolute row pointers */
+            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i)
+                for (int m = 0; m < 3; ++m) r->row_ptr[m][i] += range_base[t][m];
+        });
+        for (int m = 0; m < 3; ++m) { R->row_ptr[m][n] = R->nnz[m] = base[m]; }
+        return R;
+    }
     static void build(entry &e, const r1cs_constraint_system<FieldT> &cs, int m)
     {
         using namespace libiop_b200;
         const std::size_t n = cs.constraints_.size();
         const bool trace = std::getenv("B200_FLATTEN_TRACE") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
-        std::unique_ptr<uint64_t[]> row_ptr(new uint64_t[n + 1]);
+        if (!e.rows) e.rows = index_rows(cs);
+        const row_index &R = *e.rows;
+        const uint64_t nnz = R.nnz[m];
+        const uint64_t *rp = R.row_ptr[m].get();
+        const linear_term<FieldT> *const *tp = R.terms[m].get();
         const unsigned T = fill_threads(n);
-        std::vector<uint64_t> range_total(T), range_base(T);
-        uint64_t *rp = row_ptr.get();
-        on_threads(T, [&cs, rp, n, T, m, &range_total](unsigned t) {
-            uint64_t run = 0;
-            for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) { rp[i] = run; run += row_of(cs.constraints_[i], m).terms.size(); }
-            range_total[t] = run;
-        });
-        uint64_t nnz = 0;
-        for (unsigned t = 0; t < T; ++t) { range_base[t] = nnz; nnz += range_total[t]; }
-        rp[n] = nnz;
-        std::unique_ptr<uint32_t[]> col(new uint32_t[nnz ? nnz : 1]), row(new uint32_t[nnz ? nnz : 1]);
+        std::unique_ptr<uint32_t[]> col(new uint32_t[nnz ? nnz : 1]);
         std::unique_ptr<void, raw_free> coeff_store(::operator new((nnz ? nnz : 1) * sizeof(FieldT)));      /* every slot is written below */
         FieldT *coeff = static_cast<FieldT *>(coeff_store.get());
-        uint32_t *colp = col.get(), *rowp = row.get();
+        uint32_t *colp = col.get();
         const auto t1 = std::chrono::steady_clock::now();
-        on_threads(T, [&cs, rp, colp, rowp, coeff, n, T, m, &range_base](unsigned t) {
+        on_threads(T, [rp, tp, colp, coeff, n, T](unsigned t) {
             for (std::size_t i = n * t / T, end = n * (t + 1) / T; i < end; ++i) {
-                uint64_t k = (rp[i] += range_base[t]);
-                for (const auto &term : row_of(cs.constraints_[i], m).terms) { colp[k] = (uint32_t)term.index_; rowp[k] = (uint32_t)i; new (&coeff[k]) FieldT(term.coeff_); ++k; }
+                const linear_term<FieldT> *term = tp[i];
+                for (uint64_t k = rp[i], stop = rp[i + 1]; k < stop; ++k, ++term) { colp[k] = (uint32_t)term->index_; new (&coeff[k]) FieldT(term->coeff_); }
             }
         });
         const auto t2 = std::chrono::steady_clock::now();
@@ -122,13 +154,15 @@ class constraint_matrices {
         F.n_rows = n; F.nnz = nnz;
         upload_bytes(F.row_ptr, rp, (n + 1) * sizeof(uint64_t));
         upload_bytes(F.col, colp, nnz * sizeof(uint32_t));
-        upload_bytes(F.row, rowp, nnz * sizeof(uint32_t));
+        F.row.reset(new device_bytes((nnz ? nnz : 1) * sizeof(uint32_t)));       /* the explicit row of every entry: expanded on the device */
+        throw_status(context(), b200_csr_row_indices_dev(context(), n, F.row_ptr->get(), F.row->get()));
         F.coeff = device_buffer(nnz ? nnz : 1);
         if (nnz) throw_status(context(), b200_upload(context(), F.coeff.get(), 0, reinterpret_cast<const uint64_t *>(coeff), nnz));
         throw_status(context(), b200_wait_uploads(context()));        /* the host arrays die with this scope */
         e.built[m] = true;
+        if (e.built[0] && e.built[1] && e.built[2]) e.rows.reset();
         if (trace)
-            std::fprintf(stderr, "[b200] flatten %c: %zu rows, %llu entries, count pass %.2f ms, fill pass %.2f ms on %u threads, upload %.2f ms\n",
+            std::fprintf(stderr, "[b200] flatten %c: %zu rows, %llu entries, row index %.2f ms, fill pass %.2f ms on %u threads, upload %.2f ms\n",
                          "ABC"[m], n, (unsigned long long)nnz, std::chrono::duration<double, std::milli>(t1 - t0).count(),
                          std::chrono::duration<double, std::milli>(t2 - t1).count(), T,
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());

@@ -156,6 +156,13 @@ int b200_scatter_dev(b200_ctx *, b200_buf out, b200_buf x, b200_bytes map, size_
 }
 int b200_fill(b200_ctx *, b200_buf dst, size_t off, const uint64_t value[3], size_t n)
 { for (size_t i = 0; i < n; ++i) std::memcpy(E(dst) + off + i, value, 24); return 0; }
+int b200_csr_row_indices_dev(b200_ctx *, size_t n_rows, b200_bytes row_ptr, b200_bytes row_out)
+{
+    const uint64_t *rp = reinterpret_cast<const uint64_t *>(row_ptr);
+    uint32_t *ro = reinterpret_cast<uint32_t *>(row_out);
+    for (size_t i = 0; i < n_rows; ++i) for (uint64_t k = rp[i]; k < rp[i + 1]; ++k) ro[k] = (uint32_t)i;
+    return 0;
+}
 int b200_csr_transpose_dev(b200_ctx *, size_t n_cols, size_t nnz, b200_bytes col, b200_bytes row, b200_buf coeff,
                            b200_bytes col_ptr_out, b200_bytes src_out, b200_buf coeff_out)
 {

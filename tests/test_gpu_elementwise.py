@@ -409,6 +409,16 @@ def test_gather_multi(dev, n_bufs, n, k):
         assert (got[s] == data[s][idx]).all()
 
 
+@pytest.mark.parametrize("n_rows,max_terms", [(1 << 12, 1), (5000, 4), (100, 0), (1, 7)])
+def test_csr_row_indices_on_device(dev, n_rows, max_terms):
+    """b200_csr_row_indices_dev: row_out[k] = i for k in [row_ptr[i], row_ptr[i+1]), rows with no entries included"""
+    rng = np.random.default_rng(n_rows + max_terms)
+    counts = rng.integers(0, max_terms + 1, size=n_rows)
+    row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    got = dev.csr_row_indices(row_ptr)
+    assert (got == np.repeat(np.arange(n_rows, dtype=np.uint32), counts)).all()
+
+
 @pytest.mark.parametrize("n_rows,n_cols,nnz", [(1 << 12, 1 << 12, 3 << 12), (100, 37, 1000), (5000, 70000, 20000), (8, 8, 0)])
 def test_csr_transpose_on_device(dev, n_rows, n_cols, nnz):
     """b200_csr_transpose_dev: the entries of an (row, col, coeff) list regrouped by column (counting sort with atomic cursors).
