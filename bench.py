@@ -397,8 +397,7 @@ def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0, verify_last=False):
         with _quiet_stdout():
             p = prover.DropinProver()
             seed = prover.DEFAULT_SEED + seed_offset          # one independent instance per rank (BASELINE config 5: seeds s, s+1, ...)
-            for _ in range(warmup):
-                p.aurora_gf192(log_n, seed=seed, verify=False)
+            warm = [p.aurora_gf192(log_n, seed=seed, verify=False)[0] for _ in range(warmup)]
             s0, l0 = p.device_stats(), p.lazy_stats()
             times, dump, acc = [], b"", -1
             for r in range(runs):
@@ -411,6 +410,9 @@ def whole_prover_e2e(log_n, runs=3, warmup=2, seed_offset=0, verify_last=False):
         sha = hashlib.sha256(dump).hexdigest()
         g = golden_fingerprint("aurora_gf192", log_n) if seed_offset == 0 else None
         return {"prover_s": float(np.median(times)), "prover_s_all": times,
+                # the untimed warm-up proofs of this process: the first builds the per-domain tables (twiddles, recursed shifts,
+                # x^-1 over the codeword domain, index tables), the pinned slabs and the lazy-vector reservation
+                "warmup_prover_s": warm,
                 "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // runs, "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // runs,
                 "gpu_launches_per_proof": (s1["launches"] - s0["launches"]) // runs,
                 "transcript_bytes": len(dump), "transcript_sha256": sha, "instance_seed": hex(seed),
