@@ -146,16 +146,43 @@ def ncu_traffic(kernel_substr="additive_tile_pass<0", grid=2048):
         return None, None
 
 
+def gpu_cpu_affinity(index, n_cpus):
+    """the CPUs NVML names as closest to GPU `index` (same NUMA node / PCIe root), or None"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpus + 63) // 64)
+        return {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+    except Exception:
+        return None
+
+
 def pin_rank_to_cores(local_rank, world):
-    """one disjoint slice of the host cores per rank: the reference's host code is single-threaded and every rank also drives
-    its own PCIe traffic — unpinned, 8 ranks migrate over the same cores (round-1 SCALE: e2e efficiency 0.856 at N = 8)"""
+    """one disjoint slice of the host cores per rank: the reference's host code is single-threaded, the drop-in flattens the
+    constraint matrices on a few threads, and every rank drives its own PCIe traffic — unpinned, 8 ranks migrate over the same
+    cores (round-1 SCALE: e2e efficiency 0.856 at N = 8).  The slice is taken from the cores NVML reports as closest to the
+    rank's GPU (shared evenly with the other ranks whose GPUs report the same set) when that is known, else from an even split
+    of the process's cores."""
     try:
         cores = sorted(os.sched_getaffinity(0))
-        if world > 1 and len(cores) >= world:
+        if world <= 1 or len(cores) < world:
+            return None
+        n_cpus = os.cpu_count() or (max(cores) + 1)
+        near = [gpu_cpu_affinity(r, n_cpus) for r in range(world)]
+        mine = None
+        if all(a for a in near):
+            group = [r for r in range(world) if near[r] == near[local_rank]]          # ranks sharing this GPU's CPU set
+            pool = [c for c in cores if c in near[local_rank]]
+            per = len(pool) // len(group)
+            if per >= 1:
+                k = group.index(local_rank)
+                mine = pool[k * per:(k + 1) * per]
+        if not mine:
             per = len(cores) // world
             mine = cores[local_rank * per:(local_rank + 1) * per]
-            os.sched_setaffinity(0, set(mine))
-            return mine
+        os.sched_setaffinity(0, set(mine))
+        return mine
     except Exception:
         pass
     return None
@@ -347,9 +374,12 @@ def run_gpu(args):
     if dist:
         import torch
         t = torch.tensor([e2e.get("prover_s", float("inf"))], device="cuda")
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if "prover_s" in e2e:
             e2e["prover_s_max_over_ranks"] = float(t.item())
+            e2e["prover_s_per_rank"] = [round(float(x.item()), 5) for x in per_rank]
     if "prover_s" in e2e:
         secs = e2e.get("prover_s_max_over_ranks", e2e["prover_s"])
         e2e = dict({"value": world * N / secs, "unit": "constraints/s"}, **e2e)
