@@ -19,9 +19,11 @@
 #define B200_DROPIN_CONSTRAINT_MATRICES_HPP_
 #include <array>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <list>
 #include <map>
 #include <memory>
@@ -29,6 +31,7 @@
 #include <new>
 #include <thread>
 #include <vector>
+#include <pthread.h>
 #include <sched.h>
 
 #include "b200_ref_traits.hpp"
@@ -37,6 +40,72 @@
 
 namespace libiop {
 namespace b200_glue {
+
+/* A few persistent host threads for the flatten passes.  Threads are created once per process (on first use, more when a
+   larger fan-out is asked for) and parked on a condition variable: no thread creation — and no thread-exit loss of the small-
+   block pool's per-thread free lists — per proof.  run(T, f) executes f(0) .. f(T-1), the caller taking part; one run at a
+   time.  A forked child starts with an empty pool (threads do not survive fork). */
+class host_workers {
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    unsigned n_threads_ = 0;
+    const std::function<void(unsigned)> *job_ = nullptr;
+    unsigned n_tasks_ = 0, next_task_ = 0, done_tasks_ = 0;
+    unsigned long long epoch_ = 0;
+
+    void work()
+    {
+        for (;;) {
+            unsigned t;
+            const std::function<void(unsigned)> *f;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!job_ || next_task_ >= n_tasks_) return;
+                t = next_task_++; f = job_;
+            }
+            (*f)(t);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (++done_tasks_ == n_tasks_) cv_done_.notify_all();
+            }
+        }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+            }
+            work();
+        }
+    }
+    static void forget_in_child() { new (&instance()) host_workers(); }          /* fresh mutexes, no threads */
+
+public:
+    static host_workers &instance()
+    {
+        static host_workers *w = [] { host_workers *p = new host_workers(); pthread_atfork(nullptr, nullptr, &host_workers::forget_in_child); return p; }();
+        return *w;
+    }
+    void run(unsigned T, const std::function<void(unsigned)> &f)
+    {
+        if (T <= 1) { f(0u); return; }
+        std::lock_guard<std::mutex> one_at_a_time(run_mu_);
+        while (n_threads_ + 1 < T) { std::thread(&host_workers::loop, this).detach(); ++n_threads_; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &f; n_tasks_ = T; next_task_ = 0; done_tasks_ = 0; ++epoch_;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return done_tasks_ == n_tasks_; });
+        job_ = nullptr;
+    }
+};
 
 struct flat_matrix {
     std::size_t n_rows = 0, nnz = 0;
@@ -81,13 +150,11 @@ class constraint_matrices {
         const unsigned avail = sched_getaffinity(0, sizeof set, &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
         return avail >= 8 ? 8u : (avail ? avail : 1u);
     }
-    /* runs f(t) for t = 0 .. T-1, t = 0 on the calling thread */
+    /* runs f(t) for t = 0 .. T-1 on the process's persistent host workers, the calling thread taking part */
     template<typename Fn> static void on_threads(unsigned T, Fn f)
     {
-        std::vector<std::thread> workers;
-        for (unsigned t = 1; t < T; ++t) workers.emplace_back(f, t);
-        f(0u);
-        for (auto &w : workers) w.join();
+        const std::function<void(unsigned)> job(f);
+        host_workers::instance().run(T, job);
     }
     static const linear_combination<FieldT> &row_of(const r1cs_constraint<FieldT> &c, int m) { return m == 0 ? c.a_ : m == 1 ? c.b_ : c.c_; }
     struct raw_free { void operator()(void *p) const { ::operator delete(p); } };
