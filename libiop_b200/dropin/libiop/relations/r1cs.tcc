@@ -84,4 +84,22 @@ template<> inline void r1cs_constraint_system<FIELD>::create_Az_Bz_Cz_from_varia
 }
 B200_FOR_EACH_FIELD(B200_ABCZ_SPECIALISE)
 #undef B200_ABCZ_SPECIALISE
+
+/* A_matrix / B_matrix / C_matrix (r1cs.tcc:175-236): the row-of-maps form Ligero's interleaved protocol builds three times per
+   proof.  The reference copies every row's term vector before inserting its entries into the map; the specialisations read
+   the terms in place and size the outer vector once.  Same maps. */
+#define B200_NAIVE_MATRIX_SPECIALISE(FIELD, NAME, MEMBER)                                                                  \
+template<> inline naive_sparse_matrix<FIELD> r1cs_constraint_system<FIELD>::NAME() const                                   \
+{                                                                                                                          \
+    naive_sparse_matrix<FIELD> matrix(this->num_constraints());                                                            \
+    for (std::size_t i = 0; i < matrix.size(); ++i)                                                                        \
+        for (const linear_term<FIELD> &term : this->constraints_[i].MEMBER.terms)                                          \
+            matrix[i].insert(std::pair<std::size_t, FIELD>(term.index_, term.coeff_));                                     \
+    return matrix;                                                                                                         \
+}
+#define B200_NAIVE_MATRICES(FIELD) B200_NAIVE_MATRIX_SPECIALISE(FIELD, A_matrix, a_) B200_NAIVE_MATRIX_SPECIALISE(FIELD, B_matrix, b_) \
+                                   B200_NAIVE_MATRIX_SPECIALISE(FIELD, C_matrix, c_)
+B200_FOR_EACH_FIELD(B200_NAIVE_MATRICES)
+#undef B200_NAIVE_MATRICES
+#undef B200_NAIVE_MATRIX_SPECIALISE
 } // namespace libiop

@@ -278,6 +278,49 @@ double b200_prover_ligero_gf192(uint32_t log_n, double height_width_ratio, uint3
     return seconds(t0, t1);
 }
 
+/* The steps of ligero_snark_prover (snark/ligero_snark.tcc:40-72) timed one by one on one generated instance, like
+   b200_prover_aurora_gf192_phases: secs_out[0] ligero_iop construction, [1] register_interactions, [2] register_queries (+ seals),
+   [3] produce_proof, [4] get_transcript, [5] destruction of the protocol objects and oracles.  Diagnostic only. */
+void b200_prover_ligero_gf192_phases(uint32_t log_n, double height_width_ratio, uint32_t rs_extra, uint64_t seed, uint32_t repeats,
+                                     double *secs_out)
+{
+    init_once();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = seeded_example<G>(n, 15, n - 1, seed);
+    ligero_snark_parameters<G, binary_hash_digest> params;
+    params.security_level_ = 128;
+    params.LDT_reducer_soundness_type_ = LDT_reducer_soundness_type::optimistic_heuristic;
+    params.height_width_ratio_ = (float)height_width_ratio;
+    params.RS_extra_dimensions_ = rs_extra;
+    params.make_zk_ = false;
+    params.domain_type_ = affine_subspace_type;
+    params.bcs_params_ = default_bcs_params<G, binary_hash_digest>(blake2b_type, 128, log_n);
+    for (uint32_t r = 0; r < repeats; ++r) {
+        double *out = secs_out + 6 * r;
+        auto t0 = std::chrono::steady_clock::now();
+        const auto lap = [&t0]() { const auto t1 = std::chrono::steady_clock::now(); const double s = seconds(t0, t1); t0 = t1; return s; };
+        {
+            const ligero_iop_parameters<G> iop_params = obtain_iop_parameters_from_ligero_snark_params<G>(
+                params, ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+            bcs_prover<G, binary_hash_digest> IOP(params.bcs_params_);
+            ligero_iop<G> full_protocol(IOP, ex.constraint_system_, iop_params);
+            out[0] = lap();
+            full_protocol.register_interactions();
+            IOP.seal_interaction_registrations();
+            out[1] = lap();
+            full_protocol.register_queries();
+            IOP.seal_query_registrations();
+            out[2] = lap();
+            full_protocol.produce_proof(ex.primary_input_, ex.auxiliary_input_);
+            out[3] = lap();
+            const ligero_snark_argument<G, binary_hash_digest> transcript = IOP.get_transcript();
+            out[4] = lap();
+        }
+        out[5] = lap();
+    }
+}
+
 /* device-side counters of the adapter's context: kernels launched, bytes uploaded / downloaded so far */
 void b200_prover_device_stats(uint64_t *launches, uint64_t *h2d_bytes, uint64_t *d2h_bytes)
 {

@@ -75,6 +75,14 @@ class DropinProver:
                          (C.c_uint32(log_n), C.c_double(ratio), C.c_uint32(rs_extra), C.c_int(1 if make_zk else 0), C.c_uint64(seed),
                           C.c_int(1 if verify else 0)))
 
+    def ligero_gf192_phases(self, log_n, repeats, ratio=0.1, rs_extra=2, seed=DEFAULT_SEED):
+        """per proof: seconds of [ligero_iop construction, register_interactions, register_queries, produce_proof, get_transcript,
+        destruction] (diagnostic)"""
+        secs = (C.c_double * (6 * repeats))()
+        self.lib.b200_prover_ligero_gf192_phases(C.c_uint32(log_n), C.c_double(ratio), C.c_uint32(rs_extra), C.c_uint64(seed),
+                                                 C.c_uint32(repeats), secs)
+        return [list(secs[6 * r:6 * r + 6]) for r in range(repeats)]
+
     def arena_stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.lib.b200_prover_arena_stats(C.byref(a), C.byref(b), C.byref(c))
