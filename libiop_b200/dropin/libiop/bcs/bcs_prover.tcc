@@ -64,8 +64,16 @@ template<> inline bcs_transformation_transcript<FIELD, binary_hash_digest> bcs_p
             throw std::invalid_argument("evaluation position is outside of domain");                                       \
         read_at[oracle_id].push_back(position);                                                                            \
     };                                                                                                                     \
+    /* a position handle is shared by many queries (Ligero: ~10^3 oracles per position): obtained once each, in first-use    \
+       order, i.e. exactly when the reference's loop obtains it first */                                                     \
+    std::vector<std::vector<std::size_t>> known_position(2);                                                               \
+    const std::size_t unknown = ~std::size_t(0);                                                                           \
     for (std::size_t q = 0; q < this->query_registrations_.size(); ++q) {                                                  \
-        const std::size_t position = this->obtain_query_position(this->query_registrations_[q].query_position());          \
+        const query_position_handle handle = this->query_registrations_[q].query_position();                              \
+        std::vector<std::size_t> &memo = known_position[handle.type() == random_query_type ? 0 : 1];                       \
+        if (memo.size() <= handle.id()) memo.resize(handle.id() + 1, unknown);                                             \
+        if (memo[handle.id()] == unknown) memo[handle.id()] = this->obtain_query_position(handle);                         \
+        const std::size_t position = memo[handle.id()];                                                                    \
         const oracle_handle_ptr top = this->query_registrations_[q].oracle();                                              \
         if (dynamic_cast<const oracle_handle *>(top.get())) { record(top->id(), position); continue; }                     \
         if (!dynamic_cast<const virtual_oracle_handle *>(top.get())) throw std::invalid_argument("oracle type not supported"); \
@@ -96,8 +104,12 @@ template<> inline bcs_transformation_transcript<FIELD, binary_hash_digest> bcs_p
             const std::size_t num_leaves = this->domains_[kv.first.id()].num_elements() / round_params.quotient_map_size_; \
             std::vector<std::size_t> query_positions;                                                                      \
             std::vector<std::shared_ptr<std::vector<FIELD>>> contents;                                                     \
+            const std::vector<std::size_t> *previous = nullptr;                                                            \
             for (auto &oracle_h : kv.second) {                                                                             \
-                query_positions.insert(query_positions.end(), read_at[oracle_h.id()].begin(), read_at[oracle_h.id()].end()); \
+                const std::vector<std::size_t> &mine = read_at[oracle_h.id()];                                             \
+                if (!previous || mine != *previous)          /* oracles read by the same queries bring nothing new */       \
+                    query_positions.insert(query_positions.end(), mine.begin(), mine.end());                               \
+                previous = &mine;                                                                                          \
                 contents.emplace_back(this->oracles_[oracle_h.id()].evaluated_contents());                                 \
             }                                                                                                              \
             std::sort(query_positions.begin(), query_positions.end());                                                     \
