@@ -117,6 +117,27 @@ def test_device_matrix_paths_at_other_parameters_against_the_cpu_reference(sim):
     assert got_f[2] == 1 and bytes(got_f[1]) == bytes(want_f[1])
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_matrix_flattening_on_host_workers(sim, threads):
+    """The R1CS matrices are flattened by a few persistent host threads (b200_constraint_matrices.hpp: host_workers).  The
+    split of the rows over the workers must not show in the result: the same Aurora N = 2^14 proof (the smallest size served
+    from the device matrices) with 1, 3 and 8 workers, twice each, against the committed fingerprint."""
+    want = [c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "prover_fingerprints_extra.json")))
+            if c["prover"] == "aurora_gf192" and c["log_n"] == 14 and not c["zk"]][0]
+    saved = os.environ.get("B200_HOST_THREADS")
+    os.environ["B200_HOST_THREADS"] = threads
+    try:
+        for _ in range(2):
+            with quiet_stdout():
+                _, dump, acc = sim.aurora_gf192(14, make_zk=False)
+            assert acc == 1 and (len(dump), hashlib.sha256(dump).hexdigest()) == (want["bytes"], want["sha256"])
+    finally:
+        if saved is None:
+            os.environ.pop("B200_HOST_THREADS", None)
+        else:
+            os.environ["B200_HOST_THREADS"] = saved
+
+
 def test_provers_do_not_read_device_resident_vectors_on_the_host(sim):
     """Oracles the adapter produces stay on the device behind lazy host vectors; a host read is served correctly by the fault
     handler but costs a whole-vector download.  None of the provers may take that path (the same check runs on the GPU box in
