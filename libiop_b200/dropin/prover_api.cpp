@@ -140,6 +140,30 @@ double b200_prover_aurora_gf192(uint32_t log_n, uint32_t k_inputs, int make_zk, 
     return seconds(t0, t1);
 }
 
+/* the same with the number of variables chosen freely (generate_r1cs_example<gf192>(2^log_n, k, num_variables)): variable
+   counts that are not a power of two minus one, variable domains larger or smaller than the constraint domain */
+double b200_prover_aurora_gf192_shape(uint32_t log_n, uint32_t k_inputs, uint64_t num_variables, int make_zk, uint32_t rs_extra,
+                                      uint32_t fri_loc, uint64_t seed, int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)
+{
+    init_once();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, (size_t)num_variables);
+    aurora_snark_parameters<G, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
+        blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    arm_proof_randomness(make_zk != 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
+        ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+    const auto t1 = std::chrono::steady_clock::now();
+    emit(proof, buf, cap, len);
+    if (accepted)
+        *accepted = verify ? (aurora_snark_verifier<G, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, proof, params) ? 1 : 0) : -1;
+    return seconds(t0, t1);
+}
+
 /* The same prover call `repeats` times on ONE generated instance (instance generation costs more than the proof at
    N = 2^20); secs_out[repeats].  Used for throughput measurements with several prover processes per GPU. */
 void b200_prover_aurora_gf192_repeat(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,

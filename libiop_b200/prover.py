@@ -21,7 +21,8 @@ class DropinProver:
         if not os.path.exists(lib_path):
             raise RuntimeError(f"{lib_path} is missing: `make -C libiop_b200/dropin` (needs the reference checkout at build time)")
         self.lib = C.CDLL(lib_path)
-        for fn in ("b200_prover_aurora_gf192", "b200_prover_aurora_edwards", "b200_prover_fractal_edwards", "b200_prover_ligero_gf192"):
+        for fn in ("b200_prover_aurora_gf192", "b200_prover_aurora_gf192_shape", "b200_prover_aurora_edwards", "b200_prover_fractal_edwards",
+                   "b200_prover_ligero_gf192"):
             getattr(self.lib, fn).restype = C.c_double
 
     def seed(self, s):
@@ -40,6 +41,12 @@ class DropinProver:
         return self._run(self.lib.b200_prover_aurora_gf192,
                          (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_int(1 if make_zk else 0), C.c_uint32(rs_extra), C.c_uint32(fri_loc),
                           C.c_uint64(seed), C.c_int(1 if verify else 0)))
+
+    def aurora_gf192_shape(self, log_n, num_variables, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED, verify=True):
+        """2^log_n constraints over `num_variables` variables (any count >= k_inputs)"""
+        return self._run(self.lib.b200_prover_aurora_gf192_shape,
+                         (C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_uint64(num_variables), C.c_int(1 if make_zk else 0), C.c_uint32(rs_extra),
+                          C.c_uint32(fri_loc), C.c_uint64(seed), C.c_int(1 if verify else 0)))
 
     def aurora_gf192_repeat(self, log_n, repeats, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=DEFAULT_SEED):
         """prover seconds of `repeats` proofs of one generated instance (instance generation excluded)"""

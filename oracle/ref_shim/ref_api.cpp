@@ -320,6 +320,35 @@ double REFN(aurora_gf192)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+/* the same with the number of variables chosen freely: generate_r1cs_example<gf192>(2^log_n, k, num_variables) — variable
+   counts that are not a power of two minus one, variable domains larger or smaller than the constraint domain */
+double REFN(aurora_gf192_shape)(uint32_t log_n, uint32_t k_inputs, uint64_t num_variables, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
+                              uint64_t seed, int verify, uint8_t *buf, size_t cap, size_t *len, int *accepted)
+{
+    REFN(init)();
+    b200_shim_randombytes_seed(seed);
+    const size_t n = (size_t)1 << log_n;
+    r1cs_example<G> ex = generate_r1cs_example<G>(n, k_inputs, (size_t)num_variables);
+    aurora_snark_parameters<G, binary_hash_digest> params(
+        128, LDT_reducer_soundness_type::optimistic_heuristic, FRI_soundness_type::heuristic,
+        blake2b_type, (size_t)fri_loc, (size_t)rs_extra, make_zk != 0, affine_subspace_type,
+        ex.constraint_system_.num_constraints(), ex.constraint_system_.num_variables());
+    const auto t0 = std::chrono::steady_clock::now();
+    const aurora_snark_argument<G, binary_hash_digest> proof = aurora_snark_prover<G, binary_hash_digest>(
+        ex.constraint_system_, ex.primary_input_, ex.auxiliary_input_, params);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::vector<uint8_t> o;
+    dump_transcript(o, proof);
+    if (len) *len = o.size();
+    if (buf && o.size() <= cap) std::memcpy(buf, o.data(), o.size());
+    if (accepted) {
+        *accepted = -1;
+        if (verify)
+            *accepted = aurora_snark_verifier<G, binary_hash_digest>(ex.constraint_system_, ex.primary_input_, proof, params) ? 1 : 0;
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 /* the same prover call `repeats` times on one generated instance (throughput measurements, bench/e2e_throughput.py) */
 void REFN(aurora_gf192_repeat)(uint32_t log_n, uint32_t k_inputs, int make_zk, uint32_t rs_extra, uint32_t fri_loc,
                                uint64_t seed, uint32_t repeats, double *secs_out)

@@ -247,7 +247,7 @@ class Reference:
         self.lib = _Renamed()
         self._real = real
         self.lib.ref_init()
-        for fn in ("ref_aurora_gf192", "ref_aurora_edwards", "ref_fractal_edwards", "ref_ligero_gf192"):
+        for fn in ("ref_aurora_gf192", "ref_aurora_gf192_shape", "ref_aurora_edwards", "ref_fractal_edwards", "ref_ligero_gf192"):
             getattr(self.lib, fn).restype = C.c_double
 
     def seed(self, s):
@@ -377,6 +377,16 @@ class Reference:
                                          C.c_uint32(rs_extra), C.c_uint32(fri_loc), C.c_uint64(seed),
                                          C.c_int(int(verify)), _b(buf), C.c_size_t(cap),
                                          C.byref(ln), C.byref(acc))
+        return secs, buf[:ln.value].tobytes(), acc.value
+
+    def aurora_gf192_shape(self, log_n, num_variables, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2,
+                           seed=0x9E3779B97F4A7C15, verify=True, cap=1 << 26):
+        """2^log_n constraints over `num_variables` variables (generate_r1cs_example with a free variable count)"""
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(); acc = C.c_int()
+        secs = self.lib.ref_aurora_gf192_shape(C.c_uint32(log_n), C.c_uint32(k_inputs), C.c_uint64(num_variables), C.c_int(int(make_zk)),
+                                               C.c_uint32(rs_extra), C.c_uint32(fri_loc), C.c_uint64(seed),
+                                               C.c_int(int(verify)), _b(buf), C.c_size_t(cap), C.byref(ln), C.byref(acc))
         return secs, buf[:ln.value].tobytes(), acc.value
 
     def aurora_gf192_repeat(self, log_n, repeats, k_inputs=31, make_zk=False, rs_extra=3, fri_loc=2, seed=0x9E3779B97F4A7C15):

@@ -100,6 +100,25 @@ def test_aurora_parameter_variations_against_the_cpu_reference(sim, field, log_n
     assert bytes(got[1]) == bytes(want[1])
 
 
+@pytest.mark.parametrize("log_n,num_variables,k_inputs,zk", [(12, 8191, 31, False), (12, 2047, 7, False), (13, 4095, 3, True),
+                                                             (14, 32767, 31, False), (14, 8191, 31, False)])
+def test_aurora_with_unequal_constraint_and_variable_domains(sim, log_n, num_variables, k_inputs, zk):
+    """Constraint systems whose variable domain is larger or smaller than the constraint domain (the summation domain is the
+    larger of the two: placement strides, sizes of z and of the matrices' columns all differ from the square case), against
+    the unmodified CPU reference compiled here; at 2^14 constraints the device-matrix paths run."""
+    from oracle_lib import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libiopref.so not built (needs the reference checkout)")
+    ref = Reference()
+    before = sim.lazy_stats()["faults"]
+    with quiet_stdout():
+        want = ref.aurora_gf192_shape(log_n, num_variables, k_inputs=k_inputs, make_zk=zk)
+        got = sim.aurora_gf192_shape(log_n, num_variables, k_inputs=k_inputs, make_zk=zk)
+    assert want[2] == 1 and got[2] == 1
+    assert bytes(got[1]) == bytes(want[1])
+    assert sim.lazy_stats()["faults"] == before
+
+
 def test_device_matrix_paths_at_other_parameters_against_the_cpu_reference(sim):
     """N = 2^14 is the smallest size at which the constraint matrices are served from the device (pipelined A z / B z / C z
     extensions, transposed products, index oracles): Aurora with 3 inputs at rate 1/4, localization 3, and Fractal at rate 1/4,
