@@ -119,6 +119,22 @@ def test_aurora_with_unequal_constraint_and_variable_domains(sim, log_n, num_var
     assert sim.lazy_stats()["faults"] == before
 
 
+def test_ligero_and_fractal_parameter_variations_against_the_cpu_reference(sim):
+    """Other height/width ratios, rates and FRI localizations than the committed fingerprints (Ligero incl. zero knowledge)."""
+    from oracle_lib import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libiopref.so not built (needs the reference checkout)")
+    ref = Reference()
+    with quiet_stdout():
+        pairs = [(ref.ligero_gf192(13, ratio=0.05, rs_extra=3), sim.ligero_gf192(13, ratio=0.05, rs_extra=3)),
+                 (ref.ligero_gf192(12, ratio=0.2, rs_extra=2, make_zk=True), sim.ligero_gf192(12, ratio=0.2, rs_extra=2, make_zk=True)),
+                 (ref.ligero_gf192(12, ratio=1.0, rs_extra=2), sim.ligero_gf192(12, ratio=1.0, rs_extra=2)),
+                 (ref.fractal_edwards(12, rs_extra=2, fri_loc=1)[:3], sim.fractal_edwards(12, rs_extra=2, fri_loc=1)[:3]),
+                 (ref.fractal_edwards(13, rs_extra=3, fri_loc=3)[:3], sim.fractal_edwards(13, rs_extra=3, fri_loc=3)[:3])]
+    for want, got in pairs:
+        assert got[2] == 1 and bytes(got[1]) == bytes(want[1])
+
+
 def test_device_matrix_paths_at_other_parameters_against_the_cpu_reference(sim):
     """N = 2^14 is the smallest size at which the constraint matrices are served from the device (pipelined A z / B z / C z
     extensions, transposed products, index oracles): Aurora with 3 inputs at rate 1/4, localization 3, and Fractal at rate 1/4,
